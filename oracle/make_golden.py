@@ -1,0 +1,180 @@
+"""Mint golden vectors by RUNNING THE REFERENCE (build container only).
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+Imports the reference's own modules from /root/reference (read-only; nothing is
+copied) and records inputs + outputs of
+
+    utils.matching.matching_templates / matching_features_similarity
+    utils.corr_lookup.CorrLookup / bilinear_sample / coords_grid
+    utils.correspondence.compute_init_correspondences / compute_stage3_correspondences
+    model.stage3.raft_decoder.CorrelationPyramid   (through a stub mmcv.cnn.ConvModule)
+
+on seeded synthetic inputs (picopose_b200/synth.py).  /root/reference does not
+exist on the GPU box, so tests only ever read the committed .npz files.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("PICOPOSE_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+
+def _import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit(f"reference tree not found at {REF}")
+    sys.path.insert(0, REF)
+    # CorrelationPyramid's module imports mmcv.cnn.ConvModule (not installed);
+    # it carries no arithmetic of this path, a stub is enough to import the file.
+    mmcv = types.ModuleType("mmcv")
+    cnn = types.ModuleType("mmcv.cnn")
+
+    class ConvModule(torch.nn.Module):  # pragma: no cover - never instantiated here
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    cnn.ConvModule = ConvModule
+    mmcv.cnn = cnn
+    sys.modules.setdefault("mmcv", mmcv)
+    sys.modules.setdefault("mmcv.cnn", cnn)
+    warnings.filterwarnings("ignore")
+    import utils.matching as ref_matching
+    import utils.corr_lookup as ref_lookup
+    import utils.correspondence as ref_corresp
+    from model.stage3.raft_decoder import CorrelationPyramid
+    return ref_matching, ref_lookup, ref_corresp, CorrelationPyramid
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def main():
+    from picopose_b200 import synth
+
+    ref_matching, ref_lookup, ref_corresp, CorrelationPyramid = _import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # ---------------- stage-1 matching ----------------
+    def match_case(name, B, N, C, H, k, seed, mask="disc", special=None):
+        src, tar, planted = synth.planted_match_inputs(B, N, C, H, seed=seed)
+        if mask == "disc":
+            m = synth.disc_mask(B)
+        elif mask == "bern":
+            m = synth.bernoulli_mask(B, 224, 0.7, seed + 100)
+        elif mask == "ones":
+            m = torch.ones(B, 224, 224)
+        elif mask == "zeros":
+            m = torch.zeros(B, 224, 224)
+        if special == "identical":          # query == template 0 exactly
+            tar = src[:, 0].clone()
+        src_masks = torch.ones(B, N, 224, 224)[:, :, :1, :1]  # unused by the reference
+        score, idx = ref_matching.matching_templates(src.clone(), tar.clone(), src_masks, m.clone(), topk=k)
+        # also the dense per-template scores (k = N) for a sharper check
+        score_all, idx_all = ref_matching.matching_templates(src.clone(), tar.clone(), src_masks, m.clone(), topk=N)
+        sim_avg = torch.zeros(B, N)
+        sim_avg.scatter_(1, idx_all, score_all)
+        np.savez_compressed(os.path.join(OUT, f"match_{name}.npz"),
+                            src=_np(src), tar=_np(tar), mask=_np(m).astype(np.uint8), topk=k,
+                            score=_np(score), idx=_np(idx), sim_avg=_np(sim_avg), planted=_np(planted))
+        print(f"match_{name}: top-{k} idx {idx.tolist()}")
+
+    match_case("small", 2, 7, 16, 4, 3, seed=0)
+    match_case("medium", 1, 12, 64, 8, 5, seed=1)
+    match_case("bern", 2, 9, 32, 8, 5, seed=2, mask="bern")
+    match_case("ones", 1, 6, 16, 4, 5, seed=3, mask="ones")
+    match_case("allmasked", 1, 6, 16, 4, 2, seed=4, mask="zeros")
+    match_case("identical", 1, 6, 16, 4, 2, seed=5, mask="ones", special="identical")
+
+    # ---------------- stage-2 similarity volume ----------------
+    for name, B, C, H, seed in (("small", 2, 16, 4, 10), ("medium", 1, 32, 8, 11)):
+        g = torch.Generator().manual_seed(seed)
+        src = torch.randn(B, C, H, H, generator=g)
+        tar = torch.randn(B, C, H, H, generator=g)
+        sm = synth.bernoulli_mask(B, 224, 0.7, seed + 1)
+        tm = torch.ones(B, 224, 224)
+        out = ref_matching.matching_features_similarity(src.clone(), tar.clone(), sm.clone(), tm)
+        np.savez_compressed(os.path.join(OUT, f"sim_{name}.npz"), src=_np(src), tar=_np(tar),
+                            src_mask=_np(sm).astype(np.uint8), out=_np(out))
+        print(f"sim_{name}: out {tuple(out.shape)}")
+
+    # ---------------- stage-3 lookup ----------------
+    def lookup_case(name, B, H, L, r, seed, sigma, W=None, ramp=False, zero_flow=False):
+        pyr, flow = synth.lookup_inputs(B, H, L, seed=seed, flow_sigma=sigma, W=W)
+        if ramp:                     # KAT: volume value == x coordinate
+            Wv = pyr[0].shape[-1]
+            pyr = [torch.arange(Wv, dtype=torch.float32).view(1, 1, 1, Wv).expand_as(pyr[0]).contiguous()]
+        if zero_flow:
+            flow = torch.zeros_like(flow)
+        mod = ref_lookup.CorrLookup(radius=r)
+        out = mod([p.clone() for p in pyr], flow.clone())
+        d = {f"pyr{i}": _np(p) for i, p in enumerate(pyr)}
+        np.savez_compressed(os.path.join(OUT, f"lookup_{name}.npz"), flow=_np(flow), out=_np(out),
+                            radius=r, levels=L, **d)
+        print(f"lookup_{name}: out {tuple(out.shape)}")
+
+    lookup_case("small", 2, 6, 2, 2, seed=20, sigma=2.0)
+    lookup_case("ramp", 1, 8, 1, 1, seed=21, sigma=0.0, ramp=True, zero_flow=True)
+    lookup_case("ladder", 1, 16, 3, 4, seed=22, sigma=4.0)
+    lookup_case("rect", 1, 8, 2, 3, seed=23, sigma=3.0, W=12)
+    lookup_case("intflow", 1, 8, 1, 2, seed=24, sigma=0.0, zero_flow=True)
+
+    # generic bilinear_sample (FlowDecoder.feature_sample uses align_corners=True)
+    g = torch.Generator().manual_seed(30)
+    feat = torch.randn(2, 3, 5, 7, generator=g)
+    grid = torch.stack([torch.rand(2, 4, 6, generator=g) * 9 - 1, torch.rand(2, 4, 6, generator=g) * 7 - 1], dim=-1)
+    out_t = ref_lookup.bilinear_sample(feat, grid.clone(), align_corners=True)
+    out_f = ref_lookup.bilinear_sample(feat, grid.clone(), align_corners=False)
+    cg = ref_lookup.coords_grid(2, torch.arange(0, 7), torch.arange(0, 5))
+    np.savez_compressed(os.path.join(OUT, "bilinear.npz"), feat=_np(feat), grid=_np(grid),
+                        out_true=_np(out_t), out_false=_np(out_f), coords=_np(cg))
+
+    # correlation pyramid
+    g = torch.Generator().manual_seed(40)
+    f1 = torch.randn(2, 8, 8, 8, generator=g)
+    f2 = torch.randn(2, 8, 8, 8, generator=g)
+    pyr = CorrelationPyramid(num_levels=3)(f1, f2)
+    np.savez_compressed(os.path.join(OUT, "pyramid.npz"), f1=_np(f1), f2=_np(f2),
+                        **{f"lvl{i}": _np(p) for i, p in enumerate(pyr)})
+
+    # ---------------- correspondence glue ----------------
+    B = 4
+    Ms = synth.random_affines(B, seed=50)
+    Ms[0] = torch.eye(3)
+    Ms[1] = torch.eye(3)
+    Ms[1, 0, 2] = 28.0
+    tm = synth.bernoulli_mask(B, 224, 0.8, 51)
+    tm[0] = 1.0
+    tm[1] = 1.0
+    flow0, cert0 = ref_corresp.compute_init_correspondences(Ms.clone(), tm.clone())
+    np.savez_compressed(os.path.join(OUT, "corresp_init.npz"), Ms=_np(Ms), mask=_np(tm).astype(np.uint8),
+                        flow=_np(flow0), cert=_np(cert0))
+
+    flow = torch.zeros(1, 2, 4, 4)
+    flow[:, 0] = 0.6
+    flow[:, 1] = -0.4
+    cert = torch.full((1, 1, 4, 4), 3.0)
+    cert[0, 0, 1, 2] = -3.0      # (h=1, w=2) -> flat k = w*H + h = 9
+    tar, src = ref_corresp.compute_stage3_correspondences(flow.clone(), cert.clone())
+    g = torch.Generator().manual_seed(52)
+    flow_r = 3.0 * torch.randn(3, 2, 16, 16, generator=g)
+    cert_r = 2.0 * torch.randn(3, 1, 16, 16, generator=g)
+    tar_r, src_r = ref_corresp.compute_stage3_correspondences(flow_r.clone(), cert_r.clone())
+    np.savez_compressed(os.path.join(OUT, "corresp_stage3.npz"), flow=_np(flow), cert=_np(cert),
+                        tar=_np(tar), src=_np(src), flow_r=_np(flow_r), cert_r=_np(cert_r),
+                        tar_r=_np(tar_r), src_r=_np(src_r))
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

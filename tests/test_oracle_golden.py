@@ -1,0 +1,134 @@
+"""Pin the oracle: replay the reference's own outputs (tests/golden/*.npz, minted by
+oracle/make_golden.py from /root/reference) through oracle/*.py.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import correspondence_oracle as OC
+from oracle import corr_lookup_oracle as OL
+from oracle import matching_oracle as OM
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+MATCH = ["small", "medium", "bern", "ones", "allmasked", "identical"]
+
+
+@pytest.mark.parametrize("name", MATCH)
+def test_matching_templates_matches_reference(name):
+    g = load(f"match_{name}.npz")
+    src, tar = torch.from_numpy(g["src"]), torch.from_numpy(g["tar"])
+    mask = torch.from_numpy(g["mask"]).float()
+    k = int(g["topk"])
+    sim_avg = OM.template_scores(src, tar, mask)
+    np.testing.assert_allclose(sim_avg.numpy(), g["sim_avg"], rtol=0, atol=2e-6)
+    score, idx = OM.matching_templates(src, tar, None, mask, topk=k)
+    np.testing.assert_allclose(score.numpy(), g["score"], rtol=0, atol=2e-6)
+    if name != "allmasked":                      # all-zero scores: topk tie order is unspecified
+        np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    assert idx.dtype == torch.int64 and score.dtype == torch.float32
+
+
+@pytest.mark.parametrize("name", ["small", "ones", "allmasked", "identical"])
+def test_matching_loops_agree(name):
+    g = load(f"match_{name}.npz")
+    out = OM.template_scores_loops(g["src"], g["tar"], g["mask"].astype(np.float32))
+    np.testing.assert_allclose(out, g["sim_avg"], rtol=0, atol=3e-6)
+
+
+def test_matching_kats():
+    g = load("match_allmasked.npz")
+    assert np.all(g["sim_avg"] == 0.0)                     # all-masked query scores exactly 0
+    g = load("match_identical.npz")
+    # identical query/template 0, full mask: every patch but index 0 is its own best match
+    T = g["src"].shape[-1] ** 2
+    H = g["src"].shape[-1]
+    np.testing.assert_allclose(g["sim_avg"][0, 0], (T - 1) / float(H * H), atol=1e-5)
+    g = load("match_medium.npz")
+    np.testing.assert_array_equal(g["idx"][0], g["planted"][0][:5])  # planted ranking recovered
+
+
+@pytest.mark.parametrize("name", ["small", "medium"])
+def test_similarity_volume(name):
+    g = load(f"sim_{name}.npz")
+    src, tar = torch.from_numpy(g["src"]), torch.from_numpy(g["tar"])
+    sm = torch.from_numpy(g["src_mask"]).float()
+    out = OM.similarity_volume(src, tar, sm)
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=2e-6)
+    if name == "small":
+        np.testing.assert_allclose(OM.similarity_volume_loops(g["src"], g["tar"], g["src_mask"]), g["out"], atol=3e-6)
+
+
+LOOKUP = ["small", "ramp", "ladder", "rect", "intflow"]
+
+
+@pytest.mark.parametrize("name", LOOKUP)
+def test_corr_lookup(name):
+    g = load(f"lookup_{name}.npz")
+    L, r = int(g["levels"]), int(g["radius"])
+    pyr = [torch.from_numpy(g[f"pyr{i}"]) for i in range(L)]
+    flow = torch.from_numpy(g["flow"])
+    out = OL.corr_lookup(pyr, flow, r)
+    assert out.shape == g["out"].shape
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("name", ["small", "ramp", "intflow"])
+def test_corr_lookup_loops(name):
+    g = load(f"lookup_{name}.npz")
+    L, r = int(g["levels"]), int(g["radius"])
+    out = OL.corr_lookup_loops([g[f"pyr{i}"] for i in range(L)], g["flow"], r)
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=5e-6)
+
+
+def test_corr_lookup_ramp_kat():
+    g = load("lookup_ramp.npz")
+    # x-ramp volume, zero flow, r=1: window is x-major -> channels [3,3,3,4,4,4,5,5,5] at (4,4)
+    np.testing.assert_allclose(g["out"][0, :, 4, 4], [3, 3, 3, 4, 4, 4, 5, 5, 5], atol=1e-5)
+
+
+def test_bilinear_and_grid():
+    g = load("bilinear.npz")
+    feat, grid = torch.from_numpy(g["feat"]), torch.from_numpy(g["grid"])
+    np.testing.assert_allclose(OL.bilinear_sample(feat, grid.clone(), True).numpy(), g["out_true"], atol=3e-6)
+    np.testing.assert_allclose(OL.bilinear_sample(feat, grid.clone(), False).numpy(), g["out_false"], atol=3e-6)
+    np.testing.assert_array_equal(OL.coords_grid(2, 7, 5).numpy(), g["coords"])
+
+
+def test_correlation_pyramid():
+    g = load("pyramid.npz")
+    pyr = OL.correlation_pyramid(torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"]), 3)
+    for i, p in enumerate(pyr):
+        np.testing.assert_allclose(p.numpy(), g[f"lvl{i}"], atol=2e-6)
+
+
+def test_init_correspondences():
+    g = load("corresp_init.npz")
+    flow, cert = OC.init_correspondences(torch.from_numpy(g["Ms"]), torch.from_numpy(g["mask"]).float())
+    np.testing.assert_allclose(flow.numpy(), g["flow"], atol=2e-5)
+    np.testing.assert_array_equal(cert.numpy(), g["cert"])
+    np.testing.assert_allclose(g["flow"][0], 0.5, atol=1e-6)          # identity: half-patch offset
+    np.testing.assert_allclose(g["flow"][1, 0], 2.5, atol=1e-6)       # +28 px in x = +2 patches
+    np.testing.assert_allclose(g["flow"][1, 1], 0.5, atol=1e-6)
+
+
+def test_stage3_correspondences():
+    g = load("corresp_stage3.npz")
+    tar, src = OC.stage3_correspondences(torch.from_numpy(g["flow"]), torch.from_numpy(g["cert"]))
+    np.testing.assert_array_equal(tar.numpy(), g["tar"])
+    np.testing.assert_array_equal(src.numpy(), g["src"])
+    assert tar.dtype == torch.int64
+    # KAT from SURVEY 8(c): k = w*H + h ; k=1 -> src (0,1), tar (0,0); k in {0,4,8,9,12..15} -> -1
+    np.testing.assert_array_equal(g["src"][0, 1], [0, 1])
+    np.testing.assert_array_equal(g["tar"][0, 1], [0, 0])
+    for k in (0, 4, 8, 9, 12, 13, 14, 15):
+        np.testing.assert_array_equal(g["src"][0, k], [-1, -1])
+    tar, src = OC.stage3_correspondences(torch.from_numpy(g["flow_r"]), torch.from_numpy(g["cert_r"]))
+    np.testing.assert_array_equal(tar.numpy(), g["tar_r"])
+    np.testing.assert_array_equal(src.numpy(), g["src_r"])
