@@ -1,0 +1,138 @@
+/*
+ * picopose_b200 -- C ABI of the B200-native PicoPose correspondence hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes,
+ * no torch types.  Every pointer is a DEVICE pointer owned by the caller
+ * (PyTorch allocates, the library never allocates, frees or retains memory);
+ * `stream` is a cudaStream_t passed as void*; all work is enqueued
+ * asynchronously on it.  Return value: 0 on success, negative pp_status on
+ * error with a message in pp_last_error().  There is no CPU fallback: calls
+ * fail with PP_ERR_DEVICE on anything but an sm_100 device.
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to the PicoPose repository).
+ */
+#ifndef PICOPOSE_B200_H
+#define PICOPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define PP_API __attribute__((visibility("default")))
+#else
+#define PP_API
+#endif
+
+typedef enum pp_status {
+    PP_OK = 0,
+    PP_ERR_ARG = -1,       /* bad shape / null pointer / unsupported option (mirrors the reference's asserts) */
+    PP_ERR_ALIGN = -2,     /* pointer or stride not aligned as required */
+    PP_ERR_WORKSPACE = -3, /* caller-provided workspace too small */
+    PP_ERR_DEVICE = -4,    /* not an sm_100 device / driver entry point missing */
+    PP_ERR_LAUNCH = -5,    /* CUDA launch or API failure */
+    PP_ERR_KERNEL = -6     /* a kernel reported an internal fault (pipeline timeout) */
+} pp_status;
+
+/* arithmetic mode of the stage-1 contraction */
+typedef enum pp_mode {
+    PP_MODE_BF16 = 0,   /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)                 */
+    PP_MODE_FP32 = 1,   /* fp32-accurate: 3-way bf16 split, 6 cross terms on the same tensor path */
+    PP_MODE_BF16X3 = 2  /* 2-way bf16 split, 3 cross terms (~1e-6 abs error)                   */
+} pp_mode;
+
+PP_API int pp_version(void);
+PP_API const char* pp_last_error(void);
+/* Reads and clears the device-side fault flag (synchronises the device). 0 = no fault. */
+PP_API int pp_check_device_faults(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 3 -- correlation-window lookup.
+ * Replaces CorrLookup.forward, utils/corr_lookup.py:100-134 (called from
+ * model/stage3/flow_decoder.py:61).
+ *   pyr_ptrs[l] : level-l volume, (B*H*W, 1, pyr_h[l], pyr_w[l]) fp32 contiguous   (HOST array of DEVICE ptrs)
+ *   flow        : (B, 2, H, W) fp32, channel 0 = x, 1 = y
+ *   out         : (B, L*(2r+1)^2, H, W) fp32; channel l*D*D + a*D + b samples (x/2^l + a-r, y/2^l + b-r),
+ *                 bilinear, zero padding, align_corners=True arithmetic of F.grid_sample.
+ * ------------------------------------------------------------------------------------------ */
+PP_API int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, const int* pyr_w, int L,
+                   const float* flow, int B, int H, int W, int radius,
+                   float* out, void* stream);
+
+/* Replaces bilinear_sample, utils/corr_lookup.py:29-65 (mode='bilinear', padding_mode='zeros');
+ * used by FlowDecoder.feature_sample, model/stage3/flow_decoder.py:49-56.
+ *   feat (N,C,Hf,Wf) fp32; grid (N,Ho,Wo,2) if grid_chw == 0 else (N,2,Ho,Wo); out (N,C,Ho,Wo).
+ *   scale != 0: grid holds pixel coordinates and is normalised as the reference does
+ *   (the caller's grid is NOT modified, unlike the reference's in-place scaling). */
+PP_API int pp_bilinear_sample(const float* feat, const float* grid, int N, int C, int Hf, int Wf,
+                       int Ho, int Wo, int grid_chw, int align_corners, int scale,
+                       float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1 -- query-vs-template matching.
+ *
+ * Operand preparation ("prologue"): L2-normalise over C (eps 1e-12, F.normalize), cast to
+ * bf16 (split into terms for the fp32 modes) and lay out K-major for the tensor cores.
+ *   feats : (G, C, P) fp32, P = H*W contiguous      -> prepared : (G, P, Kp) bf16,
+ *   Kp = pp_match_kp(C, mode).  is_query selects which side of the split-term pairing is written.
+ * Replaces the F.normalize + rearrange lines utils/matching.py:13-14,18-19,40-41,43-44.
+ * ------------------------------------------------------------------------------------------ */
+PP_API int pp_match_kp(int C, int mode);
+PP_API int pp_match_prepare(const float* feats, int64_t G, int C, int P, int mode, int is_query,
+                     void* prepared, void* stream);
+
+/* Bytes of scratch pp_match_scores needs for (B detections, N views, T = H*W patches). */
+PP_API size_t pp_match_scores_workspace(int B, int N, int T);
+
+/* Fused similarity GEMM + bidirectional max/argmax + validity-masked mean.
+ * Replaces utils/matching.py:38-39,47-67 (the sim tensor never reaches HBM).
+ *   q_prep    : (B, T, Kp) bf16   prepared query features
+ *   bank_prep : (n_banks, N, T, Kp) bf16 prepared template banks
+ *   bank_of_det : (B,) int32 device array, bank used by detection b; NULL = identity (n_banks == B)
+ *   tar_mask  : (B, Hm, Wm) fp32 0/1 query masks (nearest-resized to H x W as F.interpolate does)
+ *   sim_avg   : (B, N) fp32 out
+ *   optional outs (NULL to skip): score_t2s (B,N,T) fp32, idx_t2s (B,N,T) int32, idx_s2t (B,N,T) int32
+ *   cluster   : 0 = default, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
+ */
+PP_API int pp_match_scores(const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
+                    const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
+                    float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
+                    void* workspace, size_t workspace_bytes, int cluster, void* stream);
+
+/* Row-wise top-k (descending, lowest index first on ties).  Replaces torch.topk, utils/matching.py:68.
+ *   scores (B,N) fp32 -> out_score (B,k) fp32, out_idx (B,k) int64 (+ idx_offset, for sharded banks). */
+PP_API int pp_topk(const float* scores, int B, int N, int k, int64_t idx_offset,
+            float* out_score, int64_t* out_idx, void* stream);
+
+/* Stage-2 input volume.  Replaces matching_features_similarity, utils/matching.py:6-26.
+ *   q_prep, s_prep : (B, T, Kp) prepared query / template features; src_mask (B,Hm,Wm) fp32
+ *   out : (B, S, H, W) fp32 with out[b,s,h,w] = max(0, sim[b, t = w*H+h, s] * mask_s)
+ *   workspace >= pp_match_similarity_workspace(B, T) bytes. */
+PP_API size_t pp_match_similarity_workspace(int B, int T);
+PP_API int pp_match_similarity(const void* q_prep, const void* s_prep, const float* src_mask,
+                        int B, int H, int W, int Kp, int Hm, int Wm, float* out,
+                        void* workspace, size_t workspace_bytes, int cluster, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Correspondence glue.
+ * pp_init_correspondences replaces compute_init_correspondences, utils/correspondence.py:10-26:
+ *   Ms (B,3,3) fp32, tem_mask (B,Hm,Wm) fp32 -> flow (B,2,h,w), certainty (B,1,h,w).
+ * pp_stage3_correspondences replaces compute_stage3_correspondences, utils/correspondence.py:28-59
+ *   (no host synchronisation, unlike the reference's torch.nonzero):
+ *   flow (B,2,H,W), certainty (B,1,H,W) -> tar_pts, src_pts (B, H*W, 2) int64, flat index w*H+h.
+ * ------------------------------------------------------------------------------------------ */
+PP_API int pp_init_correspondences(const float* Ms, const float* tem_mask, int B, int Hm, int Wm,
+                            int h, int w, float* flow, float* certainty, void* stream);
+PP_API int pp_stage3_correspondences(const float* flow, const float* certainty, int B, int H, int W,
+                              float threshold, int64_t* tar_pts, int64_t* src_pts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICOPOSE_B200_H */

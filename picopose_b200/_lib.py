@@ -1,0 +1,92 @@
+"""ctypes binding of libpicopose_b200.so (the C ABI declared in include/picopose_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised -- the product path never routes through
+PyTorch ops or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpicopose_b200.so")
+
+MODE_BF16, MODE_FP32, MODE_BF16X3 = 0, 1, 2
+MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "bf16x3": MODE_BF16X3}
+
+# name -> (restype, argtypes); must list every symbol include/picopose_b200.h declares
+_vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+SIGNATURES = {
+    "pp_version": (_i, []),
+    "pp_last_error": (C.c_char_p, []),
+    "pp_check_device_faults": (_i, []),
+    "pp_corr_lookup": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "pp_bilinear_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pp_match_kp": (_i, [_i, _i]),
+    "pp_match_prepare": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "pp_match_scores_workspace": (_sz, [_i, _i, _i]),
+    "pp_match_scores": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "pp_topk": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
+    "pp_match_similarity_workspace": (_sz, [_i, _i]),
+    "pp_match_similarity": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
+    "pp_init_correspondences": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pp_stage3_correspondences": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m picopose_b200.build` "
+                "(nvcc, sm_100a). picopose_b200 has no PyTorch/CPU fallback path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().pp_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError(f"picopose_b200 {what} failed ({rc}): {last_error()}")
+
+
+def check_device_faults() -> None:
+    check(load().pp_check_device_faults(), "device fault check")
+
+
+# ---- torch helpers (torch is only the allocator / stream provider) -----------------------------
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "picopose_b200 runs on a CUDA (sm_100) device only: got a tensor on "
+                f"'{t.device}'; there is no CPU fallback")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_of(t) -> int:
+    import torch
+    return torch.cuda.current_stream(t.device).cuda_stream

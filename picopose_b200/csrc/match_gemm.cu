@@ -1,0 +1,393 @@
+// Stage-1 similarity contraction on the 5th-gen tensor cores with a fused reduction epilogue.
+//
+// Replaces the reference's  sim = einsum("b c t, b n c s -> b n t s")  and everything that sweeps
+// the materialised sim tensor afterwards (utils/matching.py:47-51, and :22 for the stage-2 volume):
+// the T x S similarity tile lives only in TMEM; the epilogue reduces it on the fly to
+//   * per query row t   : max_s sim[t,s] and its first argmax            (utils/matching.py:50)
+//   * per template col s: max_t m[t]*sim[t,s] and its first argmax       (utils/matching.py:48,51)
+// published as packed 64-bit keys with atomicMax, so tiles of one (b, n) may run on any SM in any order.
+//
+// Structure (persistent, warp-specialised, one CTA or one CTA pair per 148 SMs):
+//   warp 0     TMA producer: K-major bf16 tiles, 128-byte swizzle, STAGES-deep mbarrier ring
+//   warp 1     MMA issuer  : tcgen05.mma kind::f16, M = 128*CL, N = 256, K = 16 per instruction,
+//                            accumulators double-buffered in TMEM (2 x 256 columns)
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue    : tcgen05.ld 32x32b -> registers; warp w reads lane quarter w%4,
+//                            column half (w-4)/4 of the 128 x 256 accumulator
+// CL = 2 pairs two SMs (cta_group::2): each CTA loads its own 128 A rows and half of the B tile, the
+// leader issues M=256 MMAs, commits are multicast to both CTAs.
+#include "pp_common.cuh"
+#include "pp_ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace pp {
+
+constexpr int BLOCK_M = 128;  // accumulator rows per CTA (= TMEM lanes)
+constexpr int BLOCK_N = 256;  // accumulator columns per tile (UMMA N)
+constexpr int BLOCK_K = 64;   // bf16 elements per k-block: one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_ACC = 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int GEMM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;  // 384
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KiB
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;              // ~2 s: a stuck pipeline traps instead of hanging
+
+enum { EPI_MATCH = 0, EPI_EMIT = 1 };
+
+struct GemmParams {
+    int B, N, T;  // detections, views per bank, patches (T == S)
+    int num_k_blocks;
+    int num_mt, num_nt;  // tiles along T (per 128*CL rows) and S (per 256 columns)
+    long long total_tiles;
+    const int32_t* bank_of_det;    // (B,) or null = identity
+    const float* mrow;             // (B, T) nearest-resized query mask
+    unsigned long long* rowkey;    // (B, N, T)
+    unsigned long long* colkey;    // (B, N, T)
+    float* emit;                   // EPI_EMIT: (B*N, T, T) raw similarities
+    int* fault;                    // host-mapped fault record
+};
+
+template <int CL>
+struct GemmCfg {
+    static constexpr int STAGES = CL == 1 ? 4 : 6;
+    static constexpr int B_ROWS = BLOCK_N / CL;
+    static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+__device__ __noinline__ void report_fault(int* fault, int code, int a, int b) {
+    if (fault) {
+        fault[1] = blockIdx.x;
+        fault[2] = threadIdx.x;
+        fault[3] = a;
+        fault[4] = b;
+        __threadfence_system();
+        fault[0] = code;
+        __threadfence_system();
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fault, int code, int aux) {
+    if (ptx::mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) report_fault(fault, code, aux, (int)parity);
+    }
+}
+
+struct TileCoord {
+    int b, n, nt, mt;
+};
+__device__ __forceinline__ TileCoord decode_tile(long long tile, const GemmParams& p) {
+    TileCoord c;
+    c.mt = (int)(tile % p.num_mt);
+    long long r = tile / p.num_mt;
+    c.nt = (int)(r % p.num_nt);
+    r /= p.num_nt;
+    c.n = (int)(r % p.N);
+    c.b = (int)(r / p.N);
+    return c;
+}
+
+template <int CL, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmParams p) {
+    using Cfg = GemmCfg<CL>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // 128-byte swizzle atoms need 1024-byte alignment
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
+    const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + NUM_ACC + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const long long cluster_id = blockIdx.x / CL;
+    const long long num_clusters = gridDim.x / CL;
+
+    if (CL > 1) ptx::cluster_sync();  // both CTAs resident before the paired TMEM allocation
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_a);
+        ptx::prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), CL);  // one producer arrival per CTA (on the leader's barrier)
+            ptx::mbar_init(empty_bar(s), 1);  // one tcgen05.commit arrival
+        }
+        for (int s = 0; s < NUM_ACC; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), CL * NUM_EPI_WARPS);  // one arrival per epilogue warp of every CTA
+        }
+        ptx::fence_barrier_init();
+    } else if (warp == 2) {
+        ptx::tmem_alloc<CL>(ptx::smem_u32((const void*)tmem_slot), 512);
+    }
+    ptx::tc_fence_before();
+    if (CL > 1) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer (every CTA) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+            const TileCoord tc = decode_tile(tile, p);
+            const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
+            const int a_row = tc.b * p.T + tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M;
+            const long long b_row_ll = ((long long)bank * p.N + tc.n) * p.T + tc.nt * BLOCK_N + (int)cta_rank * Cfg::B_ROWS;
+            const int b_row = (int)b_row_ll;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u, p.fault, 1, stage);
+                const uint32_t da = smem_a + stage * A_STAGE_BYTES;
+                const uint32_t db = smem_b + stage * Cfg::B_STAGE_BYTES;
+                if (CL == 1) {
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    ptx::tma_load_2d(&tmap_a, full_bar(stage), da, kb * BLOCK_K, a_row);
+                    ptx::tma_load_2d(&tmap_b, full_bar(stage), db, kb * BLOCK_K, b_row);
+                } else {
+                    ptx::tma_load_2d_pair(&tmap_a, full_bar(stage), da, kb * BLOCK_K, a_row);
+                    ptx::tma_load_2d_pair(&tmap_b, full_bar(stage), db, kb * BLOCK_K, b_row);
+                    if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CL);
+                    else ptx::mbar_arrive_cluster(full_bar(stage), 0);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ===================== MMA issuer (leader CTA, one thread) =====================
+        constexpr uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0;
+        long long iter = 0;
+        for (long long tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
+            const int as = (int)(iter & 1);
+            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+            mbar_wait(tempty_bar(as), aphase ^ 1u, p.fault, 2, as);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(full_bar(stage), phase, p.fault, 3, stage);
+                ptx::tc_fence_after();
+                const uint64_t adesc = ptx::smem_desc_sw128(smem_a + stage * A_STAGE_BYTES);
+                const uint64_t bdesc = ptx::smem_desc_sw128(smem_b + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    // advance 16 elements = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+                    ptx::umma_bf16<CL>(adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), tmem_d,
+                                       (kb > 0 || k > 0) ? 1u : 0u, idesc);
+                }
+                ptx::umma_commit<CL>(empty_bar(stage));  // smem slot reusable once these MMAs retire
+                if (kb == p.num_k_blocks - 1) ptx::umma_commit<CL>(tfull_bar(as));
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= FIRST_EPI_WARP) {
+        // ===================== epilogue (every CTA) =====================
+        const int e = warp - FIRST_EPI_WARP;
+        const int q = warp & 3;   // TMEM lane quarter this warp may read
+        const int hh = e >> 2;    // column half
+        long long iter = 0;
+        for (long long tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
+            const TileCoord tc = decode_tile(tile, p);
+            const int as = (int)(iter & 1);
+            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+            const int T = p.T;
+            const int warp_row0 = tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M + q * 32;
+            const int t = warp_row0 + lane;
+            const bool row_ok = t < T;
+            const float m_t = (EPI == EPI_MATCH && row_ok) ? __ldg(p.mrow + (size_t)tc.b * T + t) : 0.f;
+            const size_t bn = (size_t)tc.b * p.N + tc.n;
+
+            mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + hh * 128);
+
+            float best = -INFINITY;
+            int best_s = 0;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                ptx::tmem_ld_wait();
+                if (c == 3) {
+                    // this warp has drained its part of the accumulator: hand the TMEM stage back
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CL == 1) ptx::mbar_arrive(tempty_bar(as));
+                        else ptx::mbar_arrive_cluster(tempty_bar(as), 0);
+                    }
+                }
+                const int s0 = tc.nt * BLOCK_N + hh * 128 + c * 32;
+                if (s0 >= T) continue;  // warp-uniform: chunk entirely past the last template patch
+                const int ncols = min(32, T - s0);
+                if (EPI == EPI_MATCH) {
+                    float ck_v = -INFINITY;
+                    int ck_l = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = __uint_as_float(v[j]);
+                        const bool col_ok = j < ncols;  // uniform
+                        // rows: running first-argmax over s (strict > keeps the first index on ties)
+                        if (col_ok && x > best) { best = x; best_s = s0 + j; }
+                        // columns: masked rows contribute +0.0, rows past T nothing
+                        const float xc = row_ok ? fmaf(x, m_t, 0.0f) : -INFINITY;
+                        const float cm = ptx::warp_max_f32(xc);
+                        const unsigned ball = __ballot_sync(0xffffffffu, xc == cm);
+                        if (lane == j) { ck_v = cm; ck_l = __ffs(ball) - 1; }
+                    }
+                    if (lane < ncols && warp_row0 < T) {
+                        atomicMax(p.colkey + bn * T + s0 + lane, pack_key(ck_v, (uint32_t)(warp_row0 + ck_l)));
+                    }
+                } else {
+                    if (row_ok) {
+                        float* dst = p.emit + (bn * T + t) * (size_t)T + s0;
+                        if (ncols == 32 && (T & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncols) dst[j] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            }
+            if (EPI == EPI_MATCH && row_ok && best > -INFINITY) {
+                atomicMax(p.rowkey + bn * T + t, pack_key(best + 0.0f, (uint32_t)best_s));
+            }
+        }
+    }
+
+    // ===================== teardown =====================
+    ptx::tc_fence_before();
+    if (CL > 1) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<CL>(tmem_base, 512);
+}
+
+// ---- host side ----------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major tensor (rows x Kp), box = (BLOCK_K x box_rows), 128-byte swizzle
+static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t kp, uint32_t box_rows) {
+    auto fn = get_encode_fn();
+    if (!fn) return fail(PP_ERR_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {kp, rows};
+    cuuint64_t strides[1] = {kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PP_ERR_LAUNCH, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return PP_OK;
+}
+
+static int* g_fault_host = nullptr;  // pinned, host-mapped: survives a trapped kernel
+static int* g_fault_dev = nullptr;
+static int ensure_fault_buffer() {
+    if (g_fault_host) return PP_OK;
+    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_fault_host), 64 * sizeof(int), cudaHostAllocMapped));
+    for (int i = 0; i < 64; ++i) g_fault_host[i] = 0;
+    PP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_fault_dev), g_fault_host, 0));
+    return PP_OK;
+}
+
+template <int CL, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<CL>;
+    auto kern = match_gemm_kernel<CL, EPI>;
+    PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    long long clusters = sm_count() / CL;
+    if (clusters > p.total_tiles) clusters = p.total_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    return PP_OK;
+}
+
+// Shared by pp_match_scores (EPI_MATCH) and pp_match_similarity (EPI_EMIT).
+int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
+                   int B, int N, int T, int Kp, const float* mrow, unsigned long long* rowkey,
+                   unsigned long long* colkey, float* emit, int cluster, cudaStream_t st) {
+    PP_CHECK_ARG(Kp > 0 && Kp % BLOCK_K == 0, "Kp must be a positive multiple of %d (got %d)", BLOCK_K, Kp);
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(q_prep) & 127) == 0 && (reinterpret_cast<uintptr_t>(bank_prep) & 127) == 0,
+                 "prepared operands must be 128-byte aligned");
+    PP_CHECK_ARG((long long)n_banks * N * T < (1LL << 31) && (long long)B * T < (1LL << 31),
+                 "operand row count exceeds the 2^31 TMA coordinate range; split the call");
+    if (cluster == 0) cluster = 2;
+    PP_CHECK_ARG(cluster == 1 || cluster == 2, "cluster must be 0, 1 or 2 (got %d)", cluster);
+    if (int rc = ensure_fault_buffer()) return rc;
+    GemmParams p{};
+    p.B = B;
+    p.N = N;
+    p.T = T;
+    p.num_k_blocks = Kp / BLOCK_K;
+    p.num_mt = (T + BLOCK_M * cluster - 1) / (BLOCK_M * cluster);
+    p.num_nt = (T + BLOCK_N - 1) / BLOCK_N;
+    p.total_tiles = (long long)B * N * p.num_mt * p.num_nt;
+    p.bank_of_det = bank_of_det;
+    p.mrow = mrow;
+    p.rowkey = rowkey;
+    p.colkey = colkey;
+    p.emit = emit;
+    p.fault = g_fault_dev;
+    if (p.total_tiles == 0) return PP_OK;
+    CUtensorMap ta, tb;
+    if (int rc = make_tmap(&ta, q_prep, (uint64_t)B * T, (uint64_t)Kp, BLOCK_M)) return rc;
+    if (int rc = make_tmap(&tb, bank_prep, (uint64_t)n_banks * N * T, (uint64_t)Kp, BLOCK_N / cluster)) return rc;
+    if (cluster == 1) {
+        return epi == EPI_MATCH ? launch_gemm<1, EPI_MATCH>(ta, tb, p, st) : launch_gemm<1, EPI_EMIT>(ta, tb, p, st);
+    }
+    return epi == EPI_MATCH ? launch_gemm<2, EPI_MATCH>(ta, tb, p, st) : launch_gemm<2, EPI_EMIT>(ta, tb, p, st);
+}
+
+int read_fault_record(int* out5) {
+    if (!g_fault_host) return 0;
+    for (int i = 0; i < 5; ++i) out5[i] = g_fault_host[i];
+    const int code = g_fault_host[0];
+    g_fault_host[0] = 0;
+    return code;
+}
+
+}  // namespace pp

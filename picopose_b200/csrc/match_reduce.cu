@@ -1,0 +1,206 @@
+// Stage-1 reductions around the tensor-core contraction: mask resize, score finalisation, top-k,
+// and the stage-2 similarity-volume layout pass.  (Reference: utils/matching.py:16-17,38-39,54-68,23-25.)
+#include "pp_common.cuh"
+
+namespace pp {
+
+int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
+                   int B, int N, int T, int Kp, const float* mrow, unsigned long long* rowkey,
+                   unsigned long long* colkey, float* emit, int cluster, cudaStream_t st);
+
+// F.interpolate(mask[:,None], size=(H,W)) (nearest) flattened to (B, H*W): utils/matching.py:38-39 / :16-17
+__global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm, int Wm, int H, int W,
+                                   float* __restrict__ out) {
+    const int total = B * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = i / (H * W);
+        const int r = i - b * H * W;
+        const int y = r / W, x = r - y * W;
+        out[i] = mask[((size_t)b * Hm + nearest_src(y, Hm, H)) * Wm + nearest_src(x, Wm, W)];
+    }
+}
+
+// One block per (b, n): decode the row / column keys, apply the reference's validity rule
+// (utils/matching.py:54-60) and the masked mean (:63-67).
+__global__ void __launch_bounds__(256)
+finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
+                       const float* __restrict__ mrow, int N, int T, float inv_hh, float* __restrict__ sim_avg,
+                       float* __restrict__ score_t2s, int32_t* __restrict__ idx_t2s, int32_t* __restrict__ idx_s2t) {
+    const size_t bn = blockIdx.x;
+    const int b = (int)(bn / N);
+    float sum = 0.f, cnt = 0.f;
+    for (int j = threadIdx.x; j < T; j += blockDim.x) {
+        const float m = mrow[(size_t)b * T + j];
+        const unsigned long long rk = rowkey[bn * T + j];
+        const unsigned long long ck = colkey[bn * T + j];
+        // a masked query row is all zeros in the reference: max 0 at index 0
+        const bool on = m != 0.f;
+        const float sc = (on && rk) ? key_value(rk) * m : 0.f;
+        const int it = (on && rk) ? (int)key_index(rk) : 0;
+        const int is = ck ? (int)key_index(ck) : 0;
+        const float valid = (it != 0 && is != 0) ? m : 0.f;  // tar_mask * (idx_src2tar != 0) * (idx_tar2src != 0)
+        sum = fmaf(sc, valid, sum);
+        cnt += valid;
+        if (score_t2s) score_t2s[bn * T + j] = sc;
+        if (idx_t2s) idx_t2s[bn * T + j] = it;
+        if (idx_s2t) idx_s2t[bn * T + j] = is;
+    }
+    __shared__ float s_sum[8], s_cnt[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ts = 0.f, tc = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += s_sum[w]; tc += s_cnt[w]; }
+        sim_avg[bn] = tc > 0.f ? ts * inv_hh : 0.f;  // divisor is H*H, not the valid count (:65-67)
+    }
+}
+
+// Row-wise top-k by repeated block arg-max; ties resolve to the lowest index (torch leaves them unspecified).
+__global__ void __launch_bounds__(256)
+topk_kernel(const float* __restrict__ scores, int N, int k, long long idx_offset, float* __restrict__ out_score,
+            long long* __restrict__ out_idx) {
+    extern __shared__ unsigned long long s_keys[];  // N packed keys + 8 partials
+    unsigned long long* s_red = s_keys + N;
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_keys[i] = pack_key(scores[(size_t)b * N + i] + 0.0f, (uint32_t)i);
+    __syncthreads();
+    for (int r = 0; r < k; ++r) {
+        unsigned long long best = 0ull;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) best = s_keys[i] > best ? s_keys[i] : best;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_red[w] > best ? s_red[w] : best;
+            const uint32_t idx = key_index(best);
+            out_score[(size_t)b * k + r] = key_value(best);
+            out_idx[(size_t)b * k + r] = (long long)idx + idx_offset;
+            s_keys[idx] = 0ull;  // remove the winner
+        }
+        __syncthreads();
+    }
+}
+
+// stage-2 volume: out[b, s, h, w] = max(0, sim[b, t = w*H + h, s] * mask_s)   (utils/matching.py:23-25)
+__global__ void similarity_layout_kernel(const float* __restrict__ sim, const float* __restrict__ mcol, int B, int H,
+                                         int W, float* __restrict__ out) {
+    const int T = H * W;
+    const long long total = (long long)B * T * T;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / ((long long)T * T));
+        const int r = (int)(i - (long long)b * T * T);
+        const int s = r / T;
+        const int hw = r - s * T;
+        const int h = hw / W, w = hw - h * W;
+        const int t = w * H + h;
+        float v = sim[((size_t)b * T + t) * T + s] * mcol[(size_t)b * T + s];
+        out[i] = v < 0.f ? 0.f : v;
+    }
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace pp
+
+extern "C" size_t pp_match_scores_workspace(int B, int N, int T) {
+    if (B < 0 || N < 0 || T < 0) return 0;
+    const size_t keys = (size_t)B * N * T * sizeof(unsigned long long);
+    return pp::align_up((size_t)B * T * sizeof(float), 256) + 2 * pp::align_up(keys, 256);
+}
+
+extern "C" int pp_match_scores(const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
+                               const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
+                               float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t, void* workspace,
+                               size_t workspace_bytes, int cluster, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    PP_CHECK_ARG(q_prep && bank_prep && tar_mask && sim_avg, "pp_match_scores: null pointer");
+    PP_CHECK_ARG(H == W, "pp_match_scores: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
+    PP_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_scores: bad shape");
+    PP_CHECK_ARG(bank_of_det != nullptr || n_banks == B, "pp_match_scores: identity bank mapping needs n_banks == B");
+    if (B == 0 || N == 0) return PP_OK;
+    const int T = H * W;
+    const size_t need = pp_match_scores_workspace(B, N, T);
+    if (!workspace || workspace_bytes < need)
+        return fail(PP_ERR_WORKSPACE, "pp_match_scores: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_scores: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    float* mrow = reinterpret_cast<float*>(ws);
+    const size_t keys = align_up((size_t)B * N * T * sizeof(unsigned long long), 256);
+    unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(ws + align_up((size_t)B * T * sizeof(float), 256));
+    unsigned long long* colkey = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(rowkey) + keys);
+
+    resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(tar_mask, B, Hm, Wm, H, W, mrow);
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys, st));
+    if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, mrow, rowkey, colkey, nullptr,
+                                cluster, st))
+        return rc;
+    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, mrow, N, T, 1.0f / (float)(H * H),
+                                                                      sim_avg, score_t2s, idx_t2s, idx_s2t);
+    PP_CUDA(cudaGetLastError());
+    return PP_OK;
+}
+
+extern "C" int pp_topk(const float* scores, int B, int N, int k, int64_t idx_offset, float* out_score,
+                       int64_t* out_idx, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    PP_CHECK_ARG(scores && out_score && out_idx, "pp_topk: null pointer");
+    // torch.topk raises when k exceeds the dimension ("selected index k out of range")
+    PP_CHECK_ARG(k >= 0 && k <= N, "pp_topk: selected index k out of range (k=%d, N=%d)", k, N);
+    PP_CHECK_ARG(N <= 24000, "pp_topk: at most 24000 candidates per row (got %d)", N);
+    if (B == 0 || k == 0) return PP_OK;
+    const size_t smem = ((size_t)N + 8) * sizeof(unsigned long long);
+    if (smem > 48 * 1024)
+        PP_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, N, k, (long long)idx_offset, out_score,
+                                                                    reinterpret_cast<long long*>(out_idx));
+    PP_CUDA(cudaGetLastError());
+    return PP_OK;
+}
+
+extern "C" size_t pp_match_similarity_workspace(int B, int T) {
+    if (B < 0 || T < 0) return 0;
+    return pp::align_up((size_t)B * T * sizeof(float), 256) + pp::align_up((size_t)B * T * T * sizeof(float), 256);
+}
+
+extern "C" int pp_match_similarity(const void* q_prep, const void* s_prep, const float* src_mask, int B, int H, int W,
+                                   int Kp, int Hm, int Wm, float* out, void* workspace, size_t workspace_bytes,
+                                   int cluster, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    PP_CHECK_ARG(q_prep && s_prep && src_mask && out, "pp_match_similarity: null pointer");
+    PP_CHECK_ARG(H == W, "pp_match_similarity: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
+    PP_CHECK_ARG(B >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_similarity: bad shape");
+    if (B == 0) return PP_OK;
+    const int T = H * W;
+    const size_t need = pp_match_similarity_workspace(B, T);
+    if (!workspace || workspace_bytes < need)
+        return fail(PP_ERR_WORKSPACE, "pp_match_similarity: workspace of %zu bytes needed, %zu given", need,
+                    workspace_bytes);
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_similarity: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    float* mcol = reinterpret_cast<float*>(ws);
+    float* sim = reinterpret_cast<float*>(ws + align_up((size_t)B * T * sizeof(float), 256));
+    resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(src_mask, B, Hm, Wm, H, W, mcol);
+    PP_CUDA(cudaGetLastError());
+    // one "view" per detection: banks == detections, N = 1
+    if (int rc = run_match_gemm(1, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, sim, cluster, st))
+        return rc;
+    const long long total = (long long)B * T * T;
+    int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
+    similarity_layout_kernel<<<grid, 256, 0, st>>>(sim, mcol, B, H, W, out);
+    PP_CUDA(cudaGetLastError());
+    return PP_OK;
+}

@@ -1,0 +1,59 @@
+// Shared host/device helpers for libpicopose_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+#include "../../include/picopose_b200.h"
+
+namespace pp {
+
+// ---- host-side error plumbing -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define PP_CHECK_ARG(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) return ::pp::fail(PP_ERR_ARG, __VA_ARGS__);  \
+    } while (0)
+
+#define PP_CUDA(call)                                                                            \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return ::pp::fail(PP_ERR_LAUNCH, "%s failed: %s (%s:%d)", #call,                     \
+                              cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+// Verifies the current device is sm_100 (cached per device).
+int require_sm100();
+int sm_count();
+
+// ---- small device helpers -----------------------------------------------------------------
+// Monotone map float -> uint32 (a < b  <=>  ord(a) < ord(b)); -0.0 must be canonicalised first.
+__device__ __forceinline__ uint32_t f32_ord(float v) {
+    uint32_t u = __float_as_uint(v);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord_f32(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+    return __uint_as_float(u);
+}
+// (value, index) -> 64-bit key whose unsigned max is "largest value, then smallest index".
+__device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
+    return ((unsigned long long)f32_ord(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_value(unsigned long long k) { return ord_f32((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_index(unsigned long long k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+// F.interpolate(mode='nearest') source index: min(floor(dst * in/out), in - 1), computed in fp32 like ATen.
+__host__ __device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
+    float scale = (float)in_size / (float)out_size;
+    int s = (int)floorf((float)dst * scale);
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+}  // namespace pp

@@ -1,0 +1,224 @@
+"""Stage-1 matching: host side of the reference's ``utils/matching.py`` on libpicopose_b200.
+
+Same names, argument meaning and results as the reference:
+
+* ``matching_templates(src_feats, tar_feat, src_masks, tar_mask, topk=5)``  (utils/matching.py:29-69)
+* ``matching_features_similarity(src_feat, tar_feat, src_mask, tar_mask)``  (utils/matching.py:6-26)
+
+plus the pieces a serving loop wants: ``TemplateBank`` (a template bank
+normalised / cast / laid out once per object, the way run_test.py:121-134 caches
+template features once per object) and ``template_scores`` (dense per-view
+scores and the coarse 2D-2D correspondences = bidirectional argmax indices).
+
+PyTorch only allocates tensors and provides the stream; every arithmetic step
+runs in the sm_100a kernels behind the C ABI (include/picopose_b200.h).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_WORKSPACE_LIMIT = int(os.environ.get("PICOPOSE_B200_WORKSPACE_MB", "1024")) << 20
+
+
+def default_mode() -> str:
+    return os.environ.get("PICOPOSE_B200_MODE", "bf16")
+
+
+def default_cluster() -> int:
+    return int(os.environ.get("PICOPOSE_B200_CLUSTER", "0"))
+
+
+def _mode_id(mode: Optional[str]) -> int:
+    mode = default_mode() if mode is None else mode
+    if mode not in _lib.MODES:
+        raise ValueError(f"unknown mode '{mode}' (expected one of {sorted(_lib.MODES)})")
+    return _lib.MODES[mode]
+
+
+def _as_f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def prepare_features(feats: torch.Tensor, mode: Optional[str] = None, is_query: bool = False) -> torch.Tensor:
+    """(..., C, H, W) fp32 -> (..., H*W, Kp) bf16: L2-normalised over C, K-major, split per `mode`."""
+    _lib.require_cuda(feats)
+    lib = _lib.load()
+    mid = _mode_id(mode)
+    feats = _as_f32(feats)
+    *lead, Cc, H, W = feats.shape
+    G = 1
+    for d in lead:
+        G *= d
+    P = H * W
+    kp = lib.pp_match_kp(Cc, mid)
+    if kp <= 0:
+        raise RuntimeError(f"picopose_b200: bad feature dim {Cc}")
+    out = torch.empty((*lead, P, kp), dtype=torch.bfloat16, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(lib.pp_match_prepare(_lib.ptr(feats), G, Cc, P, mid, int(is_query), _lib.ptr(out),
+                                        _lib.stream_of(feats)), "pp_match_prepare")
+    return out
+
+
+class TemplateBank:
+    """Template banks prepared once: (n_banks, N, C, H, W) fp32 -> resident (n_banks, N, H*W, Kp) bf16."""
+
+    def __init__(self, prepared: torch.Tensor, C: int, H: int, W: int, mode: str):
+        self.prepared = prepared
+        self.C, self.H, self.W, self.mode = C, H, W, mode
+
+    @classmethod
+    def from_features(cls, src_feats: torch.Tensor, mode: Optional[str] = None) -> "TemplateBank":
+        if src_feats.dim() == 4:
+            src_feats = src_feats.unsqueeze(0)
+        if src_feats.dim() != 5:
+            raise ValueError("expected (n_banks, N, C, H, W) template features")
+        mode = default_mode() if mode is None else mode
+        _, _, Cc, H, W = src_feats.shape
+        return cls(prepare_features(src_feats, mode, is_query=False), Cc, H, W, mode)
+
+    @property
+    def n_banks(self) -> int:
+        return self.prepared.shape[0]
+
+    @property
+    def n_views(self) -> int:
+        return self.prepared.shape[1]
+
+    @property
+    def device(self):
+        return self.prepared.device
+
+    def view_slice(self, start: int, stop: int) -> "TemplateBank":
+        """Bank restricted to views [start, stop) (template-axis sharding); copies to keep rows dense."""
+        return TemplateBank(self.prepared[:, start:stop].contiguous(), self.C, self.H, self.W, self.mode)
+
+
+def _resolve_bank(src_feats, mode, B):
+    """-> (TemplateBank, bank_of_det or None).  Accepts a TemplateBank, a dense (B,N,C,H,W) tensor, or a
+    batch-expanded view (stride 0 over B) of one shared bank."""
+    if isinstance(src_feats, TemplateBank):
+        return src_feats, None
+    if src_feats.dim() != 5:
+        raise ValueError("src_feats must be (B, N, C, H, W)")
+    if src_feats.shape[0] > 1 and src_feats.stride(0) == 0:
+        bank = TemplateBank.from_features(src_feats[:1], mode)
+        return bank, torch.zeros(B, dtype=torch.int32, device=src_feats.device)
+    return TemplateBank.from_features(src_feats, mode), None
+
+
+def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *, mode: Optional[str] = None,
+                    bank_index: Optional[torch.Tensor] = None, want_indices: bool = False,
+                    cluster: Optional[int] = None):
+    """Dense scores sim_avg (B, N) of utils/matching.py:38-67.
+
+    With want_indices also returns (score_t2s (B,N,T) f32, idx_t2s (B,N,T) i32, idx_s2t (B,N,T) i32): the
+    bidirectional nearest-neighbour patch correspondences the reference computes at :50-51.
+    `bank_index` (B,) maps detections to banks of a shared TemplateBank.
+    """
+    _lib.require_cuda(tar_feat, tar_mask)
+    lib = _lib.load()
+    B, Cc, H, W = tar_feat.shape
+    if H != W:
+        raise AssertionError("matching_templates expects a square patch grid (H == W)")
+    bank, auto_index = _resolve_bank(src_feats, mode, B)
+    if bank_index is None:
+        bank_index = auto_index
+    if bank.device != tar_feat.device:
+        raise RuntimeError("template bank and query features live on different devices")
+    if (bank.C, bank.H, bank.W) != (Cc, H, W):
+        raise ValueError(f"bank features {(bank.C, bank.H, bank.W)} do not match the query {(Cc, H, W)}")
+    if bank_index is None and bank.n_banks != B:
+        raise ValueError(f"{bank.n_banks} banks for {B} detections: pass bank_index")
+    if bank_index is not None:
+        bank_index = bank_index.to(device=tar_feat.device, dtype=torch.int32).contiguous()
+    N, T = bank.n_views, H * W
+    dev = tar_feat.device
+    q = prepare_features(tar_feat, bank.mode, is_query=True)  # (B, T, Kp)
+    kp = q.shape[-1]
+    mask = _as_f32(tar_mask)
+    Hm, Wm = mask.shape[-2:]
+    sim_avg = torch.empty(B, N, dtype=torch.float32, device=dev)
+    sc = it = is_ = None
+    if want_indices:
+        sc = torch.empty(B, N, T, dtype=torch.float32, device=dev)
+        it = torch.empty(B, N, T, dtype=torch.int32, device=dev)
+        is_ = torch.empty(B, N, T, dtype=torch.int32, device=dev)
+    cl = default_cluster() if cluster is None else cluster
+    # bound the scratch (two 64-bit keys per (b, n, t)) by slicing the detection batch
+    per_det = max(1, lib.pp_match_scores_workspace(1, N, T))
+    chunk = max(1, min(B, _WORKSPACE_LIMIT // per_det))
+    ws = torch.empty(lib.pp_match_scores_workspace(chunk, N, T), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_of(tar_feat)
+        for b0 in range(0, B, chunk):
+            b1 = min(B, b0 + chunk)
+            nb = b1 - b0
+            if bank_index is not None:
+                bidx, bank_ptr, n_banks = _lib.ptr(bank_index[b0:b1]), _lib.ptr(bank.prepared), bank.n_banks
+            else:
+                bidx, bank_ptr, n_banks = 0, _lib.ptr(bank.prepared[b0:b1]), nb
+            _lib.check(lib.pp_match_scores(
+                _lib.ptr(q[b0:b1]), bank_ptr, n_banks, bidx, _lib.ptr(mask[b0:b1]), nb, N, H, W, kp, Hm, Wm,
+                _lib.ptr(sim_avg[b0:b1]), _lib.ptr(sc[b0:b1]) if want_indices else 0,
+                _lib.ptr(it[b0:b1]) if want_indices else 0, _lib.ptr(is_[b0:b1]) if want_indices else 0,
+                _lib.ptr(ws), ws.numel(), cl, st), "pp_match_scores")
+    if want_indices:
+        return sim_avg, sc, it, is_
+    return sim_avg
+
+
+def topk_scores(sim_avg: torch.Tensor, k: int, idx_offset: int = 0):
+    """torch.topk(sim_avg, k, dim=1) replacement (sorted descending, int64 indices)."""
+    _lib.require_cuda(sim_avg)
+    lib = _lib.load()
+    sim_avg = _as_f32(sim_avg)
+    B, N = sim_avg.shape
+    if k > N:
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")
+    score = torch.empty(B, k, dtype=torch.float32, device=sim_avg.device)
+    idx = torch.empty(B, k, dtype=torch.int64, device=sim_avg.device)
+    with torch.cuda.device(sim_avg.device):
+        _lib.check(lib.pp_topk(_lib.ptr(sim_avg), B, N, k, idx_offset, _lib.ptr(score), _lib.ptr(idx),
+                               _lib.stream_of(sim_avg)), "pp_topk")
+    return score, idx
+
+
+def matching_templates(src_feats, tar_feat, src_masks, tar_mask, topk=5, *, mode: Optional[str] = None,
+                       bank_index: Optional[torch.Tensor] = None):
+    """Drop-in for utils/matching.py:29-69.  Returns (pred_score_src (B,k) f32, pred_id_src (B,k) i64).
+
+    `src_masks` is accepted and ignored, as in the reference.  `src_feats` may also
+    be a TemplateBank (pre-normalised once per object) with `bank_index` mapping detections to banks.
+    """
+    sim_avg = template_scores(src_feats, tar_feat, tar_mask, mode=mode, bank_index=bank_index)
+    return topk_scores(sim_avg, topk)
+
+
+def matching_features_similarity(src_feat, tar_feat, src_mask, tar_mask, *, mode: Optional[str] = None):
+    """Drop-in for utils/matching.py:6-26.  Returns the (B, H*W, H, W) stage-2 similarity volume."""
+    _lib.require_cuda(src_feat, tar_feat, src_mask)
+    lib = _lib.load()
+    B, Cc, H, W = src_feat.shape
+    if H != W:
+        raise AssertionError("matching_features_similarity expects a square patch grid (H == W)")
+    mode = default_mode() if mode is None else mode
+    q = prepare_features(tar_feat, mode, is_query=True)
+    s = prepare_features(src_feat, mode, is_query=False)
+    mask = _as_f32(src_mask)
+    Hm, Wm = mask.shape[-2:]
+    T = H * W
+    out = torch.empty(B, T, H, W, dtype=torch.float32, device=src_feat.device)
+    ws = torch.empty(lib.pp_match_similarity_workspace(B, T), dtype=torch.uint8, device=src_feat.device)
+    with torch.cuda.device(src_feat.device):
+        _lib.check(lib.pp_match_similarity(_lib.ptr(q), _lib.ptr(s), _lib.ptr(mask), B, H, W, q.shape[-1], Hm, Wm,
+                                           _lib.ptr(out), _lib.ptr(ws), ws.numel(), default_cluster(),
+                                           _lib.stream_of(src_feat)), "pp_match_similarity")
+    return out

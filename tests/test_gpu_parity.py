@@ -1,0 +1,361 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes) against the CPU oracle and the
+committed golden vectors.  Run on the B200 box:  python -m pytest tests -m gpu -x -q
+
+Tolerances (BASELINE.json north_star): integer outputs bit-exact wherever the reference's own
+decision gap exceeds 1e-3; scores within 1e-2 relative in bf16 mode and 1e-5 in fp32 mode; lookup /
+flow coordinates within 1e-5 (fp32 path).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import correspondence_oracle as OC
+from oracle import corr_lookup_oracle as OL
+from oracle import matching_oracle as OM
+from picopose_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_loaded():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    _lib.load()
+    yield
+    _lib.check_device_faults()
+
+
+def cuda(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 3: correlation lookup
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["small", "ramp", "ladder", "rect", "intflow"])
+def test_corr_lookup_golden(name):
+    from picopose_b200.corr_lookup import CorrLookup
+    g = load(f"lookup_{name}.npz")
+    L, r = int(g["levels"]), int(g["radius"])
+    pyr = [cuda(g[f"pyr{i}"]) for i in range(L)]
+    out = CorrLookup(radius=r)(pyr, cuda(g["flow"]))
+    assert out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,H,L,r,sigma", [
+    (2, 16, 1, 2, 2.0), (1, 32, 2, 2, 3.0), (1, 64, 3, 2, 4.0),      # native ladder (r = int(4/2))
+    (2, 64, 1, 4, 4.0), (1, 64, 1, 5, 4.0), (1, 64, 1, 6, 4.0), (1, 64, 1, 7, 4.0), (1, 64, 1, 8, 4.0),
+    (1, 64, 3, 4, 4.0), (1, 20, 2, 3, 30.0), (1, 8, 1, 10, 2.0),      # far-out windows, generic-radius kernel
+])
+def test_corr_lookup_vs_oracle(B, H, L, r, sigma):
+    from picopose_b200.corr_lookup import corr_lookup
+    pyr, flow = synth.lookup_inputs(B, H, L, seed=7 + r, flow_sigma=sigma)
+    ref = OL.corr_lookup(pyr, flow, r)
+    out = corr_lookup([p.to(DEV) for p in pyr], flow.to(DEV), r)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
+
+
+def test_corr_lookup_edge_cases():
+    from picopose_b200.corr_lookup import corr_lookup
+    # integer flows put every tap exactly on a pixel; huge / non-finite flows fall entirely into padding
+    pyr, flow = synth.lookup_inputs(1, 16, 2, seed=3, flow_sigma=0.0)
+    flow[:, 0] = 3.0
+    flow[:, 1] = -2.0
+    flow[0, 0, 0, 0] = 1e9
+    flow[0, 1, 0, 1] = -1e9
+    ref = OL.corr_lookup(pyr, flow, 2)
+    out = corr_lookup([p.to(DEV) for p in pyr], flow.to(DEV), 2)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
+    assert float(out[0, :, 0, 0].abs().max()) == 0.0
+    # empty batch
+    e = corr_lookup([torch.zeros(0, 1, 16, 16, device=DEV)], torch.zeros(0, 2, 16, 16, device=DEV), 2)
+    assert tuple(e.shape) == (0, 25, 16, 16)
+    with pytest.raises(RuntimeError):
+        corr_lookup([p for p in pyr], flow, 2)          # CPU tensors: no fallback
+
+
+def test_corr_lookup_full_size_property():
+    """Config 4 shape at reduced batch: zero flow on a volume whose slice q equals a ramp in x
+    reproduces the tap x-coordinates exactly (window order is x-major) wherever in bounds."""
+    from picopose_b200.corr_lookup import corr_lookup
+    B, H, r = 8, 64, 4
+    D = 2 * r + 1
+    ramp = torch.arange(H, dtype=torch.float32, device=DEV).view(1, 1, 1, H).expand(B * H * H, 1, H, H).contiguous()
+    out = corr_lookup([ramp], torch.zeros(B, 2, H, H, device=DEV), r)
+    w = torch.arange(H, device=DEV).view(1, 1, 1, H).float()
+    a = (torch.arange(D * D, device=DEV) // D - r).view(1, D * D, 1, 1).float()
+    b = (torch.arange(D * D, device=DEV) % D - r).view(1, D * D, 1, 1).float()
+    hgrid = torch.arange(H, device=DEV).view(1, 1, H, 1).float()
+    x = w + a
+    y = hgrid + b
+    expect = torch.where((x >= 0) & (x <= H - 1) & (y >= 0) & (y <= H - 1), x, torch.zeros_like(x)).expand(B, -1, -1, -1)
+    np.testing.assert_allclose(out.cpu().numpy(), expect.cpu().numpy(), atol=2e-5)
+
+
+def test_bilinear_sample_and_coords_grid():
+    from picopose_b200.corr_lookup import bilinear_sample, coords_grid
+    g = load("bilinear.npz")
+    feat, grid = cuda(g["feat"]), cuda(g["grid"])
+    keep = grid.clone()
+    np.testing.assert_allclose(bilinear_sample(feat, grid, align_corners=True).cpu().numpy(), g["out_true"], atol=1e-5)
+    np.testing.assert_allclose(bilinear_sample(feat, grid, align_corners=False).cpu().numpy(), g["out_false"], atol=1e-5)
+    assert torch.equal(grid, keep)                                     # caller's grid untouched
+    np.testing.assert_array_equal(
+        coords_grid(2, torch.arange(0, 7, device=DEV), torch.arange(0, 5, device=DEV)).cpu().numpy(), g["coords"])
+    # FlowDecoder.feature_sample shape: (B,256,H,W) warped by grid (B,2,H,W), align_corners=True
+    gen = torch.Generator().manual_seed(5)
+    f = torch.randn(2, 256, 16, 16, generator=gen)
+    gr = OL.coords_grid(2, 16, 16) + 2.0 * torch.randn(2, 2, 16, 16, generator=gen)
+    ref = OL.bilinear_sample(f, gr, align_corners=True)
+    out = bilinear_sample(f.to(DEV), gr.to(DEV), align_corners=True)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# correspondence glue
+# ------------------------------------------------------------------------------------------------
+
+def test_correspondences_golden():
+    from picopose_b200.correspondence import compute_init_correspondences, compute_stage3_correspondences
+    g = load("corresp_init.npz")
+    flow, cert = compute_init_correspondences(cuda(g["Ms"]), cuda(g["mask"], torch.float32))
+    np.testing.assert_allclose(flow.cpu().numpy(), g["flow"], atol=2e-5)
+    np.testing.assert_array_equal(cert.cpu().numpy(), g["cert"])
+    g = load("corresp_stage3.npz")
+    for suffix in ("", "_r"):
+        tar, src = compute_stage3_correspondences(cuda(g["flow" + suffix]), cuda(g["cert" + suffix]))
+        assert tar.dtype == torch.int64 and src.dtype == torch.int64
+        np.testing.assert_array_equal(tar.cpu().numpy(), g["tar" + suffix])
+        np.testing.assert_array_equal(src.cpu().numpy(), g["src" + suffix])
+
+
+def test_stage3_correspondences_native_size():
+    from picopose_b200.correspondence import compute_stage3_correspondences
+    gen = torch.Generator().manual_seed(9)
+    flow = 5.0 * torch.randn(4, 2, 64, 64, generator=gen)
+    cert = torch.randn(4, 1, 64, 64, generator=gen)
+    tar_ref, src_ref = OC.stage3_correspondences(flow, cert)
+    tar, src = compute_stage3_correspondences(flow.to(DEV), cert.to(DEV))
+    np.testing.assert_array_equal(src.cpu().numpy(), src_ref.numpy())
+    np.testing.assert_array_equal(tar.cpu().numpy(), tar_ref.numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 1: matching
+# ------------------------------------------------------------------------------------------------
+
+def test_prepare_features_layout():
+    from picopose_b200.matching import prepare_features
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 2, 72, 5, 5, generator=gen)                     # C=72: K padding 72 -> 128
+    ref = torch.nn.functional.normalize(x, dim=2).reshape(3, 2, 72, 25).transpose(2, 3)
+    out = prepare_features(x.to(DEV), "bf16").float().cpu()
+    assert tuple(out.shape) == (3, 2, 25, 128)
+    np.testing.assert_allclose(out[..., :72].numpy(), ref.bfloat16().float().numpy(), atol=4e-3, rtol=0)
+    assert float(out[..., 72:].abs().max()) == 0.0
+    # split modes reconstruct the fp32 value: query segments [q1 q1 q2 | q1 q2 q3], bank [b1 b2 b1 | b3 b2 b1]
+    o6 = prepare_features(x.to(DEV), "fp32", is_query=True).float().cpu()
+    assert o6.shape[-1] == 448
+    s = [o6[..., i * 72:(i + 1) * 72] for i in range(6)]
+    assert torch.equal(s[0], s[1]) and torch.equal(s[0], s[3]) and torch.equal(s[2], s[4])
+    np.testing.assert_allclose((s[0] + s[2] + s[5]).numpy(), ref.numpy(), atol=3e-7, rtol=0)
+    b6 = prepare_features(x.to(DEV), "fp32", is_query=False).float().cpu()
+    t = [b6[..., i * 72:(i + 1) * 72] for i in range(6)]
+    assert torch.equal(t[0], t[2]) and torch.equal(t[0], t[5]) and torch.equal(t[1], t[4])
+    np.testing.assert_allclose((t[0] + t[1] + t[3]).numpy(), ref.numpy(), atol=3e-7, rtol=0)
+
+
+MODE_TOL = {"bf16": 4e-3, "bf16x3": 2e-5, "fp32": 1e-5}
+
+
+def _check_match(src, tar, mask, k, mode, cluster, ref=None):
+    """Runs the CUDA path and checks it against the oracle under the north_star tolerances.
+
+    Integer outputs must be exact wherever the reference's own decision gap exceeds 1e-3.  The score of
+    a (detection, view) pair may additionally move by score_j / H^2 for every patch j whose validity
+    flag (argmax != 0, utils/matching.py:58-59) is decided by a gap narrower than the arithmetic error.
+    """
+    from picopose_b200.matching import matching_templates, template_scores
+    if ref is None:
+        ref = OM.template_scores(src, tar, mask, want_indices=True)
+    sim_ref, sc_ref, it_ref, is_ref = ref
+    tol = MODE_TOL[mode]
+    band = 2 * tol
+    sim, sc, it, is_ = template_scores(src.to(DEV), tar.to(DEV), mask.to(DEV), mode=mode, want_indices=True,
+                                       cluster=cluster)
+    _lib.check_device_faults()
+    B, N, T = sc_ref.shape
+    H = int(round(T ** 0.5))
+    m = OM.nearest_mask(mask.float(), H, H)                            # (B,T)
+    np.testing.assert_allclose(sc.cpu().numpy(), sc_ref.numpy(), rtol=0, atol=tol)
+    a = OM._unit(tar.float(), 1).reshape(B, -1, T)
+    b_ = OM._unit(src.float(), 2).reshape(B, N, -1, T)
+    it_c, is_c = it.cpu().long(), is_.cpu().long()
+    allowed = torch.full((B, N), tol)
+    n_checked = 0
+    for bi in range(B):
+        simm = torch.matmul(a[bi].t().unsqueeze(0), b_[bi]) * m[bi].view(1, T, 1)   # (N,T,S)
+        top2 = simm.topk(2, dim=2).values
+        gap_r = top2[..., 0] - top2[..., 1]
+        sure = gap_r > 1e-3
+        assert torch.equal(it_c[bi][sure], it_ref[bi][sure])
+        top2c = simm.topk(2, dim=1).values
+        gap_c = top2c[:, 0] - top2c[:, 1]
+        sure_c = gap_c > 1e-3
+        assert torch.equal(is_c[bi][sure_c], is_ref[bi][sure_c])
+        n_checked += int(sure.sum()) + int(sure_c.sum())
+        # patches whose "argmax != 0" flag hangs on a gap inside the arithmetic error band
+        amb_r = torch.where(it_ref[bi] == 0, gap_r < band, (top2[..., 0] - simm[:, :, 0]) < band)
+        amb_c = torch.where(is_ref[bi] == 0, gap_c < band, (top2c[:, 0] - simm[:, 0, :]) < band)
+        amb = (amb_r | amb_c) & (m[bi].view(1, T) != 0)
+        allowed[bi] += (amb * (sc_ref[bi].abs() + tol)).sum(dim=1) / float(H * H)
+    assert n_checked > 0 or float(m.sum()) == 0
+    diff = (sim.cpu() - sim_ref).abs()
+    assert bool((diff <= allowed + 1e-2 * sim_ref.abs() * (mode == "bf16")).all()), (diff.max(), allowed.max())
+    # top-k: exact wherever adjacent reference scores are more than 1e-3 apart
+    score, idx = matching_templates(src.to(DEV), tar.to(DEV), None, mask.to(DEV), topk=k, mode=mode)
+    assert score.dtype == torch.float32 and idx.dtype == torch.int64
+    sref, iref = torch.topk(sim_ref, k, dim=1)
+    full = torch.sort(sim_ref, dim=1, descending=True).values
+    slack = allowed.max(dim=1).values
+    for bi in range(B):
+        gaps = full[bi, :-1] - full[bi, 1:] if N > 1 else torch.ones(1)
+        for j in range(k):
+            left = gaps[j - 1] > 1e-3 + 2 * slack[bi] if j > 0 else True
+            right = gaps[j] > 1e-3 + 2 * slack[bi] if j < N - 1 else True
+            if left and right:
+                assert int(idx[bi, j]) == int(iref[bi, j]), (bi, j, idx[bi].tolist(), iref[bi].tolist())
+        assert bool(((score[bi].cpu() - sref[bi]).abs() <= slack[bi] + 1e-2 * sref[bi].abs() * (mode == "bf16")).all())
+    return sim
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("mode", ["bf16", "fp32", "bf16x3"])
+@pytest.mark.parametrize("name", ["small", "medium", "bern", "ones", "allmasked", "identical"])
+def test_matching_golden(name, mode, cluster):
+    g = load(f"match_{name}.npz")
+    src, tar = torch.from_numpy(g["src"]), torch.from_numpy(g["tar"])
+    mask = torch.from_numpy(g["mask"]).float()
+    sim = _check_match(src, tar, mask, int(g["topk"]), mode, cluster)
+    if mode == "fp32":                       # against the reference's own output, fp32-mode tolerance
+        np.testing.assert_allclose(sim.cpu().numpy(), g["sim_avg"], rtol=0, atol=MODE_TOL[mode])
+    if name == "allmasked":
+        assert float(sim.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("B,N,C,H,mode", [
+    (2, 5, 128, 16, "bf16"),      # native patch grid (T = 256): one 2-CTA tile per (b, n)
+    (2, 5, 128, 16, "fp32"),
+    (1, 3, 384, 32, "bf16"),      # north-star grid (T = 1024): 4 x 4 tiles per (b, n)
+    (1, 3, 64, 32, "fp32"),
+    (3, 4, 40, 12, "bf16"),       # T = 144: ragged tiles, K padding 40 -> 64
+    (1, 7, 1024, 16, "bf16"),     # C = 1024 (16 k-blocks)
+])
+def test_matching_vs_oracle(B, N, C, H, mode, cluster):
+    src, tar, _ = synth.planted_match_inputs(B, N, C, H, seed=11)
+    mask = synth.disc_mask(B) if H != 12 else synth.bernoulli_mask(B, 224, 0.7, 3)
+    _check_match(src, tar, mask, min(5, N), mode, cluster)
+
+
+def test_matching_shared_bank_and_chunking(monkeypatch):
+    """A TemplateBank shared through bank_index, an expanded (stride-0) batch view, and detection
+    chunking under a tiny workspace limit all give the same scores as dense per-detection banks."""
+    from picopose_b200 import matching as M
+    banks, tar, obj, top1 = synth.shared_bank_inputs(2, 6, 64, 8, B=5, seed=4)
+    mask = synth.disc_mask(5)
+    dense = banks[obj]                                               # (5,6,64,8,8) copies, like run_test.py:161-162
+    ref = M.template_scores(dense.to(DEV), tar.to(DEV), mask.to(DEV))
+    bank = M.TemplateBank.from_features(banks.to(DEV))
+    got = M.template_scores(bank, tar.to(DEV), mask.to(DEV), bank_index=obj.to(DEV))
+    assert torch.equal(ref, got)
+    monkeypatch.setattr(M, "_WORKSPACE_LIMIT", 1)                    # forces one detection per launch
+    got2 = M.template_scores(bank, tar.to(DEV), mask.to(DEV), bank_index=obj.to(DEV))
+    assert torch.equal(ref, got2)
+    one = banks[:1].to(DEV).expand(5, -1, -1, -1, -1)                # stride-0 batch view of one bank
+    got3 = M.template_scores(one, tar.to(DEV), mask.to(DEV))
+    ref3 = M.template_scores(banks[:1].to(DEV).repeat(5, 1, 1, 1, 1), tar.to(DEV), mask.to(DEV))
+    assert torch.equal(ref3, got3)
+    assert torch.equal(ref.argmax(dim=1).cpu(), top1)
+
+
+def test_matching_config2_properties():
+    """BASELINE config 2 at full size (1 x 162 x 1024 x 32^2): the planted ranking is recovered in both
+    arithmetic modes, both CTA groupings agree bit for bit, and reruns are deterministic."""
+    from picopose_b200 import matching as M
+    src, tar, planted = synth.planted_match_inputs(1, 162, 1024, 32, seed=0)
+    mask = synth.disc_mask(1).to(DEV)
+    src, tar = src.to(DEV), tar.to(DEV)
+    bank = M.TemplateBank.from_features(src, "bf16")
+    s1 = M.template_scores(bank, tar, mask, cluster=1)
+    s2 = M.template_scores(bank, tar, mask, cluster=2)
+    s2b = M.template_scores(bank, tar, mask, cluster=2)
+    _lib.check_device_faults()
+    assert torch.equal(s1, s2) and torch.equal(s2, s2b)
+    score, idx = M.matching_templates(bank, tar, None, mask, topk=5)
+    assert idx[0].tolist() == planted[0, :5].tolist()
+    assert bool((score[0, :-1] - score[0, 1:] > 1e-3).all())
+    sf = M.template_scores(src, tar, mask, mode="bf16x3")
+    np.testing.assert_allclose(s2.cpu().numpy(), sf.cpu().numpy(), rtol=1e-2, atol=2e-3)
+    assert M.topk_scores(sf, 5)[1][0].tolist() == planted[0, :5].tolist()
+
+
+def test_matching_config1_vs_oracle():
+    """BASELINE config 1 (1 x 42 x 384 x 32^2) in full against the CPU oracle."""
+    src, tar, planted = synth.planted_match_inputs(1, 42, 384, 32, seed=0)
+    mask = synth.disc_mask(1)
+    ref = OM.template_scores(src, tar, mask, want_indices=True)
+    for mode in ("bf16", "fp32"):
+        _check_match(src, tar, mask, 5, mode, 0, ref=ref)
+
+
+@pytest.mark.parametrize("name", ["small", "medium"])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_similarity_volume_golden(name, mode):
+    from picopose_b200.matching import matching_features_similarity
+    g = load(f"sim_{name}.npz")
+    out = matching_features_similarity(cuda(g["src"]), cuda(g["tar"]), cuda(g["src_mask"], torch.float32),
+                                       torch.ones(1, device=DEV), mode=mode)
+    _lib.check_device_faults()
+    assert tuple(out.shape) == g["out"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=0, atol=MODE_TOL[mode])
+
+
+def test_similarity_volume_native_size():
+    from picopose_b200.matching import matching_features_similarity
+    gen = torch.Generator().manual_seed(2)
+    src = torch.randn(4, 1024, 16, 16, generator=gen)
+    tar = torch.randn(4, 1024, 16, 16, generator=gen)
+    sm = synth.bernoulli_mask(4, 224, 0.7, 8)
+    ref = OM.similarity_volume(src, tar, sm)
+    out = matching_features_similarity(src.to(DEV), tar.to(DEV), sm.to(DEV), None, mode="fp32")
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
+    out = matching_features_similarity(src.to(DEV), tar.to(DEV), sm.to(DEV), None, mode="bf16")
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=4e-3)
+
+
+def test_topk_matches_torch():
+    from picopose_b200.matching import topk_scores
+    gen = torch.Generator().manual_seed(6)
+    s = torch.randn(9, 642, generator=gen).to(DEV)
+    score, idx = topk_scores(s, 5)
+    rs, ri = torch.topk(s, 5, dim=1)
+    assert torch.equal(score, rs) and torch.equal(idx, ri)
+    score, idx = topk_scores(s, 642)
+    assert torch.equal(score, torch.sort(s, dim=1, descending=True).values)
+    with pytest.raises(RuntimeError):
+        topk_scores(s, 643)
