@@ -51,6 +51,11 @@ PP_API int pp_version(void);
 PP_API const char* pp_last_error(void);
 /* Reads and clears the device-side fault flag (synchronises the device). 0 = no fault. */
 PP_API int pp_check_device_faults(void);
+/* Number of kernels this library has launched in this process (measurement aid). */
+PP_API long long pp_launch_count(void);
+/* Measurement aid: the next tensor-core GEMM launched from this thread records `start_event` right
+ * before and `stop_event` right after itself on its stream (both cudaEvent_t; pass NULLs to cancel). */
+PP_API void pp_profile_gemm_events(void* start_event, void* stop_event);
 
 /* ------------------------------------------------------------------------------------------
  * Stage 3 -- correlation-window lookup.

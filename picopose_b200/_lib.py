@@ -22,6 +22,8 @@ SIGNATURES = {
     "pp_version": (_i, []),
     "pp_last_error": (C.c_char_p, []),
     "pp_check_device_faults": (_i, []),
+    "pp_launch_count": (C.c_longlong, []),
+    "pp_profile_gemm_events": (None, [_vp, _vp]),
     "pp_corr_lookup": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pp_bilinear_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_match_kp": (_i, [_i, _i]),

@@ -1,6 +1,7 @@
 // C-ABI plumbing of libpicopose_b200: error reporting, device gate, fault read-back.
 #include "pp_common.cuh"
 
+#include <atomic>
 #include <cstring>
 
 namespace pp {
@@ -20,6 +21,18 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+bool take_profile_events(cudaEvent_t* start, cudaEvent_t* stop) {
+    if (!g_prof_start || !g_prof_stop) return false;
+    *start = g_prof_start;
+    *stop = g_prof_stop;
+    g_prof_start = g_prof_stop = nullptr;
+    return true;
 }
 
 static int g_sm_count[64];
@@ -63,6 +76,13 @@ int read_fault_record(int* out5);
 }  // namespace pp
 
 extern "C" int pp_version(void) { return PP_VERSION; }
+
+extern "C" long long pp_launch_count(void) { return pp::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" void pp_profile_gemm_events(void* start_event, void* stop_event) {
+    pp::g_prof_start = static_cast<cudaEvent_t>(start_event);
+    pp::g_prof_stop = static_cast<cudaEvent_t>(stop_event);
+}
 
 extern "C" const char* pp_last_error(void) { return pp::g_err; }
 

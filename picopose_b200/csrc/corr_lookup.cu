@@ -244,7 +244,7 @@ template <int RT>
 static int launch_lookup(const LookupParams& p, int warps_per_block, size_t smem, int grid, cudaStream_t st) {
     PP_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     corr_lookup_kernel<RT><<<grid, warps_per_block * 32, smem, st>>>(p);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }
 
@@ -322,6 +322,6 @@ extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, i
     if (grid_dim > cap) grid_dim = cap;
     bilinear_sample_kernel<<<grid_dim, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         feat, grid, N, C, Hf, Wf, Ho, Wo, grid_chw, align_corners, scale, out);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }

@@ -72,7 +72,7 @@ extern "C" int pp_init_correspondences(const float* Ms, const float* tem_mask, i
     const int total = B * h * w;
     init_corr_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(Ms, tem_mask, B, Hm, Wm, h,
                                                                                        w, flow, certainty);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }
 
@@ -89,6 +89,6 @@ extern "C" int pp_stage3_correspondences(const float* flow, const float* certain
     stage3_corr_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         flow, certainty, B, H, W, threshold, reinterpret_cast<long long*>(tar_pts),
         reinterpret_cast<long long*>(src_pts));
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }

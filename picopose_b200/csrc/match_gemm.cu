@@ -342,7 +342,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    const bool prof = take_profile_events(&ev0, &ev1);
+    if (prof) PP_CUDA(cudaEventRecord(ev0, st));
     PP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    if (prof) PP_CUDA(cudaEventRecord(ev1, st));
+    count_launch();
     return PP_OK;
 }
 

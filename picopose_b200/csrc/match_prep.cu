@@ -135,7 +135,7 @@ template <int NCHUNK>
 static int launch_prepare(dim3 grid, cudaStream_t st, const float* feats, int C, int P, int Kp, int nseg, int nparts,
                           int is_query, __nv_bfloat16* prep) {
     match_prepare_kernel<NCHUNK><<<grid, PREP_THREADS, 0, st>>>(feats, C, P, Kp, nseg, nparts, is_query, prep);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }
 

@@ -140,14 +140,14 @@ extern "C" int pp_match_scores(const void* q_prep, const void* bank_prep, int64_
     unsigned long long* colkey = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(rowkey) + keys);
 
     resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(tar_mask, B, Hm, Wm, H, W, mrow);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys, st));
     if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, mrow, rowkey, colkey, nullptr,
                                 cluster, st))
         return rc;
     finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, mrow, N, T, 1.0f / (float)(H * H),
                                                                       sim_avg, score_t2s, idx_t2s, idx_s2t);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }
 
@@ -165,7 +165,7 @@ extern "C" int pp_topk(const float* scores, int B, int N, int k, int64_t idx_off
         PP_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, N, k, (long long)idx_offset, out_score,
                                                                     reinterpret_cast<long long*>(out_idx));
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }
 
@@ -194,13 +194,13 @@ extern "C" int pp_match_similarity(const void* q_prep, const void* s_prep, const
     float* mcol = reinterpret_cast<float*>(ws);
     float* sim = reinterpret_cast<float*>(ws + align_up((size_t)B * T * sizeof(float), 256));
     resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(src_mask, B, Hm, Wm, H, W, mcol);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     // one "view" per detection: banks == detections, N = 1
     if (int rc = run_match_gemm(1, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, sim, cluster, st))
         return rc;
     const long long total = (long long)B * T * T;
     int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
     similarity_layout_kernel<<<grid, 256, 0, st>>>(sim, mcol, B, H, W, out);
-    PP_CUDA(cudaGetLastError());
+    PP_LAUNCHED();
     return PP_OK;
 }

@@ -28,6 +28,17 @@ int fail(int code, const char* fmt, ...);
                               cudaGetErrorString(e__), __FILE__, __LINE__);                      \
     } while (0)
 
+// Kernel-launch accounting (pp_launch_count) and the optional event pair recorded around the next
+// tensor-core GEMM launch (pp_profile_gemm_events), used by bench.py for the roofline figure.
+void count_launch();
+bool take_profile_events(cudaEvent_t* start, cudaEvent_t* stop);
+
+#define PP_LAUNCHED()                 \
+    do {                              \
+        PP_CUDA(cudaGetLastError());  \
+        ::pp::count_launch();         \
+    } while (0)
+
 // Verifies the current device is sm_100 (cached per device).
 int require_sm100();
 int sm_count();
