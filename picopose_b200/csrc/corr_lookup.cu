@@ -254,6 +254,7 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
                               const float* flow, int B, int H, int W, int radius, float* out, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (B == 0) return PP_OK;  // empty batch: nothing to do (pointers of empty tensors may be null)
     PP_CHECK_ARG(pyr_ptrs && pyr_h && pyr_w && flow && out, "pp_corr_lookup: null pointer");
     PP_CHECK_ARG(L >= 1 && L <= LOOKUP_MAX_LEVELS, "pp_corr_lookup: 1 <= levels <= %d (got %d)", LOOKUP_MAX_LEVELS, L);
     PP_CHECK_ARG(radius >= 0 && radius <= LOOKUP_MAX_RADIUS, "pp_corr_lookup: 0 <= radius <= %d (got %d)",
@@ -313,6 +314,7 @@ extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, i
                                   int Wo, int grid_chw, int align_corners, int scale, float* out, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (N == 0) return PP_OK;
     PP_CHECK_ARG(feat && grid && out, "pp_bilinear_sample: null pointer");
     PP_CHECK_ARG(N >= 0 && C > 0 && Hf > 0 && Wf > 0 && Ho > 0 && Wo > 0, "pp_bilinear_sample: bad shape");
     if (N == 0) return PP_OK;

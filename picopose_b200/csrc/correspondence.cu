@@ -59,6 +59,7 @@ extern "C" int pp_init_correspondences(const float* Ms, const float* tem_mask, i
                                        float* flow, float* certainty, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (B == 0) return PP_OK;
     PP_CHECK_ARG(Ms && tem_mask && flow && certainty, "pp_init_correspondences: null pointer");
     PP_CHECK_ARG(Hm == Wm, "pp_init_correspondences: mask must be square (reference asserts H == W), got %dx%d", Hm, Wm);
     PP_CHECK_ARG(B >= 0 && h > 0 && w > 0 && Hm >= h, "pp_init_correspondences: bad shape");
@@ -80,6 +81,7 @@ extern "C" int pp_stage3_correspondences(const float* flow, const float* certain
                                          float threshold, int64_t* tar_pts, int64_t* src_pts, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (B == 0) return PP_OK;
     PP_CHECK_ARG(flow && certainty && tar_pts && src_pts, "pp_stage3_correspondences: null pointer");
     PP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "pp_stage3_correspondences: bad shape");
     if (B == 0) return PP_OK;

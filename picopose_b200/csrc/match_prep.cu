@@ -151,6 +151,7 @@ extern "C" int pp_match_prepare(const float* feats, int64_t G, int C, int P, int
                                 void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (G == 0) return PP_OK;
     PP_CHECK_ARG(feats && prepared, "pp_match_prepare: null pointer");
     PP_CHECK_ARG(mode >= 0 && mode <= 2, "pp_match_prepare: unknown mode %d", mode);
     PP_CHECK_ARG(C > 0 && C % 8 == 0, "pp_match_prepare: feature dim must be a positive multiple of 8 (got %d)", C);

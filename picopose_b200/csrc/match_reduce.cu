@@ -122,6 +122,7 @@ extern "C" int pp_match_scores(const void* q_prep, const void* bank_prep, int64_
                                size_t workspace_bytes, int cluster, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (B == 0 || N == 0) return PP_OK;
     PP_CHECK_ARG(q_prep && bank_prep && tar_mask && sim_avg, "pp_match_scores: null pointer");
     PP_CHECK_ARG(H == W, "pp_match_scores: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
     PP_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_scores: bad shape");
@@ -155,6 +156,7 @@ extern "C" int pp_topk(const float* scores, int B, int N, int k, int64_t idx_off
                        int64_t* out_idx, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (B == 0 || k == 0) return PP_OK;
     PP_CHECK_ARG(scores && out_score && out_idx, "pp_topk: null pointer");
     // torch.topk raises when k exceeds the dimension ("selected index k out of range")
     PP_CHECK_ARG(k >= 0 && k <= N, "pp_topk: selected index k out of range (k=%d, N=%d)", k, N);
@@ -179,6 +181,7 @@ extern "C" int pp_match_similarity(const void* q_prep, const void* s_prep, const
                                    int cluster, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
+    if (B == 0) return PP_OK;
     PP_CHECK_ARG(q_prep && s_prep && src_mask && out, "pp_match_similarity: null pointer");
     PP_CHECK_ARG(H == W, "pp_match_similarity: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
     PP_CHECK_ARG(B >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_similarity: bad shape");

@@ -45,12 +45,13 @@ def merge_topk(local_score: torch.Tensor, local_idx: torch.Tensor, k: int, group
     if world == 1:
         all_s, all_i = local_score, local_idx
     else:
-        gs = torch.empty(world, B, k, dtype=local_score.dtype, device=local_score.device)
-        gi = torch.empty(world, B, k, dtype=local_idx.dtype, device=local_idx.device)
+        # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+        gs = torch.empty(world * B, k, dtype=local_score.dtype, device=local_score.device)
+        gi = torch.empty(world * B, k, dtype=local_idx.dtype, device=local_idx.device)
         dist.all_gather_into_tensor(gs, local_score, group=group)
         dist.all_gather_into_tensor(gi, local_idx, group=group)
-        all_s = gs.permute(1, 0, 2).reshape(B, world * k)
-        all_i = gi.permute(1, 0, 2).reshape(B, world * k)
+        all_s = gs.view(world, B, k).permute(1, 0, 2).reshape(B, world * k)
+        all_i = gi.view(world, B, k).permute(1, 0, 2).reshape(B, world * k)
     select = select or _select_cuda
     val, pos = select(all_s.contiguous(), k)
     return val, torch.gather(all_i, 1, pos)

@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: the reference-facing Python surface, argument checking, the overlay
+mechanism, sharding arithmetic and the synthetic generators."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_public_surface_mirrors_the_reference():
+    import inspect
+    from picopose_b200 import corr_lookup, correspondence, matching
+    assert list(inspect.signature(matching.matching_templates).parameters)[:5] == \
+        ["src_feats", "tar_feat", "src_masks", "tar_mask", "topk"]
+    assert inspect.signature(matching.matching_templates).parameters["topk"].default == 5
+    assert list(inspect.signature(matching.matching_features_similarity).parameters)[:4] == \
+        ["src_feat", "tar_feat", "src_mask", "tar_mask"]
+    sig = inspect.signature(corr_lookup.bilinear_sample).parameters
+    assert [sig[k].default for k in ("mode", "padding_mode", "align_corners", "scale")] == ["bilinear", "zeros", False, True]
+    mod = corr_lookup.CorrLookup()
+    assert isinstance(mod, torch.nn.Module) and mod.r == 4 and mod.align_corners is True
+    assert len(list(mod.parameters())) == 0 and len(mod.state_dict()) == 0      # checkpoints unaffected
+    assert inspect.signature(correspondence.compute_init_correspondences).parameters["size"].default == (16, 16)
+    assert inspect.signature(correspondence.compute_stage3_correspondences).parameters["threshold"].default == 0.5
+
+
+def test_coords_grid_matches_golden():
+    from picopose_b200.corr_lookup import coords_grid
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bilinear.npz"))
+    out = coords_grid(2, torch.arange(0, 7), torch.arange(0, 5))
+    np.testing.assert_array_equal(out.numpy(), g["coords"])
+    assert out.dtype == torch.float32
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    from picopose_b200 import corr_lookup, correspondence, matching
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        matching.matching_templates(torch.zeros(1, 2, 8, 4, 4), torch.zeros(1, 8, 4, 4), None, torch.zeros(1, 224, 224))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        matching.matching_features_similarity(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4), torch.zeros(1, 224, 224), None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        corr_lookup.CorrLookup(2)([torch.zeros(16, 1, 4, 4)], torch.zeros(1, 2, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        correspondence.compute_stage3_correspondences(torch.zeros(1, 2, 4, 4), torch.zeros(1, 1, 4, 4))
+    with pytest.raises(NotImplementedError):
+        corr_lookup.bilinear_sample(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2), mode="nearest")
+
+
+def test_overlay_shadows_exactly_three_reference_modules(tmp_path):
+    """Namespace-package overlay: a fake reference tree with utils/{matching,torch_utils}.py; after
+    install_overlay, utils.matching comes from the overlay and utils.torch_utils still from the 'reference'."""
+    ref = tmp_path / "ref"
+    (ref / "utils").mkdir(parents=True)
+    (ref / "utils" / "matching.py").write_text("ORIGIN = 'reference'\n")
+    (ref / "utils" / "torch_utils.py").write_text("ORIGIN = 'reference'\n")
+    from picopose_b200 import launcher
+    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k == "utils" or k.startswith("utils.")}
+    try:
+        launcher.install_overlay(str(ref))
+        for k in list(sys.modules):
+            if k == "utils" or k.startswith("utils."):
+                del sys.modules[k]
+        m = importlib.import_module("utils.matching")
+        t = importlib.import_module("utils.torch_utils")
+        c = importlib.import_module("utils.corr_lookup")
+        assert m.__file__.startswith(launcher.OVERLAY) and hasattr(m, "matching_templates")
+        assert c.__file__.startswith(launcher.OVERLAY) and hasattr(c, "CorrLookup")
+        assert t.ORIGIN == "reference"
+    finally:
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k == "utils" or k.startswith("utils."):
+                del sys.modules[k]
+        sys.modules.update(saved_mods)
+
+
+def test_shard_range_covers_all_views():
+    from picopose_b200.sharded import shard_range
+    for n in (42, 162, 642, 5, 3):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert [shard_range(642, r, 4) for r in range(4)] == [(0, 161), (161, 322), (322, 482), (482, 642)]
+
+
+def test_planted_generator_is_seeded_and_ranked():
+    from oracle import matching_oracle as OM
+    from picopose_b200 import synth
+    a = synth.planted_match_inputs(2, 9, 32, 8, seed=3)
+    b = synth.planted_match_inputs(2, 9, 32, 8, seed=3)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    src, tar, planted = a
+    score, idx = OM.matching_templates(src, tar, None, synth.disc_mask(2), topk=5)
+    assert idx.tolist() == planted[:, :5].tolist()
+    assert bool((score[:, :-1] - score[:, 1:] > 1e-3).all())       # gaps far above the 1e-3 exactness band
+    m = synth.disc_mask(1)
+    assert m[0, 0, 0] == 0 and 0.55 < float(m.mean()) < 0.7
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    import json
+    import subprocess
+    env = dict(os.environ, PICOPOSE_BENCH_SMALL="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, env=env, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["metric"] == "detections/sec"
