@@ -82,31 +82,32 @@ PP_API int pp_bilinear_sample(const float* feat, const float* grid, int N, int C
 /* ------------------------------------------------------------------------------------------
  * Stage 1 -- query-vs-template matching.
  *
- * Operand preparation ("prologue"): L2-normalise over C (eps 1e-12, F.normalize), cast to
- * bf16 (split into terms for the fp32 modes) and lay out K-major for the tensor cores.
- *   feats : (G, C, P) fp32, P = H*W contiguous      -> prepared : (G, P, Kp) bf16,
+ * Operand preparation ("prologue"): cast to bf16 (split into terms for the fp32 modes), lay out
+ * K-major for the tensor cores and compute the inverse L2 norm over C per patch
+ * (1 / max(||x||, 1e-12), F.normalize's rule); the contraction's epilogue applies the two inverse norms.
+ *   feats : (G, C, P) fp32, P = H*W contiguous      -> prepared : (G, P, Kp) bf16, rnorm : (G, P) fp32
  *   Kp = pp_match_kp(C, mode).  is_query selects which side of the split-term pairing is written.
  * Replaces the F.normalize + rearrange lines utils/matching.py:13-14,18-19,40-41,43-44.
  * ------------------------------------------------------------------------------------------ */
 PP_API int pp_match_kp(int C, int mode);
 PP_API int pp_match_prepare(const float* feats, int64_t G, int C, int P, int mode, int is_query,
-                     void* prepared, void* stream);
+                     void* prepared, float* rnorm, void* stream);
 
 /* Bytes of scratch pp_match_scores needs for (B detections, N views, T = H*W patches). */
 PP_API size_t pp_match_scores_workspace(int B, int N, int T);
 
 /* Fused similarity GEMM + bidirectional max/argmax + validity-masked mean.
  * Replaces utils/matching.py:38-39,47-67 (the sim tensor never reaches HBM).
- *   q_prep    : (B, T, Kp) bf16   prepared query features
- *   bank_prep : (n_banks, N, T, Kp) bf16 prepared template banks
+ *   q_prep, q_rnorm       : (B, T, Kp) bf16 / (B, T) fp32            prepared query features
+ *   bank_prep, bank_rnorm : (n_banks, N, T, Kp) bf16 / (n_banks, N, T) fp32   prepared template banks
  *   bank_of_det : (B,) int32 device array, bank used by detection b; NULL = identity (n_banks == B)
  *   tar_mask  : (B, Hm, Wm) fp32 0/1 query masks (nearest-resized to H x W as F.interpolate does)
  *   sim_avg   : (B, N) fp32 out
  *   optional outs (NULL to skip): score_t2s (B,N,T) fp32, idx_t2s (B,N,T) int32, idx_s2t (B,N,T) int32
  *   cluster   : 0 = default, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
  */
-PP_API int pp_match_scores(const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
-                    const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
+PP_API int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* bank_prep, const float* bank_rnorm,
+                    int64_t n_banks, const int32_t* bank_of_det, const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
                     float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
                     void* workspace, size_t workspace_bytes, int cluster, void* stream);
 
@@ -116,11 +117,12 @@ PP_API int pp_topk(const float* scores, int B, int N, int k, int64_t idx_offset,
             float* out_score, int64_t* out_idx, void* stream);
 
 /* Stage-2 input volume.  Replaces matching_features_similarity, utils/matching.py:6-26.
- *   q_prep, s_prep : (B, T, Kp) prepared query / template features; src_mask (B,Hm,Wm) fp32
+ *   q_prep/q_rnorm, s_prep/s_rnorm : (B, T, Kp) / (B, T) prepared query / template features; src_mask (B,Hm,Wm) fp32
  *   out : (B, S, H, W) fp32 with out[b,s,h,w] = max(0, sim[b, t = w*H+h, s] * mask_s)
  *   workspace >= pp_match_similarity_workspace(B, T) bytes. */
 PP_API size_t pp_match_similarity_workspace(int B, int T);
-PP_API int pp_match_similarity(const void* q_prep, const void* s_prep, const float* src_mask,
+PP_API int pp_match_similarity(const void* q_prep, const float* q_rnorm, const void* s_prep, const float* s_rnorm,
+                        const float* src_mask,
                         int B, int H, int W, int Kp, int Hm, int Wm, float* out,
                         void* workspace, size_t workspace_bytes, int cluster, void* stream);
 

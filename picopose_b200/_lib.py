@@ -27,12 +27,13 @@ SIGNATURES = {
     "pp_corr_lookup": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pp_bilinear_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_match_kp": (_i, [_i, _i]),
-    "pp_match_prepare": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "pp_match_prepare": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_match_scores_workspace": (_sz, [_i, _i, _i]),
-    "pp_match_scores": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "pp_match_scores": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz,
+                             _i, _vp]),
     "pp_topk": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
     "pp_match_similarity_workspace": (_sz, [_i, _i]),
-    "pp_match_similarity": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
+    "pp_match_similarity": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pp_init_correspondences": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_stage3_correspondences": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
 }

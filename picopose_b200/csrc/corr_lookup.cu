@@ -6,9 +6,10 @@
 // Kernel shape (HBM-bound gather):
 //   * one warp owns 32 consecutive queries (flat h*W+w) of one detection, so every output channel
 //     store is one coalesced 128-byte line in the reference's (B, L*D*D, H, W) layout;
-//   * per level the warp first stages, with 16-byte cp.async (zero-filled outside the map), the
-//     <= (D+2) x (D+2) footprint of each of its 32 windows into shared memory -- consecutive lanes
-//     fetch consecutive 16-byte pieces of a row, only pieces the window really touches;
+//   * the window is processed in bands of JB y-taps.  Per band the warp stages, with 16-byte
+//     cp.async (zero-filled outside the map), the <= (JB+2) x (D+2) footprint of each of its 32
+//     windows into shared memory -- consecutive lanes fetch consecutive 16-byte pieces of a row and
+//     only pieces some tap really touches are requested;
 //   * then lane = query: each window sample gathers its 4 taps from shared memory.
 // Coordinates follow the reference's float arithmetic op by op (x*2/(W-1)-1 and grid_sample's
 // inverse, utils/corr_lookup.py:61-65 + ATen grid_sampler_unnormalize), so floor/weights agree.
@@ -31,8 +32,8 @@ struct LookupParams {
     int radius;
     int groups_per_b;  // ceil(HW / 32)
     int total_groups;
-    int nr_max, nv_max;  // staged rows / 16-byte pieces per row
-    int qstride;         // words between two queries' staging areas (odd -> spreads banks)
+    int nr_max, nv_max;  // generic kernel: staged rows / 16-byte pieces per row
+    int qstride;         // generic kernel: words between two queries' staging areas
 };
 
 // pixel coordinate -> (floor index, weight of the upper tap), replicating
@@ -60,18 +61,138 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int RT>  // RT > 0: compile-time radius, tap tables live in registers; RT == 0: runtime radius
-__global__ void __launch_bounds__(128) corr_lookup_kernel(const LookupParams p) {
+// ------------------------------------------------------------------------------------------------
+// Fast path: compile-time radius R, window processed in bands of JB y-taps, all levels 16-byte loadable.
+// ------------------------------------------------------------------------------------------------
+template <int R, int JB>
+struct LookupCfg {
+    static constexpr int D = 2 * R + 1;
+    static constexpr int NB = (D + JB - 1) / JB;      // bands
+    static constexpr int NRB = JB + 2;                // staged rows per band (floor jitter of +-1 included)
+    static constexpr int NV = (D + 5 + 3) / 4;        // 16-byte pieces per row: D+2 columns + 3 alignment slack
+    static constexpr int PITCH = NV * 4;              // words per staged row
+    static constexpr int QS = ((NRB * NV) | 1) * 4;   // words per query: odd number of 16-byte units (bank spread)
+    static constexpr int WARP_WORDS = 32 * QS + 64;   // + packed header (2 words per query)
+};
+
+template <int R, int JB>
+__global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupParams p) {
+    using Cfg = LookupCfg<R, JB>;
+    constexpr int D = Cfg::D, NB = Cfg::NB, NRB = Cfg::NRB, NV = Cfg::NV, PITCH = Cfg::PITCH, QS = Cfg::QS;
     extern __shared__ __align__(16) float smem[];
     const int warps_per_block = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int r = RT > 0 ? RT : p.radius;
-    const int D = 2 * r + 1;
-    constexpr int TAB = RT > 0 ? 2 * RT + 1 : 2 * LOOKUP_MAX_RADIUS + 1;
-    const int ND = RT > 0 ? TAB : D;  // compile-time trip count (full unroll) when the radius is templated
+    float* stage = smem + (size_t)warp * Cfg::WARP_WORDS;
+    int* hdr = reinterpret_cast<int*>(stage + 32 * QS);  // [2*q] = xs, [2*q+1] = y0 | pieces<<20 | rows<<26
 
-    // per-warp staging: 32 windows + a small header (origin of each window's footprint)
+    // work item = (query group, pyramid level): levels of one group run on different warps, which keeps the
+    // dependent chain per warp short when there are few queries (the native 16^2..64^2 ladder)
+    const int total_items = p.total_groups * p.L;
+    for (int item = blockIdx.x * warps_per_block + warp; item < total_items; item += gridDim.x * warps_per_block) {
+        const int g = item / p.L;
+        const int l = item - g * p.L;
+        const int b = g / p.groups_per_b;
+        const int hw0 = (g - b * p.groups_per_b) * 32;
+        const int hw = hw0 + lane;
+        const bool live = hw < p.HW;
+        const int hwc = live ? hw : p.HW - 1;
+        const int qh = hwc / p.W, qw = hwc - qh * p.W;
+        const float fx = __ldg(p.flow + ((size_t)b * 2 + 0) * p.HW + hwc);
+        const float fy = __ldg(p.flow + ((size_t)b * 2 + 1) * p.HW + hwc);
+        const float cx = __fadd_rn((float)qw, fx);  // coords_grid + flow, utils/corr_lookup.py:113
+        const float cy = __fadd_rn((float)qh, fy);
+        float* out_b = p.out + (size_t)b * p.L * D * D * p.HW;  // warp-uniform base, 32-bit offsets below
+        const int nq = min(32, p.HW - hw0);                     // live queries of this group
+
+        {
+            const int Hl = p.vh[l], Wl = p.vw[l];
+            const float inv = 1.0f / (float)(1 << l);  // exact: centroid / 2**l, utils/corr_lookup.py:125
+            const float lx = __fmul_rn(cx, inv), ly = __fmul_rn(cy, inv);
+            int xo[D], yo[D];
+            float xw[D], yw[D];
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                axis_tap(__fadd_rn(lx, (float)(a - R)), Wl, xo[a], xw[a]);
+                axis_tap(__fadd_rn(ly, (float)(a - R)), Hl, yo[a], yw[a]);
+            }
+            const int xs = xo[0] & ~3;                        // two's complement: rounds towards -inf
+            const int pieces = ((xo[D - 1] + 1 - xs) >> 2) + 1;  // 16-byte pieces per row some tap touches
+            // slice base of the group's first query; query ql of the group is ql slices further
+            const float* vol_g = p.vol[l] + ((size_t)b * p.HW + hw0) * ((size_t)Hl * Wl);
+            const uint32_t slice = (uint32_t)Hl * (uint32_t)Wl;
+
+#pragma unroll
+            for (int band = 0; band < NB; ++band) {
+                const int j0 = band * JB;
+                const int j1 = (j0 + JB < D) ? j0 + JB : D;  // compile-time after unrolling
+                const int yb = yo[j0];
+                const int rows = yo[j1 - 1] + 1 - yb + 1;
+                __syncwarp();  // previous band's readers are done with the staging area
+                hdr[2 * lane] = xs;
+                hdr[2 * lane + 1] = (yb + 8) | (pieces << 20) | (rows << 26);
+                __syncwarp();
+
+                // ---- cooperative staging: lane -> (query, row, piece), consecutive lanes = consecutive pieces ----
+                constexpr int PER_Q = NRB * NV;
+#pragma unroll 4
+                for (int i = lane; i < 32 * PER_Q; i += 32) {
+                    const int ql = i / PER_Q;          // constant divisors: mul/shift
+                    const int rem = i - ql * PER_Q;
+                    const int row = rem / NV;
+                    const int v = rem - row * NV;
+                    const int2 h = *reinterpret_cast<const int2*>(hdr + 2 * ql);
+                    if (row >= (h.y >> 26) || v >= ((h.y >> 20) & 63)) continue;  // not touched by any tap
+                    const int y = (h.y & 0xFFFFF) - 8 + row;
+                    const int x = h.x + 4 * v;
+                    float* dst = stage + ql * QS + (row * NV + v) * 4;
+                    if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl && ql < nq) {
+                        cp_async16(dst, vol_g + (size_t)ql * slice + (uint32_t)(y * Wl + x));
+                    } else {
+                        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                cp_async_wait_all();
+                __syncwarp();
+
+                // ---- lane = query: gather + separable 4-tap blend ----
+                if (live) {
+                    const float* win = stage + lane * QS;
+                    const uint32_t obase = (uint32_t)(l * D * D) * (uint32_t)p.HW + (uint32_t)hw;
+#pragma unroll
+                    for (int bb = 0; bb < JB; ++bb) {
+                        const int j = j0 + bb;
+                        if (j < j1) {
+                            const float wy1 = yw[j], wy0 = __fsub_rn(1.0f, wy1);
+                            const float* rowp = win + (yo[j] - yb) * PITCH - xs;
+#pragma unroll
+                            for (int a = 0; a < D; ++a) {
+                                const float* t0 = rowp + xo[a];
+                                const float wx1 = xw[a], wx0 = __fsub_rn(1.0f, wx1);
+                                const float h0 = fmaf(t0[1], wx1, t0[0] * wx0);
+                                const float h1 = fmaf(t0[PITCH + 1], wx1, t0[PITCH] * wx0);
+                                __stcs(out_b + (obase + (uint32_t)(a * D + j) * (uint32_t)p.HW), fmaf(h1, wy1, h0 * wy0));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic path: runtime radius (up to 16) and/or levels whose width is not a multiple of 4.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) corr_lookup_generic_kernel(const LookupParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int r = p.radius;
+    const int D = 2 * r + 1;
+    constexpr int TAB = 2 * LOOKUP_MAX_RADIUS + 1;
+
     float* stage = smem + (size_t)warp * (32 * p.qstride + 4 * 32);
     int* hdr = reinterpret_cast<int*>(stage + 32 * p.qstride);  // [0..31]=xs [32..63]=ymin [64..95]=xmax [96..127]=ymax
 
@@ -83,58 +204,53 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const LookupParams p) 
         const int qh = hwc / p.W, qw = hwc - qh * p.W;
         const float fx = __ldg(p.flow + ((size_t)b * 2 + 0) * p.HW + hwc);
         const float fy = __ldg(p.flow + ((size_t)b * 2 + 1) * p.HW + hwc);
-        const float cx = __fadd_rn((float)qw, fx);  // coords_grid + flow, utils/corr_lookup.py:113
+        const float cx = __fadd_rn((float)qw, fx);
         const float cy = __fadd_rn((float)qh, fy);
         float* out_q = p.out + (size_t)b * p.L * D * D * p.HW + hwc;
 
         for (int l = 0; l < p.L; ++l) {
             const int Hl = p.vh[l], Wl = p.vw[l];
-            const float inv = 1.0f / (float)(1 << l);  // exact: centroid / 2**l, utils/corr_lookup.py:125
+            const float inv = 1.0f / (float)(1 << l);
             const float lx = __fmul_rn(cx, inv), ly = __fmul_rn(cy, inv);
             int xo[TAB], yo[TAB];
             float xw[TAB], yw[TAB];
-#pragma unroll
-            for (int a = 0; a < ND; ++a) {
+            for (int a = 0; a < D; ++a) {
                 axis_tap(__fadd_rn(lx, (float)(a - r)), Wl, xo[a], xw[a]);
                 axis_tap(__fadd_rn(ly, (float)(a - r)), Hl, yo[a], yw[a]);
             }
             const int xmin = xo[0], xmax = xo[D - 1] + 1;
             const int ymin = yo[0], ymax = yo[D - 1] + 1;
             const bool vec = p.vec_ok[l] != 0;
-            const int xs = vec ? (xmin & ~3) : xmin;  // two's complement: rounds towards -inf
-            __syncwarp();                              // previous level's readers are done
+            const int xs = vec ? (xmin & ~3) : xmin;
+            __syncwarp();
             hdr[lane] = xs;
             hdr[32 + lane] = ymin;
             hdr[64 + lane] = xmax;
             hdr[96 + lane] = ymax;
             __syncwarp();
 
-            // ---- cooperative staging -------------------------------------------------------
+            const int cols = p.nv_max * 4;
             if (vec) {
                 const int per_q = p.nr_max * p.nv_max;
-                const int total = 32 * per_q;
-                for (int i = lane; i < total; i += 32) {
+                for (int i = lane; i < 32 * per_q; i += 32) {
                     const int ql = i / per_q;
                     const int rem = i - ql * per_q;
                     const int row = rem / p.nv_max;
                     const int v = rem - row * p.nv_max;
                     const int y = hdr[32 + ql] + row;
                     const int x = hdr[ql] + 4 * v;
-                    if (y > hdr[96 + ql] || x > hdr[64 + ql]) continue;  // not touched by any tap
+                    if (y > hdr[96 + ql] || x > hdr[64 + ql]) continue;
                     float* dst = stage + ql * p.qstride + (row * p.nv_max + v) * 4;
                     const int qhw = (g - b * p.groups_per_b) * 32 + ql;
                     if (y >= 0 && y < Hl && x >= 0 && x < Wl && qhw < p.HW) {
-                        const size_t qq = (size_t)b * p.HW + qhw;
-                        cp_async16(dst, p.vol[l] + (qq * Hl + y) * Wl + x);
+                        cp_async16(dst, p.vol[l] + (((size_t)b * p.HW + qhw) * Hl + y) * Wl + x);
                     } else {
                         *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
             } else {
-                const int cols = p.nv_max * 4;
                 const int per_q = p.nr_max * cols;
-                const int total = 32 * per_q;
-                for (int i = lane; i < total; i += 32) {
+                for (int i = lane; i < 32 * per_q; i += 32) {
                     const int ql = i / per_q;
                     const int rem = i - ql * per_q;
                     const int row = rem / cols;
@@ -145,8 +261,7 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const LookupParams p) 
                     float* dst = stage + ql * p.qstride + row * cols + c;
                     const int qhw = (g - b * p.groups_per_b) * 32 + ql;
                     if (y >= 0 && y < Hl && x >= 0 && x < Wl && qhw < p.HW) {
-                        const size_t qq = (size_t)b * p.HW + qhw;
-                        cp_async4(dst, p.vol[l] + (qq * Hl + y) * Wl + x);
+                        cp_async4(dst, p.vol[l] + (((size_t)b * p.HW + qhw) * Hl + y) * Wl + x);
                     } else {
                         *dst = 0.f;
                     }
@@ -155,29 +270,18 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const LookupParams p) 
             cp_async_wait_all();
             __syncwarp();
 
-            // ---- lane = query: gather + 4-tap blend ------------------------------------------
             const float* win = stage + lane * p.qstride;
-            const int rowpitch = p.nv_max * 4;
             float* out_l = out_q + (size_t)l * D * D * p.HW;
             if (live) {
-#pragma unroll
-                for (int a = 0; a < ND; ++a) {
+                for (int a = 0; a < D; ++a) {
                     const int cxo = xo[a] - xs;
-                    const float wx1 = xw[a];
-                    const float wx0 = __fsub_rn(1.0f, wx1);
-#pragma unroll
-                    for (int bb = 0; bb < ND; ++bb) {
-                        const float* t0 = win + (yo[bb] - ymin) * rowpitch + cxo;
-                        const float wy1 = yw[bb];
-                        const float wy0 = __fsub_rn(1.0f, wy1);
-                        const float v00 = t0[0], v01 = t0[1];
-                        const float v10 = t0[rowpitch], v11 = t0[rowpitch + 1];
-                        // same association as ATen's grid_sampler: sum of value * (wx*wy)
-                        float acc = v00 * (wx0 * wy0);
-                        acc = fmaf(v01, wx1 * wy0, acc);
-                        acc = fmaf(v10, wx0 * wy1, acc);
-                        acc = fmaf(v11, wx1 * wy1, acc);
-                        __stcs(out_l + (size_t)(a * D + bb) * p.HW, acc);
+                    const float wx1 = xw[a], wx0 = __fsub_rn(1.0f, wx1);
+                    for (int bb = 0; bb < D; ++bb) {
+                        const float* t0 = win + (yo[bb] - ymin) * cols + cxo;
+                        const float wy1 = yw[bb], wy0 = __fsub_rn(1.0f, wy1);
+                        const float h0 = fmaf(t0[1], wx1, t0[0] * wx0);
+                        const float h1 = fmaf(t0[cols + 1], wx1, t0[cols] * wx0);
+                        __stcs(out_l + (size_t)(a * D + bb) * p.HW, fmaf(h1, wy1, h0 * wy0));
                     }
                 }
             }
@@ -240,10 +344,24 @@ __global__ void bilinear_sample_kernel(const float* __restrict__ feat, const flo
     }
 }
 
-template <int RT>
-static int launch_lookup(const LookupParams& p, int warps_per_block, size_t smem, int grid, cudaStream_t st) {
-    PP_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_lookup_kernel<RT><<<grid, warps_per_block * 32, smem, st>>>(p);
+static int grid_for(long long items, int wpb, size_t smem) {
+    int blocks_per_sm = (int)((227 * 1024) / (smem + 1024));
+    blocks_per_sm = blocks_per_sm < 1 ? 1 : (blocks_per_sm > 16 ? 16 : blocks_per_sm);
+    const long long want = (items + wpb - 1) / wpb;
+    const long long cap = (long long)sm_count() * blocks_per_sm * 4;  // grid-stride beyond 4 waves
+    return (int)(want < cap ? want : cap);
+}
+
+template <int R, int JB>
+static int launch_banded(const LookupParams& p, cudaStream_t st) {
+    using Cfg = LookupCfg<R, JB>;
+    const size_t per_warp = (size_t)Cfg::WARP_WORDS * sizeof(float);
+    // blocks of up to 4 warps, sized so that at least two blocks share an SM
+    int wpb = (int)((110 * 1024) / per_warp);
+    wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+    const size_t smem = per_warp * wpb;
+    PP_CUDA(cudaFuncSetAttribute(corr_lookup_banded_kernel<R, JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    corr_lookup_banded_kernel<R, JB><<<grid_for((long long)p.total_groups * p.L, wpb, smem), wpb * 32, smem, st>>>(p);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -259,18 +377,21 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
     PP_CHECK_ARG(L >= 1 && L <= LOOKUP_MAX_LEVELS, "pp_corr_lookup: 1 <= levels <= %d (got %d)", LOOKUP_MAX_LEVELS, L);
     PP_CHECK_ARG(radius >= 0 && radius <= LOOKUP_MAX_RADIUS, "pp_corr_lookup: 0 <= radius <= %d (got %d)",
                  LOOKUP_MAX_RADIUS, radius);
-    PP_CHECK_ARG(B >= 0 && H > 0 && W > 0, "pp_corr_lookup: bad flow shape (%d,2,%d,%d)", B, H, W);
-    if (B == 0) return PP_OK;
+    PP_CHECK_ARG(B > 0 && H > 0 && W > 0, "pp_corr_lookup: bad flow shape (%d,2,%d,%d)", B, H, W);
     LookupParams p{};
     p.L = L;
+    bool all_vec = true;
     for (int l = 0; l < L; ++l) {
         PP_CHECK_ARG(pyr_ptrs[l] && pyr_h[l] > 0 && pyr_w[l] > 0, "pp_corr_lookup: bad pyramid level %d", l);
+        PP_CHECK_ARG((long long)pyr_h[l] * pyr_w[l] < (1LL << 31), "pp_corr_lookup: level %d too large", l);
         p.vol[l] = static_cast<const float*>(pyr_ptrs[l]);
         p.vh[l] = pyr_h[l];
         p.vw[l] = pyr_w[l];
         p.vec_ok[l] = (pyr_w[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(pyr_ptrs[l]) & 15) == 0);
+        all_vec = all_vec && p.vec_ok[l];
     }
     const int D = 2 * radius + 1;
+    PP_CHECK_ARG((long long)L * D * D * H * W < (1LL << 31), "pp_corr_lookup: output per detection exceeds 2^31 elements");
     p.flow = flow;
     p.out = out;
     p.B = B;
@@ -280,34 +401,34 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
     p.radius = radius;
     p.groups_per_b = (p.HW + 31) / 32;
     p.total_groups = B * p.groups_per_b;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (all_vec) {
+        // band height per radius: keeps ~12-25 KB of staging per warp so 8-16 warps share an SM
+        switch (radius) {
+            case 1: return launch_banded<1, 3>(p, st);
+            case 2: return launch_banded<2, 5>(p, st);
+            case 3: return launch_banded<3, 4>(p, st);
+            case 4: return launch_banded<4, 5>(p, st);
+            case 5: return launch_banded<5, 4>(p, st);
+            case 6: return launch_banded<6, 5>(p, st);
+            case 7: return launch_banded<7, 5>(p, st);
+            case 8: return launch_banded<8, 6>(p, st);
+            default: break;
+        }
+    }
+    // generic kernel: whole window staged at once
     p.nr_max = D + 2;
     p.nv_max = (D + 2 + 3 + 3) / 4;
-    // every window's base must stay 16-byte aligned for cp.async; an odd number of 16-byte units
-    // per window makes consecutive lanes walk through all eight 4-bank groups.
     p.qstride = ((p.nr_max * p.nv_max) | 1) * 4;
     const size_t per_warp = (size_t)(32 * p.qstride + 4 * 32) * sizeof(float);
-    // as many warps per block as fit in ~110 KB (two blocks per SM), at most 4
     int wpb = (int)((110 * 1024) / per_warp);
     wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
     const size_t smem = per_warp * wpb;
     PP_CHECK_ARG(smem <= 227 * 1024, "pp_corr_lookup: radius %d needs %zu B of shared memory", radius, smem);
-    int blocks_per_sm = (int)((227 * 1024) / (smem + 1024));
-    blocks_per_sm = blocks_per_sm < 1 ? 1 : (blocks_per_sm > 8 ? 8 : blocks_per_sm);
-    long long want = ((long long)p.total_groups + wpb - 1) / wpb;
-    long long cap = (long long)sm_count() * blocks_per_sm * 4;  // grid-stride beyond 4 waves
-    int grid = (int)(want < cap ? want : cap);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (radius) {
-        case 1: return launch_lookup<1>(p, wpb, smem, grid, st);
-        case 2: return launch_lookup<2>(p, wpb, smem, grid, st);
-        case 3: return launch_lookup<3>(p, wpb, smem, grid, st);
-        case 4: return launch_lookup<4>(p, wpb, smem, grid, st);
-        case 5: return launch_lookup<5>(p, wpb, smem, grid, st);
-        case 6: return launch_lookup<6>(p, wpb, smem, grid, st);
-        case 7: return launch_lookup<7>(p, wpb, smem, grid, st);
-        case 8: return launch_lookup<8>(p, wpb, smem, grid, st);
-        default: return launch_lookup<0>(p, wpb, smem, grid, st);
-    }
+    PP_CUDA(cudaFuncSetAttribute(corr_lookup_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    corr_lookup_generic_kernel<<<grid_for(p.total_groups, wpb, smem), wpb * 32, smem, st>>>(p);
+    PP_LAUNCHED();
+    return PP_OK;
 }
 
 extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, int C, int Hf, int Wf, int Ho,
@@ -316,8 +437,7 @@ extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, i
     if (int rc = require_sm100()) return rc;
     if (N == 0) return PP_OK;
     PP_CHECK_ARG(feat && grid && out, "pp_bilinear_sample: null pointer");
-    PP_CHECK_ARG(N >= 0 && C > 0 && Hf > 0 && Wf > 0 && Ho > 0 && Wo > 0, "pp_bilinear_sample: bad shape");
-    if (N == 0) return PP_OK;
+    PP_CHECK_ARG(N > 0 && C > 0 && Hf > 0 && Wf > 0 && Ho > 0 && Wo > 0, "pp_bilinear_sample: bad shape");
     const long long total = (long long)N * Ho * Wo;
     int grid_dim = (int)((total + 127) / 128);
     const int cap = sm_count() * 16;

@@ -43,6 +43,8 @@ struct GemmParams {
     long long total_tiles;
     const int32_t* bank_of_det;    // (B,) or null = identity
     const float* mrow;             // (B, T) nearest-resized query mask
+    const float* ra;               // (B, T) inverse norms of the query patches
+    const float* rb;               // (n_banks, N, T) inverse norms of the template patches
     unsigned long long* rowkey;    // (B, N, T)
     unsigned long long* colkey;    // (B, N, T)
     float* emit;                   // EPI_EMIT: (B*N, T, T) raw similarities
@@ -213,8 +215,12 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int warp_row0 = tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M + q * 32;
             const int t = warp_row0 + lane;
             const bool row_ok = t < T;
-            const float m_t = (EPI == EPI_MATCH && row_ok) ? __ldg(p.mrow + (size_t)tc.b * T + t) : 0.f;
+            // per-row factor of the column reduction: query mask x inverse query norm (masked rows give +0.0)
+            const float m_t = (EPI == EPI_MATCH && row_ok)
+                                  ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + t) : 0.f;
             const size_t bn = (size_t)tc.b * p.N + tc.n;
+            const int bank = (EPI == EPI_MATCH && p.bank_of_det) ? __ldg(p.bank_of_det + tc.b) : tc.b;
+            const float* rb_n = EPI == EPI_MATCH ? p.rb + ((size_t)bank * p.N + tc.n) * T : nullptr;
 
             mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
             ptx::tc_fence_after();
@@ -240,15 +246,30 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 if (s0 >= T) continue;  // warp-uniform: chunk entirely past the last template patch
                 const int ncols = min(32, T - s0);
                 if (EPI == EPI_MATCH) {
+                    // inverse norms of this chunk's 32 template patches (same for every thread: broadcast loads)
+                    float rbv[32];
+                    if (ncols == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 q4 = __ldg(reinterpret_cast<const float4*>(rb_n + s0 + j));
+                            rbv[j] = q4.x; rbv[j + 1] = q4.y; rbv[j + 2] = q4.z; rbv[j + 3] = q4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rbv[j] = __ldg(rb_n + min(s0 + j, T - 1));
+                    }
                     float ck_v = -INFINITY;
                     int ck_l = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float x = __uint_as_float(v[j]);
                         const bool col_ok = j < ncols;  // uniform
-                        // rows: running first-argmax over s (strict > keeps the first index on ties)
-                        if (col_ok && x > best) { best = x; best_s = s0 + j; }
-                        // columns: masked rows contribute +0.0, rows past T nothing
+                        // rows: running first-argmax over s of acc * rb[s] (strict > keeps the first index on ties);
+                        // the row's own positive factor ra[t] commutes with the max and is applied when finalising
+                        const float xr = x * rbv[j];
+                        if (col_ok && xr > best) { best = xr; best_s = s0 + j; }
+                        // columns: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max);
+                        // masked rows contribute +0.0, rows past T nothing
                         const float xc = row_ok ? fmaf(x, m_t, 0.0f) : -INFINITY;
                         const float cm = ptx::warp_max_f32(xc);
                         const unsigned ball = __ballot_sync(0xffffffffu, xc == cm);
@@ -353,8 +374,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 
 // Shared by pp_match_scores (EPI_MATCH) and pp_match_similarity (EPI_EMIT).
 int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
-                   int B, int N, int T, int Kp, const float* mrow, unsigned long long* rowkey,
-                   unsigned long long* colkey, float* emit, int cluster, cudaStream_t st) {
+                   int B, int N, int T, int Kp, const float* mrow, const float* ra, const float* rb,
+                   unsigned long long* rowkey, unsigned long long* colkey, float* emit, int cluster, cudaStream_t st) {
     PP_CHECK_ARG(Kp > 0 && Kp % BLOCK_K == 0, "Kp must be a positive multiple of %d (got %d)", BLOCK_K, Kp);
     PP_CHECK_ARG((reinterpret_cast<uintptr_t>(q_prep) & 127) == 0 && (reinterpret_cast<uintptr_t>(bank_prep) & 127) == 0,
                  "prepared operands must be 128-byte aligned");
@@ -373,6 +394,8 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.total_tiles = (long long)B * N * p.num_mt * p.num_nt;
     p.bank_of_det = bank_of_det;
     p.mrow = mrow;
+    p.ra = ra;
+    p.rb = rb;
     p.rowkey = rowkey;
     p.colkey = colkey;
     p.emit = emit;

@@ -5,8 +5,8 @@
 namespace pp {
 
 int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
-                   int B, int N, int T, int Kp, const float* mrow, unsigned long long* rowkey,
-                   unsigned long long* colkey, float* emit, int cluster, cudaStream_t st);
+                   int B, int N, int T, int Kp, const float* mrow, const float* ra, const float* rb,
+                   unsigned long long* rowkey, unsigned long long* colkey, float* emit, int cluster, cudaStream_t st);
 
 // F.interpolate(mask[:,None], size=(H,W)) (nearest) flattened to (B, H*W): utils/matching.py:38-39 / :16-17
 __global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm, int Wm, int H, int W,
@@ -24,7 +24,8 @@ __global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm
 // (utils/matching.py:54-60) and the masked mean (:63-67).
 __global__ void __launch_bounds__(256)
 finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
-                       const float* __restrict__ mrow, int N, int T, float inv_hh, float* __restrict__ sim_avg,
+                       const float* __restrict__ mrow, const float* __restrict__ ra, int N, int T, float inv_hh,
+                       float* __restrict__ sim_avg,
                        float* __restrict__ score_t2s, int32_t* __restrict__ idx_t2s, int32_t* __restrict__ idx_s2t) {
     const size_t bn = blockIdx.x;
     const int b = (int)(bn / N);
@@ -35,7 +36,8 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
         const unsigned long long ck = colkey[bn * T + j];
         // a masked query row is all zeros in the reference: max 0 at index 0
         const bool on = m != 0.f;
-        const float sc = (on && rk) ? key_value(rk) * m : 0.f;
+        // row key holds max_s(acc * rb[s]); the row's own inverse norm and mask value complete sim[t, argmax]
+        const float sc = (on && rk) ? key_value(rk) * ra[(size_t)b * T + j] * m : 0.f;
         const int it = (on && rk) ? (int)key_index(rk) : 0;
         const int is = ck ? (int)key_index(ck) : 0;
         const float valid = (it != 0 && is != 0) ? m : 0.f;  // tar_mask * (idx_src2tar != 0) * (idx_tar2src != 0)
@@ -89,7 +91,8 @@ topk_kernel(const float* __restrict__ scores, int N, int k, long long idx_offset
 }
 
 // stage-2 volume: out[b, s, h, w] = max(0, sim[b, t = w*H + h, s] * mask_s)   (utils/matching.py:23-25)
-__global__ void similarity_layout_kernel(const float* __restrict__ sim, const float* __restrict__ mcol, int B, int H,
+__global__ void similarity_layout_kernel(const float* __restrict__ sim, const float* __restrict__ mcol,
+                                         const float* __restrict__ ra, const float* __restrict__ rb, int B, int H,
                                          int W, float* __restrict__ out) {
     const int T = H * W;
     const long long total = (long long)B * T * T;
@@ -101,7 +104,7 @@ __global__ void similarity_layout_kernel(const float* __restrict__ sim, const fl
         const int hw = r - s * T;
         const int h = hw / W, w = hw - h * W;
         const int t = w * H + h;
-        float v = sim[((size_t)b * T + t) * T + s] * mcol[(size_t)b * T + s];
+        float v = sim[((size_t)b * T + t) * T + s] * ra[(size_t)b * T + t] * rb[(size_t)b * T + s] * mcol[(size_t)b * T + s];
         out[i] = v < 0.f ? 0.f : v;
     }
 }
@@ -116,14 +119,14 @@ extern "C" size_t pp_match_scores_workspace(int B, int N, int T) {
     return pp::align_up((size_t)B * T * sizeof(float), 256) + 2 * pp::align_up(keys, 256);
 }
 
-extern "C" int pp_match_scores(const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
-                               const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
+extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* bank_prep, const float* bank_rnorm,
+                               int64_t n_banks, const int32_t* bank_of_det, const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
                                float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t, void* workspace,
                                size_t workspace_bytes, int cluster, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
     if (B == 0 || N == 0) return PP_OK;
-    PP_CHECK_ARG(q_prep && bank_prep && tar_mask && sim_avg, "pp_match_scores: null pointer");
+    PP_CHECK_ARG(q_prep && q_rnorm && bank_prep && bank_rnorm && tar_mask && sim_avg, "pp_match_scores: null pointer");
     PP_CHECK_ARG(H == W, "pp_match_scores: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
     PP_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_scores: bad shape");
     PP_CHECK_ARG(bank_of_det != nullptr || n_banks == B, "pp_match_scores: identity bank mapping needs n_banks == B");
@@ -143,11 +146,12 @@ extern "C" int pp_match_scores(const void* q_prep, const void* bank_prep, int64_
     resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(tar_mask, B, Hm, Wm, H, W, mrow);
     PP_LAUNCHED();
     PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys, st));
-    if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, mrow, rowkey, colkey, nullptr,
-                                cluster, st))
+    if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, mrow, q_rnorm, bank_rnorm,
+                                rowkey, colkey, nullptr, cluster, st))
         return rc;
-    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, mrow, N, T, 1.0f / (float)(H * H),
-                                                                      sim_avg, score_t2s, idx_t2s, idx_s2t);
+    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, mrow, q_rnorm, N, T,
+                                                                      1.0f / (float)(H * H), sim_avg, score_t2s,
+                                                                      idx_t2s, idx_s2t);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -176,13 +180,14 @@ extern "C" size_t pp_match_similarity_workspace(int B, int T) {
     return pp::align_up((size_t)B * T * sizeof(float), 256) + pp::align_up((size_t)B * T * T * sizeof(float), 256);
 }
 
-extern "C" int pp_match_similarity(const void* q_prep, const void* s_prep, const float* src_mask, int B, int H, int W,
+extern "C" int pp_match_similarity(const void* q_prep, const float* q_rnorm, const void* s_prep, const float* s_rnorm,
+                                   const float* src_mask, int B, int H, int W,
                                    int Kp, int Hm, int Wm, float* out, void* workspace, size_t workspace_bytes,
                                    int cluster, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
     if (B == 0) return PP_OK;
-    PP_CHECK_ARG(q_prep && s_prep && src_mask && out, "pp_match_similarity: null pointer");
+    PP_CHECK_ARG(q_prep && q_rnorm && s_prep && s_rnorm && src_mask && out, "pp_match_similarity: null pointer");
     PP_CHECK_ARG(H == W, "pp_match_similarity: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
     PP_CHECK_ARG(B >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_similarity: bad shape");
     if (B == 0) return PP_OK;
@@ -199,11 +204,12 @@ extern "C" int pp_match_similarity(const void* q_prep, const void* s_prep, const
     resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(src_mask, B, Hm, Wm, H, W, mcol);
     PP_LAUNCHED();
     // one "view" per detection: banks == detections, N = 1
-    if (int rc = run_match_gemm(1, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, sim, cluster, st))
+    if (int rc = run_match_gemm(1, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                sim, cluster, st))
         return rc;
     const long long total = (long long)B * T * T;
     int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
-    similarity_layout_kernel<<<grid, 256, 0, st>>>(sim, mcol, B, H, W, out);
+    similarity_layout_kernel<<<grid, 256, 0, st>>>(sim, mcol, q_rnorm, s_rnorm, B, H, W, out);
     PP_LAUNCHED();
     return PP_OK;
 }

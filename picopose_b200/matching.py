@@ -46,8 +46,11 @@ def _as_f32(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
-def prepare_features(feats: torch.Tensor, mode: Optional[str] = None, is_query: bool = False) -> torch.Tensor:
-    """(..., C, H, W) fp32 -> (..., H*W, Kp) bf16: L2-normalised over C, K-major, split per `mode`."""
+def prepare_features(feats: torch.Tensor, mode: Optional[str] = None, is_query: bool = False):
+    """(..., C, H, W) fp32 -> (prepared (..., H*W, Kp) bf16 K-major split per `mode`, rnorm (..., H*W) fp32).
+
+    rnorm = 1 / max(||x||_2, 1e-12) over C (F.normalize's rule); the contraction applies it in its epilogue.
+    """
     _lib.require_cuda(feats)
     lib = _lib.load()
     mid = _mode_id(mode)
@@ -61,17 +64,19 @@ def prepare_features(feats: torch.Tensor, mode: Optional[str] = None, is_query: 
     if kp <= 0:
         raise RuntimeError(f"picopose_b200: bad feature dim {Cc}")
     out = torch.empty((*lead, P, kp), dtype=torch.bfloat16, device=feats.device)
+    rnorm = torch.empty((*lead, P), dtype=torch.float32, device=feats.device)
     with torch.cuda.device(feats.device):
-        _lib.check(lib.pp_match_prepare(_lib.ptr(feats), G, Cc, P, mid, int(is_query), _lib.ptr(out),
+        _lib.check(lib.pp_match_prepare(_lib.ptr(feats), G, Cc, P, mid, int(is_query), _lib.ptr(out), _lib.ptr(rnorm),
                                         _lib.stream_of(feats)), "pp_match_prepare")
-    return out
+    return out, rnorm
 
 
 class TemplateBank:
-    """Template banks prepared once: (n_banks, N, C, H, W) fp32 -> resident (n_banks, N, H*W, Kp) bf16."""
+    """Template banks prepared once: (n_banks, N, C, H, W) fp32 -> resident (n_banks, N, H*W, Kp) bf16 + inverse norms."""
 
-    def __init__(self, prepared: torch.Tensor, C: int, H: int, W: int, mode: str):
+    def __init__(self, prepared: torch.Tensor, rnorm: torch.Tensor, C: int, H: int, W: int, mode: str):
         self.prepared = prepared
+        self.rnorm = rnorm
         self.C, self.H, self.W, self.mode = C, H, W, mode
 
     @classmethod
@@ -82,7 +87,8 @@ class TemplateBank:
             raise ValueError("expected (n_banks, N, C, H, W) template features")
         mode = default_mode() if mode is None else mode
         _, _, Cc, H, W = src_feats.shape
-        return cls(prepare_features(src_feats, mode, is_query=False), Cc, H, W, mode)
+        prep, rnorm = prepare_features(src_feats, mode, is_query=False)
+        return cls(prep, rnorm, Cc, H, W, mode)
 
     @property
     def n_banks(self) -> int:
@@ -98,7 +104,8 @@ class TemplateBank:
 
     def view_slice(self, start: int, stop: int) -> "TemplateBank":
         """Bank restricted to views [start, stop) (template-axis sharding); copies to keep rows dense."""
-        return TemplateBank(self.prepared[:, start:stop].contiguous(), self.C, self.H, self.W, self.mode)
+        return TemplateBank(self.prepared[:, start:stop].contiguous(), self.rnorm[:, start:stop].contiguous(),
+                            self.C, self.H, self.W, self.mode)
 
 
 def _resolve_bank(src_feats, mode, B):
@@ -141,7 +148,7 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
         bank_index = bank_index.to(device=tar_feat.device, dtype=torch.int32).contiguous()
     N, T = bank.n_views, H * W
     dev = tar_feat.device
-    q = prepare_features(tar_feat, bank.mode, is_query=True)  # (B, T, Kp)
+    q, q_rn = prepare_features(tar_feat, bank.mode, is_query=True)  # (B, T, Kp), (B, T)
     kp = q.shape[-1]
     mask = _as_f32(tar_mask)
     Hm, Wm = mask.shape[-2:]
@@ -162,11 +169,14 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
             b1 = min(B, b0 + chunk)
             nb = b1 - b0
             if bank_index is not None:
-                bidx, bank_ptr, n_banks = _lib.ptr(bank_index[b0:b1]), _lib.ptr(bank.prepared), bank.n_banks
+                bidx, n_banks = _lib.ptr(bank_index[b0:b1]), bank.n_banks
+                bank_ptr, bank_rn = _lib.ptr(bank.prepared), _lib.ptr(bank.rnorm)
             else:
-                bidx, bank_ptr, n_banks = 0, _lib.ptr(bank.prepared[b0:b1]), nb
+                bidx, n_banks = 0, nb
+                bank_ptr, bank_rn = _lib.ptr(bank.prepared[b0:b1]), _lib.ptr(bank.rnorm[b0:b1])
             _lib.check(lib.pp_match_scores(
-                _lib.ptr(q[b0:b1]), bank_ptr, n_banks, bidx, _lib.ptr(mask[b0:b1]), nb, N, H, W, kp, Hm, Wm,
+                _lib.ptr(q[b0:b1]), _lib.ptr(q_rn[b0:b1]), bank_ptr, bank_rn, n_banks, bidx, _lib.ptr(mask[b0:b1]),
+                nb, N, H, W, kp, Hm, Wm,
                 _lib.ptr(sim_avg[b0:b1]), _lib.ptr(sc[b0:b1]) if want_indices else 0,
                 _lib.ptr(it[b0:b1]) if want_indices else 0, _lib.ptr(is_[b0:b1]) if want_indices else 0,
                 _lib.ptr(ws), ws.numel(), cl, st), "pp_match_scores")
@@ -210,15 +220,16 @@ def matching_features_similarity(src_feat, tar_feat, src_mask, tar_mask, *, mode
     if H != W:
         raise AssertionError("matching_features_similarity expects a square patch grid (H == W)")
     mode = default_mode() if mode is None else mode
-    q = prepare_features(tar_feat, mode, is_query=True)
-    s = prepare_features(src_feat, mode, is_query=False)
+    q, q_rn = prepare_features(tar_feat, mode, is_query=True)
+    s, s_rn = prepare_features(src_feat, mode, is_query=False)
     mask = _as_f32(src_mask)
     Hm, Wm = mask.shape[-2:]
     T = H * W
     out = torch.empty(B, T, H, W, dtype=torch.float32, device=src_feat.device)
     ws = torch.empty(lib.pp_match_similarity_workspace(B, T), dtype=torch.uint8, device=src_feat.device)
     with torch.cuda.device(src_feat.device):
-        _lib.check(lib.pp_match_similarity(_lib.ptr(q), _lib.ptr(s), _lib.ptr(mask), B, H, W, q.shape[-1], Hm, Wm,
+        _lib.check(lib.pp_match_similarity(_lib.ptr(q), _lib.ptr(q_rn), _lib.ptr(s), _lib.ptr(s_rn), _lib.ptr(mask),
+                                           B, H, W, q.shape[-1], Hm, Wm,
                                            _lib.ptr(out), _lib.ptr(ws), ws.numel(), default_cluster(),
                                            _lib.stream_of(src_feat)), "pp_match_similarity")
     return out

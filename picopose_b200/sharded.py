@@ -87,4 +87,6 @@ class ShardedMatcher:
         else:
             s = sim.new_empty(sim.shape[0], 0)
             i = torch.empty(sim.shape[0], 0, dtype=torch.int64, device=sim.device)
+        if self.world == 1 and kl == topk:
+            return s, i                      # single rank: the local top-k is the answer, nothing to exchange
         return merge_topk(s, i, topk, self.group, self.select)

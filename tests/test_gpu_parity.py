@@ -161,22 +161,27 @@ def test_stage3_correspondences_native_size():
 def test_prepare_features_layout():
     from picopose_b200.matching import prepare_features
     gen = torch.Generator().manual_seed(1)
-    x = torch.randn(3, 2, 72, 5, 5, generator=gen)                     # C=72: K padding 72 -> 128
-    ref = torch.nn.functional.normalize(x, dim=2).reshape(3, 2, 72, 25).transpose(2, 3)
-    out = prepare_features(x.to(DEV), "bf16").float().cpu()
-    assert tuple(out.shape) == (3, 2, 25, 128)
-    np.testing.assert_allclose(out[..., :72].numpy(), ref.bfloat16().float().numpy(), atol=4e-3, rtol=0)
+    x = 3.0 * torch.randn(3, 2, 72, 5, 5, generator=gen)               # C=72: K padding 72 -> 128
+    x[0, 0, :, 0, 0] = 0.0                                             # a zero patch: norm clamps to eps
+    xt = x.reshape(3, 2, 72, 25).transpose(2, 3)                       # (..., patch, channel) = K-major
+    out, rn = prepare_features(x.to(DEV), "bf16")
+    out, rn = out.float().cpu(), rn.cpu()
+    assert tuple(out.shape) == (3, 2, 25, 128) and tuple(rn.shape) == (3, 2, 25)
+    assert torch.equal(out[..., :72], xt.bfloat16().float())           # plain round-to-nearest cast, transposed
     assert float(out[..., 72:].abs().max()) == 0.0
-    # split modes reconstruct the fp32 value: query segments [q1 q1 q2 | q1 q2 q3], bank [b1 b2 b1 | b3 b2 b1]
-    o6 = prepare_features(x.to(DEV), "fp32", is_query=True).float().cpu()
+    ref_rn = 1.0 / torch.clamp(x.reshape(3, 2, 72, 25).norm(dim=2), min=1e-12)
+    np.testing.assert_allclose(rn.numpy(), ref_rn.numpy(), rtol=2e-6)
+    assert float(rn[0, 0, 0]) == pytest.approx(1e12, rel=1e-6)
+    # split modes reconstruct the fp32 value exactly: query segments [q1 q1 q2 | q1 q2 q3], bank [b1 b2 b1 | b3 b2 b1]
+    o6 = prepare_features(x.to(DEV), "fp32", is_query=True)[0].float().cpu()
     assert o6.shape[-1] == 448
     s = [o6[..., i * 72:(i + 1) * 72] for i in range(6)]
     assert torch.equal(s[0], s[1]) and torch.equal(s[0], s[3]) and torch.equal(s[2], s[4])
-    np.testing.assert_allclose((s[0] + s[2] + s[5]).numpy(), ref.numpy(), atol=3e-7, rtol=0)
-    b6 = prepare_features(x.to(DEV), "fp32", is_query=False).float().cpu()
+    assert torch.equal(s[0] + s[2] + s[5], xt)
+    b6 = prepare_features(x.to(DEV), "fp32", is_query=False)[0].float().cpu()
     t = [b6[..., i * 72:(i + 1) * 72] for i in range(6)]
     assert torch.equal(t[0], t[2]) and torch.equal(t[0], t[5]) and torch.equal(t[1], t[4])
-    np.testing.assert_allclose((t[0] + t[1] + t[3]).numpy(), ref.numpy(), atol=3e-7, rtol=0)
+    assert torch.equal(t[0] + t[1] + t[3], xt)
 
 
 MODE_TOL = {"bf16": 4e-3, "bf16x3": 2e-5, "fp32": 1e-5}

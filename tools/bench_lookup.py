@@ -22,7 +22,17 @@ def main():
     ap.add_argument("--radii", type=int, nargs="+", default=[4, 5, 6, 7, 8])
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to try (32/64/128), 0 = leave")
     args = ap.parse_args()
+    if args.l2_fetch:
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        torch.cuda.init()
+        torch.zeros(1, device="cuda:0")
+        val = ctypes.c_size_t(0)
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(args.l2_fetch))       # cudaLimitMaxL2FetchGranularity = 0x05
+        rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+        print("cudaLimitMaxL2FetchGranularity set rc=%d now=%d" % (rc, val.value), flush=True)
     from picopose_b200.corr_lookup import corr_lookup
     dev = "cuda:0"
     B, H, L = args.batch, args.size, args.levels

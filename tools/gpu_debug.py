@@ -37,7 +37,8 @@ def run_stage(stage):
     elif stage == "prep":
         x = torch.randn(2, 3, 128, 8, 8)
         ref = torch.nn.functional.normalize(x, dim=2).reshape(2, 3, 128, 64).transpose(2, 3)
-        out = M.prepare_features(x.to(dev), "bf16").float().cpu()
+        out, rn = M.prepare_features(x.to(dev), "bf16")
+        out = out.float().cpu() * rn.cpu().unsqueeze(-1)
         print("prep bf16 max err", float((out - ref).abs().max()), "shape", tuple(out.shape))
     elif stage in ("emit1", "emit2"):
         cl = 1 if stage == "emit1" else 2
@@ -46,8 +47,10 @@ def run_stage(stage):
             src = torch.randn(B, C, H, H)
             tar = torch.randn(B, C, H, H)
             T = H * H
-            q = M.prepare_features(tar.to(dev), "bf16", True).float().cpu()
-            s = M.prepare_features(src.to(dev), "bf16", False).float().cpu()
+            q, qn = M.prepare_features(tar.to(dev), "bf16", True)
+            s, sn = M.prepare_features(src.to(dev), "bf16", False)
+            q = q.float().cpu() * qn.cpu().unsqueeze(-1)
+            s = s.float().cpu() * sn.cpu().unsqueeze(-1)
             ref = torch.clamp(torch.matmul(q, s.transpose(1, 2)), min=0)      # (B,T,S)
             out = M.matching_features_similarity(src.to(dev), tar.to(dev), torch.ones(B, 224, 224, device=dev), None,
                                                  mode="bf16")
