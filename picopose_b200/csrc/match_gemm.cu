@@ -58,7 +58,8 @@ struct GemmCfg {
     static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+    static constexpr int RB_BYTES = NUM_EPI_WARPS * 128 * 4;  // per epilogue warp: 128 inverse template norms
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + 1024;  // + alignment slack
 };
 
 __device__ __noinline__ void report_fault(int* fault, int code, int a, int b) {
@@ -114,6 +115,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + NUM_ACC + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
+    float* rb_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -219,8 +221,20 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const float m_t = (EPI == EPI_MATCH && row_ok)
                                   ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + t) : 0.f;
             const size_t bn = (size_t)tc.b * p.N + tc.n;
-            const int bank = (EPI == EPI_MATCH && p.bank_of_det) ? __ldg(p.bank_of_det + tc.b) : tc.b;
-            const float* rb_n = EPI == EPI_MATCH ? p.rb + ((size_t)bank * p.N + tc.n) * T : nullptr;
+            float* rb_s = rb_stage + e * 128;  // this warp's 128 inverse template norms (its column half)
+            if (EPI == EPI_MATCH) {
+                // stage them before waiting for the accumulator so the global latency hides behind the MMAs
+                const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
+                const float* rb_n = p.rb + ((size_t)bank * p.N + tc.n) * T;
+                const int sbase = tc.nt * BLOCK_N + hh * 128;
+                __syncwarp();  // previous tile's readers of rb_s are done
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int s = sbase + i * 32 + lane;
+                    rb_s[i * 32 + lane] = s < T ? __ldg(rb_n + s) : 0.f;
+                }
+                __syncwarp();
+            }
 
             mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
             ptx::tc_fence_after();
@@ -246,37 +260,43 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 if (s0 >= T) continue;  // warp-uniform: chunk entirely past the last template patch
                 const int ncols = min(32, T - s0);
                 if (EPI == EPI_MATCH) {
-                    // inverse norms of this chunk's 32 template patches (same for every thread: broadcast loads)
-                    float rbv[32];
-                    if (ncols == 32) {
+                    // ---- rows: running first-argmax over s of acc * rb[s] (strict > keeps the first index on ties);
+                    // the row's own positive factor ra[t] commutes with the max and is applied when finalising.
+                    // ---- columns: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max);
+                    // masked rows contribute +0.0, rows past T lose against everything.  Each value becomes a
+                    // 32-bit key  ord(value) with its 5 low bits replaced by (31 - lane)  so that an integer max
+                    // means "largest value, then lowest row"; values closer than 2^-18 relative are ties.
+                    uint32_t k[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 q4 = __ldg(reinterpret_cast<const float4*>(rb_n + s0 + j));
-                            rbv[j] = q4.x; rbv[j + 1] = q4.y; rbv[j + 2] = q4.z; rbv[j + 3] = q4.w;
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(rb_s + c * 32 + j);  // broadcast read
+                        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float x = __uint_as_float(v[j + u]);
+                            const float xr = x * rr[u];
+                            if (j + u < ncols && xr > best) { best = xr; best_s = s0 + j + u; }
+                            const float xc = row_ok ? fmaf(x, m_t, 0.0f) : -INFINITY;
+                            k[j + u] = (f32_ord(xc) & 0xFFFFFFE0u) | (uint32_t)(31 - lane);
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) rbv[j] = __ldg(rb_n + min(s0 + j, T - 1));
                     }
-                    float ck_v = -INFINITY;
-                    int ck_l = 0;
+                    // butterfly transpose-reduce: after the 5 exchanges lane j holds the warp's winner of column j
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        const bool col_ok = j < ncols;  // uniform
-                        // rows: running first-argmax over s of acc * rb[s] (strict > keeps the first index on ties);
-                        // the row's own positive factor ra[t] commutes with the max and is applied when finalising
-                        const float xr = x * rbv[j];
-                        if (col_ok && xr > best) { best = xr; best_s = s0 + j; }
-                        // columns: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max);
-                        // masked rows contribute +0.0, rows past T nothing
-                        const float xc = row_ok ? fmaf(x, m_t, 0.0f) : -INFINITY;
-                        const float cm = ptx::warp_max_f32(xc);
-                        const unsigned ball = __ballot_sync(0xffffffffu, xc == cm);
-                        if (lane == j) { ck_v = cm; ck_l = __ffs(ball) - 1; }
+                    for (int half = 16; half >= 1; half >>= 1) {
+                        const bool up = (lane & half) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            const uint32_t send = up ? k[i] : k[i + half];
+                            const uint32_t keep = up ? k[i + half] : k[i];
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, half);
+                            k[i] = keep > recv ? keep : recv;
+                        }
                     }
                     if (lane < ncols && warp_row0 < T) {
-                        atomicMax(p.colkey + bn * T + s0 + lane, pack_key(ck_v, (uint32_t)(warp_row0 + ck_l)));
+                        const uint32_t row = (uint32_t)warp_row0 + (31u - (k[0] & 31u));
+                        const unsigned long long key = ((unsigned long long)(k[0] & 0xFFFFFFE0u) << 32) |
+                                                       (unsigned long long)(0xFFFFFFFFu - row);
+                        atomicMax(p.colkey + bn * T + s0 + lane, key);
                     }
                 } else {
                     if (row_ok) {
