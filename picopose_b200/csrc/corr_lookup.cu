@@ -15,6 +15,8 @@
 // inverse, utils/corr_lookup.py:61-65 + ATen grid_sampler_unnormalize), so floor/weights agree.
 #include "pp_common.cuh"
 
+#include <cstdlib>
+
 namespace pp {
 
 constexpr int LOOKUP_MAX_LEVELS = 8;
@@ -55,6 +57,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// 16-byte copy that reads only `src_bytes` (0 or 16) from global memory and zero-fills the rest
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -72,7 +79,7 @@ struct LookupCfg {
     static constexpr int NV = (D + 5 + 3) / 4;        // 16-byte pieces per row: D+2 columns + 3 alignment slack
     static constexpr int PITCH = NV * 4;              // words per staged row
     static constexpr int QS = ((NRB * NV) | 1) * 4;   // words per query: odd number of 16-byte units (bank spread)
-    static constexpr int WARP_WORDS = 32 * QS + 64;   // + packed header (2 words per query)
+    static constexpr int WARP_WORDS = 32 * QS;
 };
 
 template <int R, int JB>
@@ -84,7 +91,6 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     float* stage = smem + (size_t)warp * Cfg::WARP_WORDS;
-    int* hdr = reinterpret_cast<int*>(stage + 32 * QS);  // [2*q] = xs, [2*q+1] = y0 | pieces<<20 | rows<<26
 
     // work item = (query group, pyramid level): levels of one group run on different warps, which keeps the
     // dependent chain per warp short when there are few queries (the native 16^2..64^2 ladder)
@@ -129,27 +135,31 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                 const int yb = yo[j0];
                 const int rows = yo[j1 - 1] + 1 - yb + 1;
                 __syncwarp();  // previous band's readers are done with the staging area
-                hdr[2 * lane] = xs;
-                hdr[2 * lane + 1] = (yb + 8) | (pieces << 20) | (rows << 26);
-                __syncwarp();
+                const int packed = (yb + 8) | (pieces << 20) | (rows << 26);
 
-                // ---- cooperative staging: lane -> (query, row, piece), consecutive lanes = consecutive pieces ----
+                // ---- cooperative staging: for query ql (warp-uniform) lane -> (row, piece) of its footprint, so
+                // consecutive lanes fetch consecutive 16-byte pieces of a row; the footprint origin of query ql
+                // comes from its owner lane by shuffle.  Pieces outside the map are zero-filled (src-size 0),
+                // pieces no tap touches are skipped.
                 constexpr int PER_Q = NRB * NV;
+                constexpr int PASSES = (PER_Q + 31) / 32;
+#pragma unroll
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    const int slot = ps * 32 + lane;
+                    const int row = slot / NV;  // constant divisor
+                    const int v = slot - row * NV;
+                    const bool slot_ok = slot < PER_Q;
+                    float* dst0 = stage + slot * 4;
 #pragma unroll 4
-                for (int i = lane; i < 32 * PER_Q; i += 32) {
-                    const int ql = i / PER_Q;          // constant divisors: mul/shift
-                    const int rem = i - ql * PER_Q;
-                    const int row = rem / NV;
-                    const int v = rem - row * NV;
-                    const int2 h = *reinterpret_cast<const int2*>(hdr + 2 * ql);
-                    if (row >= (h.y >> 26) || v >= ((h.y >> 20) & 63)) continue;  // not touched by any tap
-                    const int y = (h.y & 0xFFFFF) - 8 + row;
-                    const int x = h.x + 4 * v;
-                    float* dst = stage + ql * QS + (row * NV + v) * 4;
-                    if ((unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl && ql < nq) {
-                        cp_async16(dst, vol_g + (size_t)ql * slice + (uint32_t)(y * Wl + x));
-                    } else {
-                        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int ql = 0; ql < 32; ++ql) {
+                        const int qx = __shfl_sync(0xffffffffu, xs, ql);
+                        const int qp = __shfl_sync(0xffffffffu, packed, ql);
+                        const int y = (qp & 0xFFFFF) - 8 + row;
+                        const int x = qx + 4 * v;
+                        const bool need = slot_ok && row < (qp >> 26) && v < ((qp >> 20) & 63);
+                        const bool inb = (unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl && ql < nq;
+                        const float* src = vol_g + (size_t)(inb ? ql : 0) * slice + (uint32_t)(inb ? y * Wl + x : 0);
+                        if (need) cp_async16_zfill(dst0 + ql * QS, src, inb ? 16u : 0u);
                     }
                 }
                 cp_async_wait_all();
@@ -403,6 +413,14 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
     p.total_groups = B * p.groups_per_b;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (all_vec) {
+        // tuning aid: PICOPOSE_LOOKUP_JB overrides the band height for the radii of the BASELINE sweep
+        static const int jb_override = [] { const char* e = getenv("PICOPOSE_LOOKUP_JB"); return e ? atoi(e) : 0; }();
+        if (jb_override) {
+            if (radius == 4 && jb_override == 3) return launch_banded<4, 3>(p, st);
+            if (radius == 4 && jb_override == 9) return launch_banded<4, 9>(p, st);
+            if (radius == 8 && jb_override == 4) return launch_banded<8, 4>(p, st);
+            if (radius == 8 && jb_override == 9) return launch_banded<8, 9>(p, st);
+        }
         // band height per radius: keeps ~12-25 KB of staging per warp so 8-16 warps share an SM
         switch (radius) {
             case 1: return launch_banded<1, 3>(p, st);

@@ -12,8 +12,8 @@
 //   warp 1     MMA issuer  : tcgen05.mma kind::f16, M = 128*CL, N = 256, K = 16 per instruction,
 //                            accumulators double-buffered in TMEM (2 x 256 columns)
 //   warp 2     TMEM allocator
-//   warps 4-11 epilogue    : tcgen05.ld 32x32b -> registers; warp w reads lane quarter w%4,
-//                            column half (w-4)/4 of the 128 x 256 accumulator
+//   warps 4-19 epilogue    : tcgen05.ld 32x32b -> registers; warp w reads lane quarter w%4,
+//                            64-column slice (w-4)/4 of the 128 x 256 accumulator
 // CL = 2 pairs two SMs (cta_group::2): each CTA loads its own 128 A rows and half of the B tile, the
 // leader issues M=256 MMAs, commits are multicast to both CTAs.
 #include "pp_common.cuh"
@@ -28,9 +28,11 @@ constexpr int BLOCK_N = 256;  // accumulator columns per tile (UMMA N)
 constexpr int BLOCK_K = 64;   // bf16 elements per k-block: one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_ACC = 2;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;                                   // 4 per TMEM lane quarter, 64 columns each
+constexpr int EPI_COLS = BLOCK_N / (NUM_EPI_WARPS / 4);               // accumulator columns per epilogue warp
+constexpr int EPI_CHUNKS = EPI_COLS / 32;
 constexpr int FIRST_EPI_WARP = 4;
-constexpr int GEMM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;  // 384
+constexpr int GEMM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;  // 640
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KiB
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;              // ~2 s: a stuck pipeline traps instead of hanging
 
@@ -40,7 +42,7 @@ struct GemmParams {
     int B, N, T;  // detections, views per bank, patches (T == S)
     int num_k_blocks;
     int num_mt, num_nt;  // tiles along T (per 128*CL rows) and S (per 256 columns)
-    long long total_tiles;
+    uint32_t total_tiles;
     const int32_t* bank_of_det;    // (B,) or null = identity
     const float* mrow;             // (B, T) nearest-resized query mask
     const float* ra;               // (B, T) inverse norms of the query patches
@@ -58,7 +60,7 @@ struct GemmCfg {
     static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int RB_BYTES = NUM_EPI_WARPS * 128 * 4;  // per epilogue warp: 128 inverse template norms
+    static constexpr int RB_BYTES = NUM_EPI_WARPS * EPI_COLS * 4;  // per epilogue warp: inverse norms of its columns
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + 1024;  // + alignment slack
 };
 
@@ -86,14 +88,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fa
 struct TileCoord {
     int b, n, nt, mt;
 };
-__device__ __forceinline__ TileCoord decode_tile(long long tile, const GemmParams& p) {
+__device__ __forceinline__ TileCoord decode_tile(uint32_t tile, const GemmParams& p) {
     TileCoord c;
-    c.mt = (int)(tile % p.num_mt);
-    long long r = tile / p.num_mt;
-    c.nt = (int)(r % p.num_nt);
-    r /= p.num_nt;
-    c.n = (int)(r % p.N);
-    c.b = (int)(r / p.N);
+    uint32_t r = tile / (uint32_t)p.num_mt;
+    c.mt = (int)(tile - r * (uint32_t)p.num_mt);
+    uint32_t r2 = r / (uint32_t)p.num_nt;
+    c.nt = (int)(r - r2 * (uint32_t)p.num_nt);
+    const uint32_t b = r2 / (uint32_t)p.N;
+    c.n = (int)(r2 - b * (uint32_t)p.N);
+    c.b = (int)b;
     return c;
 }
 
@@ -121,8 +124,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
-    const long long cluster_id = blockIdx.x / CL;
-    const long long num_clusters = gridDim.x / CL;
+    const uint32_t cluster_id = blockIdx.x / CL;
+    const uint32_t num_clusters = gridDim.x / CL;
 
     if (CL > 1) ptx::cluster_sync();  // both CTAs resident before the paired TMEM allocation
 
@@ -152,7 +155,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ===================== TMA producer (every CTA) =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (long long tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
+        for (uint32_t tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
             const TileCoord tc = decode_tile(tile, p);
             const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
             const int a_row = tc.b * p.T + tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M;
@@ -180,8 +183,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         constexpr uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, BLOCK_N);
         int stage = 0;
         uint32_t phase = 0;
-        long long iter = 0;
-        for (long long tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
+        uint32_t iter = 0;
+        for (uint32_t tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             mbar_wait(tempty_bar(as), aphase ^ 1u, p.fault, 2, as);
@@ -207,9 +210,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ===================== epilogue (every CTA) =====================
         const int e = warp - FIRST_EPI_WARP;
         const int q = warp & 3;   // TMEM lane quarter this warp may read
-        const int hh = e >> 2;    // column half
-        long long iter = 0;
-        for (long long tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
+        const int hh = e >> 2;    // which EPI_COLS-wide column slice of the tile
+        uint32_t iter = 0;
+        for (uint32_t tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
             const TileCoord tc = decode_tile(tile, p);
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
@@ -217,19 +220,21 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int warp_row0 = tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M + q * 32;
             const int t = warp_row0 + lane;
             const bool row_ok = t < T;
-            // per-row factor of the column reduction: query mask x inverse query norm (masked rows give +0.0)
+            // column reduction: value = acc * (query mask x inverse query norm) + 0.0 (masked rows give +0.0,
+            // -0.0 is canonicalised); rows past T get a huge negative value and lose against everything
             const float m_t = (EPI == EPI_MATCH && row_ok)
                                   ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + t) : 0.f;
+            const float c_add = row_ok ? 0.0f : -3.0e38f;
             const size_t bn = (size_t)tc.b * p.N + tc.n;
-            float* rb_s = rb_stage + e * 128;  // this warp's 128 inverse template norms (its column half)
+            const int sbase = tc.nt * BLOCK_N + hh * EPI_COLS;
+            float* rb_s = rb_stage + e * EPI_COLS;  // this warp's inverse template norms
             if (EPI == EPI_MATCH) {
                 // stage them before waiting for the accumulator so the global latency hides behind the MMAs
                 const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
                 const float* rb_n = p.rb + ((size_t)bank * p.N + tc.n) * T;
-                const int sbase = tc.nt * BLOCK_N + hh * 128;
                 __syncwarp();  // previous tile's readers of rb_s are done
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < EPI_CHUNKS; ++i) {
                     const int s = sbase + i * 32 + lane;
                     rb_s[i * 32 + lane] = s < T ? __ldg(rb_n + s) : 0.f;
                 }
@@ -238,16 +243,16 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
             mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + hh * 128);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + hh * EPI_COLS);
 
             float best = -INFINITY;
             int best_s = 0;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < EPI_CHUNKS; ++c) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
                 ptx::tmem_ld_wait();
-                if (c == 3) {
+                if (c == EPI_CHUNKS - 1) {
                     // this warp has drained its part of the accumulator: hand the TMEM stage back
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -256,17 +261,19 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         else ptx::mbar_arrive_cluster(tempty_bar(as), 0);
                     }
                 }
-                const int s0 = tc.nt * BLOCK_N + hh * 128 + c * 32;
+                const int s0 = sbase + c * 32;
                 if (s0 >= T) continue;  // warp-uniform: chunk entirely past the last template patch
                 const int ncols = min(32, T - s0);
                 if (EPI == EPI_MATCH) {
-                    // ---- rows: running first-argmax over s of acc * rb[s] (strict > keeps the first index on ties);
-                    // the row's own positive factor ra[t] commutes with the max and is applied when finalising.
-                    // ---- columns: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max);
-                    // masked rows contribute +0.0, rows past T lose against everything.  Each value becomes a
-                    // 32-bit key  ord(value) with its 5 low bits replaced by (31 - lane)  so that an integer max
-                    // means "largest value, then lowest row"; values closer than 2^-18 relative are ties.
-                    uint32_t k[32];
+                    // ---- rows: first-argmax over s of acc * rb[s] (strict > keeps the first index on ties); the
+                    // row's own positive factor ra[t] commutes with the max and is applied when finalising.
+                    // ---- columns: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max).
+                    // Each value becomes a float key whose 5 low mantissa bits hold (31 - lane): a float max then
+                    // means "largest value, then lowest row"; values closer than 2^-18 relative count as ties.
+                    float k[32];
+                    float cbest = -INFINITY;
+                    int cj = 0;
+                    const uint32_t lane_bits = (uint32_t)(31 - lane);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 r4 = *reinterpret_cast<const float4*>(rb_s + c * 32 + j);  // broadcast read
@@ -275,28 +282,38 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         for (int u = 0; u < 4; ++u) {
                             const float x = __uint_as_float(v[j + u]);
                             const float xr = x * rr[u];
-                            if (j + u < ncols && xr > best) { best = xr; best_s = s0 + j + u; }
-                            const float xc = row_ok ? fmaf(x, m_t, 0.0f) : -INFINITY;
-                            k[j + u] = (f32_ord(xc) & 0xFFFFFFE0u) | (uint32_t)(31 - lane);
+                            if (xr > cbest) { cbest = xr; cj = j + u; }
+                            const float xc = fmaf(x, m_t, c_add);
+                            k[j + u] = __uint_as_float((__float_as_uint(xc) & 0xFFFFFFE0u) | lane_bits);
                         }
                     }
+                    if (ncols < 32) {
+                        // ragged last chunk: redo the row scan over the valid columns only (rare, tiny shapes)
+                        cbest = -INFINITY;
+                        cj = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float xr = __uint_as_float(v[j]) * rb_s[c * 32 + j];
+                            if (j < ncols && xr > cbest) { cbest = xr; cj = j; }
+                        }
+                    }
+                    if (cbest > best) { best = cbest; best_s = s0 + cj; }
                     // butterfly transpose-reduce: after the 5 exchanges lane j holds the warp's winner of column j
 #pragma unroll
                     for (int half = 16; half >= 1; half >>= 1) {
                         const bool up = (lane & half) != 0;
 #pragma unroll
                         for (int i = 0; i < half; ++i) {
-                            const uint32_t send = up ? k[i] : k[i + half];
-                            const uint32_t keep = up ? k[i + half] : k[i];
-                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, half);
-                            k[i] = keep > recv ? keep : recv;
+                            const float send = up ? k[i] : k[i + half];
+                            const float keep = up ? k[i + half] : k[i];
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, half);
+                            k[i] = fmaxf(keep, recv);
                         }
                     }
                     if (lane < ncols && warp_row0 < T) {
-                        const uint32_t row = (uint32_t)warp_row0 + (31u - (k[0] & 31u));
-                        const unsigned long long key = ((unsigned long long)(k[0] & 0xFFFFFFE0u) << 32) |
-                                                       (unsigned long long)(0xFFFFFFFFu - row);
-                        atomicMax(p.colkey + bn * T + s0 + lane, key);
+                        const uint32_t kb = __float_as_uint(k[0]);
+                        const uint32_t row = (uint32_t)warp_row0 + (31u - (kb & 31u));
+                        atomicMax(p.colkey + bn * T + s0 + lane, pack_key(__uint_as_float(kb & 0xFFFFFFE0u), row));
                     }
                 } else {
                     if (row_ok) {
@@ -370,7 +387,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     auto kern = match_gemm_kernel<CL, EPI>;
     PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     long long clusters = sm_count() / CL;
-    if (clusters > p.total_tiles) clusters = p.total_tiles;
+    if (clusters > (long long)p.total_tiles) clusters = p.total_tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * CL));
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -411,7 +428,9 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.num_k_blocks = Kp / BLOCK_K;
     p.num_mt = (T + BLOCK_M * cluster - 1) / (BLOCK_M * cluster);
     p.num_nt = (T + BLOCK_N - 1) / BLOCK_N;
-    p.total_tiles = (long long)B * N * p.num_mt * p.num_nt;
+    const long long tiles_ll = (long long)B * N * p.num_mt * p.num_nt;
+    PP_CHECK_ARG(tiles_ll < (1LL << 31), "too many tiles in one launch (%lld); split the detection batch", tiles_ll);
+    p.total_tiles = (uint32_t)tiles_ll;
     p.bank_of_det = bank_of_det;
     p.mrow = mrow;
     p.ra = ra;
