@@ -215,18 +215,45 @@ def run_ours(args):
     gemm_avg_ms = sum(gemm_ms) / len(gemm_ms)
 
     # ---- timed region 2: end to end, per-detection inputs come from pinned host memory ----
-    for _ in range(min(3, args.warmup)):
-        s, i, _ = step(tar_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True), src_d)
-        s.cpu(); i.cpu()
+    # Every step copies its own query features + mask host->device and reads its own top-k back device->host,
+    # all inside the timed region.  Copies run on a side stream into double buffers and results land in pinned
+    # memory asynchronously, so step i+1's upload overlaps step i's kernels (a serving loop's pipelining);
+    # the region ends with a full synchronisation after the last result has reached the host.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    bufs = [(torch.empty_like(tar_d), torch.empty_like(mask_d)) for _ in range(2)]
+    res_host = [(torch.empty(world, k, dtype=torch.float32).pin_memory(), torch.empty(world, k, dtype=torch.int64).pin_memory())
+                for _ in range(2)]
+    up_done = [torch.cuda.Event() for _ in range(2)]
+    used = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n):
+        for it in range(n):
+            sl = it & 1
+            with torch.cuda.stream(copy_stream):
+                if it >= 2:
+                    copy_stream.wait_event(used[sl])       # the kernels that read this buffer two steps ago are done
+                bufs[sl][0].copy_(tar_h, non_blocking=True)
+                bufs[sl][1].copy_(mask_h, non_blocking=True)
+                up_done[sl].record(copy_stream)
+            main_stream.wait_event(up_done[sl])
+            s, i, _ = step(bufs[sl][0], bufs[sl][1], src_d)
+            used[sl].record(main_stream)
+            res_host[sl][0].copy_(s, non_blocking=True)     # device->host read of the step's result (pinned, async)
+            res_host[sl][1].copy_(i, non_blocking=True)
+        torch.cuda.synchronize()
+        return res_host[(n - 1) & 1]
+
+    e2e_loop(min(4, max(2, args.warmup)))
     barrier()
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     u0.record()
-    for _ in range(args.steps):
-        s, i, _ = step(tar_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True), src_d)
-        s_host, i_host = s.cpu(), i.cpu()                  # device->host read of the step's result
+    s_host, i_host = e2e_loop(args.steps)
     u1.record()
     barrier()
     e2e_ms_total = u0.elapsed_time(u1)
+    if not SMALL:
+        assert i_host.tolist() == planted[:, :k].tolist()
 
     # ---- extra: resident prepared bank ("warm bank", the serving mode of SURVEY 8(d)) ----
     matcher.load_bank(src_d)

@@ -126,6 +126,13 @@ PP_API int pp_match_similarity(const void* q_prep, const float* q_rnorm, const v
                         int B, int H, int W, int Kp, int Hm, int Wm, float* out,
                         void* workspace, size_t workspace_bytes, int cluster, void* stream);
 
+/* All-pairs correlation pyramid.  Replaces CorrelationPyramid.forward, model/stage3/raft_decoder.py:30-53
+ * (torch.matmul / sqrt(C) + AvgPool2d(2,2) levels), the producer of the volumes pp_corr_lookup reads.
+ *   f1_prep, f2_prep : (N, H*W, Kp) prepared features (pp_match_prepare; norms unused)
+ *   level_ptrs[l]    : (N*H*W, 1, H>>l, W>>l) fp32 outputs (HOST array of DEVICE pointers), scale = 1/sqrt(C) */
+PP_API int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
+                           int num_levels, void* const* level_ptrs, int cluster, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Correspondence glue.
  * pp_init_correspondences replaces compute_init_correspondences, utils/correspondence.py:10-26:

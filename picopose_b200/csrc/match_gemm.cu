@@ -49,7 +49,8 @@ struct GemmParams {
     const float* rb;               // (n_banks, N, T) inverse norms of the template patches
     unsigned long long* rowkey;    // (B, N, T)
     unsigned long long* colkey;    // (B, N, T)
-    float* emit;                   // EPI_EMIT: (B*N, T, T) raw similarities
+    float* emit;                   // EPI_EMIT: (B*N, T, T) raw products times emit_scale
+    float emit_scale;
     int* fault;                    // host-mapped fault record
 };
 
@@ -321,12 +322,13 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         if (ncols == 32 && (T & 3) == 0) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                                *reinterpret_cast<float4*>(dst + j) =
+                                    make_float4(__uint_as_float(v[j]) * p.emit_scale, __uint_as_float(v[j + 1]) * p.emit_scale,
+                                                __uint_as_float(v[j + 2]) * p.emit_scale, __uint_as_float(v[j + 3]) * p.emit_scale);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (j < ncols) dst[j] = __uint_as_float(v[j]);
+                                if (j < ncols) dst[j] = __uint_as_float(v[j]) * p.emit_scale;
                         }
                     }
                 }
@@ -412,7 +414,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 // Shared by pp_match_scores (EPI_MATCH) and pp_match_similarity (EPI_EMIT).
 int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
                    int B, int N, int T, int Kp, const float* mrow, const float* ra, const float* rb,
-                   unsigned long long* rowkey, unsigned long long* colkey, float* emit, int cluster, cudaStream_t st) {
+                   unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
+                   cudaStream_t st) {
     PP_CHECK_ARG(Kp > 0 && Kp % BLOCK_K == 0, "Kp must be a positive multiple of %d (got %d)", BLOCK_K, Kp);
     PP_CHECK_ARG((reinterpret_cast<uintptr_t>(q_prep) & 127) == 0 && (reinterpret_cast<uintptr_t>(bank_prep) & 127) == 0,
                  "prepared operands must be 128-byte aligned");
@@ -438,6 +441,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.rowkey = rowkey;
     p.colkey = colkey;
     p.emit = emit;
+    p.emit_scale = emit_scale;
     p.fault = g_fault_dev;
     if (p.total_tiles == 0) return PP_OK;
     CUtensorMap ta, tb;

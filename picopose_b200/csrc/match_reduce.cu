@@ -6,7 +6,8 @@ namespace pp {
 
 int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
                    int B, int N, int T, int Kp, const float* mrow, const float* ra, const float* rb,
-                   unsigned long long* rowkey, unsigned long long* colkey, float* emit, int cluster, cudaStream_t st);
+                   unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
+                   cudaStream_t st);
 
 // F.interpolate(mask[:,None], size=(H,W)) (nearest) flattened to (B, H*W): utils/matching.py:38-39 / :16-17
 __global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm, int Wm, int H, int W,
@@ -109,6 +110,20 @@ __global__ void similarity_layout_kernel(const float* __restrict__ sim, const fl
     }
 }
 
+// AvgPool2d(kernel 2, stride 2) of every (h x w) slice: model/stage3/raft_decoder.py:27,49-51
+__global__ void avgpool2_kernel(const float* __restrict__ in, long long slices, int h, int w, float* __restrict__ out) {
+    const int ho = h >> 1, wo = w >> 1;
+    const long long total = slices * ho * wo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i / (ho * wo);
+        const int r = (int)(i - q * ho * wo);
+        const int y = r / wo, x = r - y * wo;
+        const float* s = in + (q * h + 2 * y) * (long long)w + 2 * x;
+        out[i] = (s[0] + s[1] + s[w] + s[w + 1]) * 0.25f;
+    }
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace pp
@@ -147,7 +162,7 @@ extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const v
     PP_LAUNCHED();
     PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys, st));
     if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, mrow, q_rnorm, bank_rnorm,
-                                rowkey, colkey, nullptr, cluster, st))
+                                rowkey, colkey, nullptr, 1.0f, cluster, st))
         return rc;
     finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, mrow, q_rnorm, N, T,
                                                                       1.0f / (float)(H * H), sim_avg, score_t2s,
@@ -205,11 +220,40 @@ extern "C" int pp_match_similarity(const void* q_prep, const float* q_rnorm, con
     PP_LAUNCHED();
     // one "view" per detection: banks == detections, N = 1
     if (int rc = run_match_gemm(1, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                sim, cluster, st))
+                                sim, 1.0f, cluster, st))
         return rc;
     const long long total = (long long)B * T * T;
     int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
     similarity_layout_kernel<<<grid, 256, 0, st>>>(sim, mcol, q_rnorm, s_rnorm, B, H, W, out);
     PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
+                                      int num_levels, void* const* level_ptrs, int cluster, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (N == 0) return PP_OK;
+    PP_CHECK_ARG(f1_prep && f2_prep && level_ptrs, "pp_correlation_pyramid: null pointer");
+    PP_CHECK_ARG(N > 0 && H > 0 && W > 0 && num_levels >= 1 && num_levels <= 8, "pp_correlation_pyramid: bad shape");
+    for (int l = 0; l < num_levels; ++l) PP_CHECK_ARG(level_ptrs[l], "pp_correlation_pyramid: null level %d", l);
+    PP_CHECK_ARG((H >> (num_levels - 1)) >= 1 && (W >> (num_levels - 1)) >= 1, "pp_correlation_pyramid: too many levels for %dx%d", H, W);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int T = H * W;
+    // all-pairs products <f1[:, q], f2[:, key]> * scale straight into level 0: (N*H*W, 1, H, W) is row-major [q][key]
+    if (int rc = run_match_gemm(1, f1_prep, f2_prep, N, nullptr, N, 1, T, Kp, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                static_cast<float*>(level_ptrs[0]), scale, cluster, st))
+        return rc;
+    int h = H, w = W;
+    for (int l = 1; l < num_levels; ++l) {
+        const long long slices = (long long)N * T;
+        const long long total = slices * (h >> 1) * (w >> 1);
+        int grid = (int)((total + 255) / 256 < (long long)sm_count() * 32 ? (total + 255) / 256 : (long long)sm_count() * 32);
+        avgpool2_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(level_ptrs[l - 1]), slices, h, w,
+                                              static_cast<float*>(level_ptrs[l]));
+        PP_LAUNCHED();
+        h >>= 1;
+        w >>= 1;
+    }
     return PP_OK;
 }

@@ -24,7 +24,8 @@ def install_overlay(reference_root: str) -> None:
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
-    for name in ("utils", "utils.matching", "utils.corr_lookup", "utils.correspondence"):
+    for name in ("utils", "utils.matching", "utils.corr_lookup", "utils.correspondence", "model", "model.stage3",
+                 "model.stage3.raft_decoder"):
         sys.modules.pop(name, None)
 
 

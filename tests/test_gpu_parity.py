@@ -353,6 +353,47 @@ def test_similarity_volume_native_size():
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=4e-3)
 
 
+def test_correlation_pyramid():
+    from picopose_b200.correlation import CorrelationPyramid, correlation_pyramid
+    g = load("pyramid.npz")
+    pyr = CorrelationPyramid(num_levels=3)(cuda(g["f1"]), cuda(g["f2"]))
+    _lib.check_device_faults()
+    for i, lvl in enumerate(pyr):
+        assert tuple(lvl.shape) == g[f"lvl{i}"].shape
+        np.testing.assert_allclose(lvl.cpu().numpy(), g[f"lvl{i}"], rtol=0, atol=2e-5)
+    # FlowDecoder shapes: 256 channels, 16^2 (1 level) and 32^2 (2 levels); values are O(sqrt(C)) = O(16)/16
+    gen = torch.Generator().manual_seed(12)
+    for H, L in ((16, 1), (32, 2)):
+        f1 = torch.randn(2, 256, H, H, generator=gen)
+        f2 = torch.randn(2, 256, H, H, generator=gen)
+        ref = OL.correlation_pyramid(f1, f2, L)
+        out = correlation_pyramid(f1.to(DEV), f2.to(DEV), L)
+        for a, b in zip(out, ref):
+            np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=0, atol=3e-5)
+        out = correlation_pyramid(f1.to(DEV), f2.to(DEV), L, mode="bf16")
+        np.testing.assert_allclose(out[0].cpu().numpy(), ref[0].numpy(), rtol=0, atol=4e-2)
+
+
+def test_stage3_level_end_to_end():
+    """One FlowDecoder level of the stage-3 hot path on CUDA: pyramid -> lookup -> feature warp, against the oracle."""
+    from picopose_b200.corr_lookup import CorrLookup, bilinear_sample
+    from picopose_b200.correlation import CorrelationPyramid
+    gen = torch.Generator().manual_seed(13)
+    H, L, r = 32, 2, 2
+    f1 = torch.randn(1, 256, H, H, generator=gen)
+    f2 = torch.randn(1, 256, H, H, generator=gen)
+    flow = 2.0 * torch.randn(1, 2, H, H, generator=gen)
+    ref_pyr = OL.correlation_pyramid(f1, f2, L)
+    ref = OL.corr_lookup(ref_pyr, flow, r)
+    pyr = CorrelationPyramid(num_levels=L)(f1.to(DEV), f2.to(DEV))
+    out = CorrLookup(radius=r)(pyr, flow.to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5)
+    grid = OL.coords_grid(1, H, H) + flow
+    warp_ref = OL.bilinear_sample(f2, grid, align_corners=True)
+    warp = bilinear_sample(f2.to(DEV), grid.to(DEV), align_corners=True)
+    np.testing.assert_allclose(warp.cpu().numpy(), warp_ref.numpy(), rtol=0, atol=1e-5)
+
+
 def test_topk_matches_torch():
     from picopose_b200.matching import topk_scores
     gen = torch.Generator().manual_seed(6)

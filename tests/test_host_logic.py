@@ -57,12 +57,18 @@ def test_overlay_shadows_exactly_three_reference_modules(tmp_path):
     (ref / "utils").mkdir(parents=True)
     (ref / "utils" / "matching.py").write_text("ORIGIN = 'reference'\n")
     (ref / "utils" / "torch_utils.py").write_text("ORIGIN = 'reference'\n")
+    (ref / "model" / "stage3").mkdir(parents=True)
+    (ref / "model" / "stage3" / "raft_decoder.py").write_text(
+        "ORIGIN = 'reference'\nclass CorrelationPyramid: pass\nclass MotionEncoder: pass\n")
+    (ref / "model" / "stage3" / "flow_decoder.py").write_text("ORIGIN = 'reference'\n")
     from picopose_b200 import launcher
-    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k == "utils" or k.startswith("utils.")}
+    def ours(k):
+        return k in ("utils", "model") or k.startswith("utils.") or k.startswith("model.")
+    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if ours(k)}
     try:
         launcher.install_overlay(str(ref))
         for k in list(sys.modules):
-            if k == "utils" or k.startswith("utils."):
+            if ours(k):
                 del sys.modules[k]
         m = importlib.import_module("utils.matching")
         t = importlib.import_module("utils.torch_utils")
@@ -70,10 +76,16 @@ def test_overlay_shadows_exactly_three_reference_modules(tmp_path):
         assert m.__file__.startswith(launcher.OVERLAY) and hasattr(m, "matching_templates")
         assert c.__file__.startswith(launcher.OVERLAY) and hasattr(c, "CorrLookup")
         assert t.ORIGIN == "reference"
+        # model/stage3/raft_decoder.py: reference module re-exported, CorrelationPyramid swapped
+        rd = importlib.import_module("model.stage3.raft_decoder")
+        fd = importlib.import_module("model.stage3.flow_decoder")
+        assert rd.__file__.startswith(launcher.OVERLAY) and rd.ORIGIN == "reference" and hasattr(rd, "MotionEncoder")
+        assert rd.CorrelationPyramid.__module__ == "picopose_b200.correlation"
+        assert fd.ORIGIN == "reference"
     finally:
         sys.path[:] = saved_path
         for k in list(sys.modules):
-            if k == "utils" or k.startswith("utils."):
+            if ours(k):
                 del sys.modules[k]
         sys.modules.update(saved_mods)
 
