@@ -93,21 +93,29 @@ PP_API int pp_match_kp(int C, int mode);
 PP_API int pp_match_prepare(const float* feats, int64_t G, int C, int P, int mode, int is_query,
                      void* prepared, float* rnorm, void* stream);
 
+/* Query side of pp_match_scores: resizes the query masks (nearest, as F.interpolate at utils/matching.py:38-39),
+ * drops masked patches (they are rows of zeros in the reference and never need the tensor cores), prepares the
+ * remaining patches like pp_match_prepare and records the bookkeeping pp_match_scores needs.
+ *   tar_feat (B,C,H,W) fp32, tar_mask (B,Hm,Wm) fp32  ->  q_prep (B, H*W, Kp) bf16 (unmasked patches first),
+ *   q_rnorm (B, H*W) fp32, q_meta: pp_match_query_meta_bytes(B, H*W) bytes (opaque). */
+PP_API size_t pp_match_query_meta_bytes(int B, int T);
+PP_API int pp_match_prepare_query(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm, int Wm,
+                           int mode, void* q_prep, float* q_rnorm, void* q_meta, void* stream);
+
 /* Bytes of scratch pp_match_scores needs for (B detections, N views, T = H*W patches). */
 PP_API size_t pp_match_scores_workspace(int B, int N, int T);
 
 /* Fused similarity GEMM + bidirectional max/argmax + validity-masked mean.
  * Replaces utils/matching.py:38-39,47-67 (the sim tensor never reaches HBM).
- *   q_prep, q_rnorm       : (B, T, Kp) bf16 / (B, T) fp32            prepared query features
+ *   q_prep, q_rnorm, q_meta : outputs of pp_match_prepare_query for the same B, H, W
  *   bank_prep, bank_rnorm : (n_banks, N, T, Kp) bf16 / (n_banks, N, T) fp32   prepared template banks
  *   bank_of_det : (B,) int32 device array, bank used by detection b; NULL = identity (n_banks == B)
- *   tar_mask  : (B, Hm, Wm) fp32 0/1 query masks (nearest-resized to H x W as F.interpolate does)
  *   sim_avg   : (B, N) fp32 out
  *   optional outs (NULL to skip): score_t2s (B,N,T) fp32, idx_t2s (B,N,T) int32, idx_s2t (B,N,T) int32
  *   cluster   : 0 = default, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
  */
-PP_API int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* bank_prep, const float* bank_rnorm,
-                    int64_t n_banks, const int32_t* bank_of_det, const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
+PP_API int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* q_meta, const void* bank_prep,
+                    const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H, int W, int Kp,
                     float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
                     void* workspace, size_t workspace_bytes, int cluster, void* stream);
 

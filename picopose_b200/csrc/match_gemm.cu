@@ -36,6 +36,8 @@ constexpr int GEMM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;  // 640
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KiB
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;              // ~2 s: a stuck pipeline traps instead of hanging
 
+constexpr int MAX_DETS_PER_LAUNCH = 1024;  // tile prefix table lives in shared memory
+
 enum { EPI_MATCH = 0, EPI_EMIT = 1 };
 
 struct GemmParams {
@@ -44,8 +46,10 @@ struct GemmParams {
     int num_mt, num_nt;  // tiles along T (per 128*CL rows) and S (per 256 columns)
     uint32_t total_tiles;
     const int32_t* bank_of_det;    // (B,) or null = identity
-    const float* mrow;             // (B, T) nearest-resized query mask
-    const float* ra;               // (B, T) inverse norms of the query patches
+    const float* mrow;             // (B, T) nearest-resized query mask, indexed by patch
+    const int* tv;                 // (B) unmasked query patches per detection (EPI_MATCH: rows are compacted); null = T
+    const int* rowmap;             // (B, T) patch index of compact query row r
+    const float* ra;               // (B, T) inverse norms of the (compact) query rows
     const float* rb;               // (n_banks, N, T) inverse norms of the template patches
     unsigned long long* rowkey;    // (B, N, T)
     unsigned long long* colkey;    // (B, N, T)
@@ -62,7 +66,8 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int RB_BYTES = NUM_EPI_WARPS * EPI_COLS * 4;  // per epilogue warp: inverse norms of its columns
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + 1024;  // + alignment slack
+    static constexpr int PREFIX_BYTES = (MAX_DETS_PER_LAUNCH + 1) * 4;  // per-detection tile prefix (compacted rows)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + PREFIX_BYTES + 1024;  // + alignment slack
 };
 
 __device__ __noinline__ void report_fault(int* fault, int code, int a, int b) {
@@ -101,6 +106,26 @@ __device__ __forceinline__ TileCoord decode_tile(uint32_t tile, const GemmParams
     return c;
 }
 
+// Compacted query rows: detection b owns N * num_nt * ceil(tv[b] / rows_per_tile) tiles; prefix[] (shared memory)
+// holds the running tile count, a binary search maps a flat tile index back to its detection.
+__device__ __forceinline__ TileCoord decode_tile_prefix(uint32_t tile, const GemmParams& p, const uint32_t* prefix) {
+    int lo = 0, hi = p.B;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    TileCoord c;
+    c.b = lo;
+    const uint32_t local = tile - prefix[lo];
+    const uint32_t nmt = (prefix[lo + 1] - prefix[lo]) / (uint32_t)(p.N * p.num_nt);
+    const uint32_t r = local / nmt;
+    c.mt = (int)(local - r * nmt);
+    const uint32_t n = r / (uint32_t)p.num_nt;
+    c.nt = (int)(r - n * (uint32_t)p.num_nt);
+    c.n = (int)n;
+    return c;
+}
+
 template <int CL, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -120,6 +145,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + NUM_ACC + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
     float* rb_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+    uint32_t* tile_prefix = reinterpret_cast<uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::RB_BYTES);
+    const bool compact = EPI == EPI_MATCH && p.tv != nullptr;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -146,18 +173,37 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::fence_barrier_init();
     } else if (warp == 2) {
         ptx::tmem_alloc<CL>(ptx::smem_u32((const void*)tmem_slot), 512);
+    } else if (warp == 3 && compact) {
+        // inclusive scan of the per-detection tile counts (B <= MAX_DETS_PER_LAUNCH), 32 detections per step
+        uint32_t run = 0;
+        if (lane == 0) tile_prefix[0] = 0;
+        for (int b0 = 0; b0 < p.B; b0 += 32) {
+            const int b = b0 + lane;
+            uint32_t cnt = 0;
+            if (b < p.B) cnt = (uint32_t)((__ldg(p.tv + b) + BLOCK_M * CL - 1) / (BLOCK_M * CL)) * (uint32_t)(p.N * p.num_nt);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            if (b < p.B) tile_prefix[b + 1] = run + inc;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
     }
     ptx::tc_fence_before();
     if (CL > 1) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t total_tiles = compact ? tile_prefix[p.B] : p.total_tiles;
+    auto decode = [&](uint32_t tile) { return compact ? decode_tile_prefix(tile, p, tile_prefix) : decode_tile(tile, p); };
 
     if (warp == 0 && lane == 0) {
         // ===================== TMA producer (every CTA) =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (uint32_t tile = cluster_id; tile < p.total_tiles; tile += num_clusters) {
-            const TileCoord tc = decode_tile(tile, p);
+        for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+            const TileCoord tc = decode(tile);
             const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
             const int a_row = tc.b * p.T + tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M;
             const long long b_row_ll = ((long long)bank * p.N + tc.n) * p.T + tc.nt * BLOCK_N + (int)cta_rank * Cfg::B_ROWS;
@@ -185,7 +231,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         int stage = 0;
         uint32_t phase = 0;
         uint32_t iter = 0;
-        for (uint32_t tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
+        for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             mbar_wait(tempty_bar(as), aphase ^ 1u, p.fault, 2, as);
@@ -213,18 +259,22 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int q = warp & 3;   // TMEM lane quarter this warp may read
         const int hh = e >> 2;    // which EPI_COLS-wide column slice of the tile
         uint32_t iter = 0;
-        for (uint32_t tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++iter) {
-            const TileCoord tc = decode_tile(tile, p);
+        for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
+            const TileCoord tc = decode(tile);
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             const int T = p.T;
+            // rows of this tile are compact query rows r (masked patches were dropped by the prologue);
+            // t is the patch index the row stands for
+            const int rows_b = compact ? __ldg(p.tv + tc.b) : T;
             const int warp_row0 = tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M + q * 32;
-            const int t = warp_row0 + lane;
-            const bool row_ok = t < T;
-            // column reduction: value = acc * (query mask x inverse query norm) + 0.0 (masked rows give +0.0,
-            // -0.0 is canonicalised); rows past T get a huge negative value and lose against everything
+            const int r_row = warp_row0 + lane;
+            const bool row_ok = r_row < rows_b;
+            const int t = (compact && row_ok) ? __ldg(p.rowmap + (size_t)tc.b * T + r_row) : r_row;
+            // column reduction: value = acc * (query mask x inverse query norm) + 0.0 (-0.0 is canonicalised);
+            // rows past the last one get a huge negative value and lose against everything
             const float m_t = (EPI == EPI_MATCH && row_ok)
-                                  ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + t) : 0.f;
+                                  ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + r_row) : 0.f;
             const float c_add = row_ok ? 0.0f : -3.0e38f;
             const size_t bn = (size_t)tc.b * p.N + tc.n;
             const int sbase = tc.nt * BLOCK_N + hh * EPI_COLS;
@@ -311,10 +361,12 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             k[i] = fmaxf(keep, recv);
                         }
                     }
-                    if (lane < ncols && warp_row0 < T) {
+                    {
                         const uint32_t kb = __float_as_uint(k[0]);
-                        const uint32_t row = (uint32_t)warp_row0 + (31u - (kb & 31u));
-                        atomicMax(p.colkey + bn * T + s0 + lane, pack_key(__uint_as_float(kb & 0xFFFFFFE0u), row));
+                        // patch index of the winning row: held by the lane that owns that row
+                        const int win_t = __shfl_sync(0xffffffffu, t, 31 - (int)(kb & 31u));
+                        if (lane < ncols && warp_row0 < rows_b)
+                            atomicMax(p.colkey + bn * T + s0 + lane, pack_key(__uint_as_float(kb & 0xFFFFFFE0u), (uint32_t)win_t));
                     }
                 } else {
                     if (row_ok) {
@@ -413,7 +465,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 
 // Shared by pp_match_scores (EPI_MATCH) and pp_match_similarity (EPI_EMIT).
 int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
-                   int B, int N, int T, int Kp, const float* mrow, const float* ra, const float* rb,
+                   int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
+                   const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
                    cudaStream_t st) {
     PP_CHECK_ARG(Kp > 0 && Kp % BLOCK_K == 0, "Kp must be a positive multiple of %d (got %d)", BLOCK_K, Kp);
@@ -421,6 +474,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                  "prepared operands must be 128-byte aligned");
     PP_CHECK_ARG((long long)n_banks * N * T < (1LL << 31) && (long long)B * T < (1LL << 31),
                  "operand row count exceeds the 2^31 TMA coordinate range; split the call");
+    PP_CHECK_ARG(tv == nullptr || B <= MAX_DETS_PER_LAUNCH, "at most %d detections per launch (got %d)", MAX_DETS_PER_LAUNCH, B);
     if (cluster == 0) cluster = 2;
     PP_CHECK_ARG(cluster == 1 || cluster == 2, "cluster must be 0, 1 or 2 (got %d)", cluster);
     if (int rc = ensure_fault_buffer()) return rc;
@@ -436,6 +490,8 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.total_tiles = (uint32_t)tiles_ll;
     p.bank_of_det = bank_of_det;
     p.mrow = mrow;
+    p.tv = tv;
+    p.rowmap = rowmap;
     p.ra = ra;
     p.rb = rb;
     p.rowkey = rowkey;

@@ -33,7 +33,9 @@ constexpr int PREP_CT = 64;  // channels per transposed chunk
 template <int NPARTS>
 __global__ void __launch_bounds__(PREP_THREADS)
 match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int nseg, int is_query,
-                     __nv_bfloat16* __restrict__ prep, float* __restrict__ rnorm) {
+                     __nv_bfloat16* __restrict__ prep, float* __restrict__ rnorm, const int* __restrict__ rank) {
+    // rank != null: row compaction -- patch p of group g is written to row rank[g*P + p] (skipped if negative),
+    // so masked query patches never reach the tensor cores
     // [buffer][part][patch][64 channels] bf16, 16-byte units XOR-swizzled by (patch & 7)
     __shared__ __align__(16) __nv_bfloat16 s_tile[2][NPARTS][PREP_PT][PREP_CT];
     __shared__ float s_part[PREP_WARPS][PREP_PT];
@@ -87,9 +89,12 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
         const int row = warp * 4 + (lane >> 3);
         const int u = lane & 7;
         if (p0 + row < P && u < n_units) {
-            for (int s = 0; s < nseg; ++s) {
-                const uint4 val = *reinterpret_cast<const uint4*>(&s_tile[j & 1][seg_tab[s]][row][(u ^ (row & 7)) * 8]);
-                *reinterpret_cast<uint4*>(out_g + (size_t)(p0 + row) * Kp + (size_t)s * C + c0 + u * 8) = val;
+            const int orow = rank ? rank[(size_t)g * P + p0 + row] : p0 + row;
+            if (orow >= 0) {
+                for (int s = 0; s < nseg; ++s) {
+                    const uint4 val = *reinterpret_cast<const uint4*>(&s_tile[j & 1][seg_tab[s]][row][(u ^ (row & 7)) * 8]);
+                    *reinterpret_cast<uint4*>(out_g + (size_t)orow * Kp + (size_t)s * C + c0 + u * 8) = val;
+                }
             }
         }
 #pragma unroll
@@ -102,15 +107,68 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < PREP_WARPS; ++w) t += s_part[w][lane];
-        rnorm[(size_t)g * P + p0 + lane] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
+        const int orow = rank ? rank[(size_t)g * P + p0 + lane] : p0 + lane;
+        if (orow >= 0) rnorm[(size_t)g * P + orow] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
     }
     // ---- zero the K padding [nseg*C, Kp) ----
     const int pad0 = nseg * C, npad = Kp - pad0;
     if (npad > 0) {
         for (int i = threadIdx.x; i < PREP_PT * npad; i += PREP_THREADS) {
             const int row = i / npad, k = i - row * npad;
-            if (p0 + row < P) out_g[(size_t)(p0 + row) * Kp + pad0 + k] = __float2bfloat16_rn(0.f);
+            if (p0 + row < P) {
+                const int orow = rank ? rank[(size_t)g * P + p0 + row] : p0 + row;
+                if (orow >= 0) out_g[(size_t)orow * Kp + pad0 + k] = __float2bfloat16_rn(0.f);
+            }
         }
+    }
+}
+
+// Query-mask bookkeeping, one block per detection.  mask (B,Hm,Wm) is nearest-resized to H x W
+// (F.interpolate, utils/matching.py:38-39) and the unmasked patches are ranked in order:
+//   mrow[b,t]   resized mask value            rank[b,t]  compact row of patch t, -1 if masked
+//   rowmap[b,r] patch of compact row r         tv[b]      number of unmasked patches
+//   fm[b]       first masked patch, -1 if none
+__global__ void __launch_bounds__(256)
+mask_compact_kernel(const float* __restrict__ mask, int Hm, int Wm, int H, int W, float* __restrict__ mrow,
+                    int* __restrict__ rank, int* __restrict__ rowmap, int* __restrict__ tv, int* __restrict__ fm) {
+    __shared__ int s_warp[8];
+    __shared__ int s_fm;
+    const int b = blockIdx.x, T = H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_fm = 0x7fffffff;
+    __syncthreads();
+    int base = 0;
+    for (int t0 = 0; t0 < T; t0 += 256) {
+        const int t = t0 + threadIdx.x;
+        float m = 0.f;
+        if (t < T) {
+            const int y = t / W, x = t - y * W;
+            m = mask[((size_t)b * Hm + nearest_src(y, Hm, H)) * Wm + nearest_src(x, Wm, W)];
+        }
+        const bool on = t < T && m != 0.f;
+        const unsigned ball = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) s_warp[warp] = __popc(ball);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int c = s_warp[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        const int r = base + before + __popc(ball & ((1u << lane) - 1u));
+        if (t < T) {
+            mrow[(size_t)b * T + t] = m;
+            rank[(size_t)b * T + t] = on ? r : -1;
+            if (on) rowmap[(size_t)b * T + r] = t;
+            else atomicMin(&s_fm, t);
+        }
+        base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tv[b] = base;
+        fm[b] = s_fm == 0x7fffffff ? -1 : s_fm;
     }
 }
 
@@ -143,10 +201,59 @@ extern "C" int pp_match_prepare(const float* feats, int64_t G, int C, int P, int
         const float* f = feats + (size_t)g0 * C * P;
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(prepared) + (size_t)g0 * P * Kp;
         float* rn = rnorm + (size_t)g0 * P;
-        if (nparts == 1) match_prepare_kernel<1><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn);
-        else if (nparts == 2) match_prepare_kernel<2><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn);
-        else match_prepare_kernel<3><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn);
+        if (nparts == 1) match_prepare_kernel<1><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, nullptr);
+        else if (nparts == 2) match_prepare_kernel<2><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, nullptr);
+        else match_prepare_kernel<3><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, nullptr);
         PP_LAUNCHED();
     }
+    return PP_OK;
+}
+
+namespace pp {
+QueryMeta split_query_meta(void* q_meta, int B, int T) {
+    QueryMeta m;
+    char* p = static_cast<char*>(q_meta);
+    const size_t bt = (size_t)B * T * 4;
+    m.mrow = reinterpret_cast<float*>(p);
+    m.rank = reinterpret_cast<int*>(p + bt);
+    m.rowmap = reinterpret_cast<int*>(p + 2 * bt);
+    m.tv = reinterpret_cast<int*>(p + 3 * bt);
+    m.fm = reinterpret_cast<int*>(p + 3 * bt + (size_t)B * 4);
+    return m;
+}
+}  // namespace pp
+
+extern "C" size_t pp_match_query_meta_bytes(int B, int T) {
+    if (B < 0 || T < 0) return 0;
+    return ((size_t)3 * B * T + 2 * (size_t)B) * 4;
+}
+
+extern "C" int pp_match_prepare_query(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm,
+                                      int Wm, int mode, void* q_prep, float* q_rnorm, void* q_meta, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (B == 0) return PP_OK;
+    PP_CHECK_ARG(tar_feat && tar_mask && q_prep && q_rnorm && q_meta, "pp_match_prepare_query: null pointer");
+    PP_CHECK_ARG(mode >= 0 && mode <= 2, "pp_match_prepare_query: unknown mode %d", mode);
+    PP_CHECK_ARG(C > 0 && C % 8 == 0, "pp_match_prepare_query: feature dim must be a positive multiple of 8 (got %d)", C);
+    PP_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && Hm > 0 && Wm > 0, "pp_match_prepare_query: bad shape");
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(q_prep) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_meta) & 3) == 0,
+                 "pp_match_prepare_query: misaligned output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int T = H * W;
+    const int Kp = pp_match_kp(C, mode);
+    const QueryMeta m = split_query_meta(q_meta, B, T);
+    mask_compact_kernel<<<B, 256, 0, st>>>(tar_mask, Hm, Wm, H, W, m.mrow, m.rank, m.rowmap, m.tv, m.fm);
+    PP_LAUNCHED();
+    // compact rows beyond tv[b] are never written: keep them finite
+    PP_CUDA(cudaMemsetAsync(q_prep, 0, (size_t)B * T * Kp * 2, st));
+    PP_CUDA(cudaMemsetAsync(q_rnorm, 0, (size_t)B * T * 4, st));
+    const int nseg = mode_segments(mode), nparts = mode_parts(mode);
+    dim3 grid((T + PREP_PT - 1) / PREP_PT, B);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(q_prep);
+    if (nparts == 1) match_prepare_kernel<1><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, m.rank);
+    else if (nparts == 2) match_prepare_kernel<2><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, m.rank);
+    else match_prepare_kernel<3><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, m.rank);
+    PP_LAUNCHED();
     return PP_OK;
 }

@@ -5,7 +5,8 @@
 namespace pp {
 
 int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
-                   int B, int N, int T, int Kp, const float* mrow, const float* ra, const float* rb,
+                   int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
+                   const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
                    cudaStream_t st);
 
@@ -25,20 +26,26 @@ __global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm
 // (utils/matching.py:54-60) and the masked mean (:63-67).
 __global__ void __launch_bounds__(256)
 finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
-                       const float* __restrict__ mrow, const float* __restrict__ ra, int N, int T, float inv_hh,
-                       float* __restrict__ sim_avg,
+                       const float* __restrict__ mrow, const float* __restrict__ ra, const int* __restrict__ rank,
+                       const int* __restrict__ fm, int N, int T, float inv_hh, float* __restrict__ sim_avg,
                        float* __restrict__ score_t2s, int32_t* __restrict__ idx_t2s, int32_t* __restrict__ idx_s2t) {
     const size_t bn = blockIdx.x;
     const int b = (int)(bn / N);
+    // masked query rows never entered the contraction; in the reference they are rows of zeros that take part in
+    // every column max (utils/matching.py:48,51): value 0 at the first masked patch wins ties by index
+    const int fmb = fm[b];
+    const unsigned long long zero_key = fmb >= 0 ? pack_key(0.0f, (uint32_t)fmb) : 0ull;
     float sum = 0.f, cnt = 0.f;
     for (int j = threadIdx.x; j < T; j += blockDim.x) {
         const float m = mrow[(size_t)b * T + j];
         const unsigned long long rk = rowkey[bn * T + j];
-        const unsigned long long ck = colkey[bn * T + j];
+        unsigned long long ck = colkey[bn * T + j];
+        ck = ck > zero_key ? ck : zero_key;
         // a masked query row is all zeros in the reference: max 0 at index 0
         const bool on = m != 0.f;
         // row key holds max_s(acc * rb[s]); the row's own inverse norm and mask value complete sim[t, argmax]
-        const float sc = (on && rk) ? key_value(rk) * ra[(size_t)b * T + j] * m : 0.f;
+        const int rj = rank[(size_t)b * T + j];  // compact row of patch j (its inverse norm is stored there)
+        const float sc = (on && rk && rj >= 0) ? key_value(rk) * ra[(size_t)b * T + rj] * m : 0.f;
         const int it = (on && rk) ? (int)key_index(rk) : 0;
         const int is = ck ? (int)key_index(ck) : 0;
         const float valid = (it != 0 && is != 0) ? m : 0.f;  // tar_mask * (idx_src2tar != 0) * (idx_tar2src != 0)
@@ -131,40 +138,35 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 extern "C" size_t pp_match_scores_workspace(int B, int N, int T) {
     if (B < 0 || N < 0 || T < 0) return 0;
     const size_t keys = (size_t)B * N * T * sizeof(unsigned long long);
-    return pp::align_up((size_t)B * T * sizeof(float), 256) + 2 * pp::align_up(keys, 256);
+    return 2 * pp::align_up(keys, 256);
 }
 
-extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* bank_prep, const float* bank_rnorm,
-                               int64_t n_banks, const int32_t* bank_of_det, const float* tar_mask, int B, int N, int H, int W, int Kp, int Hm, int Wm,
-                               float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t, void* workspace,
-                               size_t workspace_bytes, int cluster, void* stream) {
+extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* q_meta, const void* bank_prep,
+                               const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H,
+                               int W, int Kp, float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
+                               void* workspace, size_t workspace_bytes, int cluster, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
     if (B == 0 || N == 0) return PP_OK;
-    PP_CHECK_ARG(q_prep && q_rnorm && bank_prep && bank_rnorm && tar_mask && sim_avg, "pp_match_scores: null pointer");
+    PP_CHECK_ARG(q_prep && q_rnorm && q_meta && bank_prep && bank_rnorm && sim_avg, "pp_match_scores: null pointer");
     PP_CHECK_ARG(H == W, "pp_match_scores: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
-    PP_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_scores: bad shape");
+    PP_CHECK_ARG(B > 0 && N > 0 && H > 0, "pp_match_scores: bad shape");
     PP_CHECK_ARG(bank_of_det != nullptr || n_banks == B, "pp_match_scores: identity bank mapping needs n_banks == B");
-    if (B == 0 || N == 0) return PP_OK;
     const int T = H * W;
     const size_t need = pp_match_scores_workspace(B, N, T);
     if (!workspace || workspace_bytes < need)
         return fail(PP_ERR_WORKSPACE, "pp_match_scores: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
     PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_scores: workspace must be 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    char* ws = static_cast<char*>(workspace);
-    float* mrow = reinterpret_cast<float*>(ws);
+    const QueryMeta qm = split_query_meta(const_cast<void*>(q_meta), B, T);
     const size_t keys = align_up((size_t)B * N * T * sizeof(unsigned long long), 256);
-    unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(ws + align_up((size_t)B * T * sizeof(float), 256));
-    unsigned long long* colkey = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(rowkey) + keys);
-
-    resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(tar_mask, B, Hm, Wm, H, W, mrow);
-    PP_LAUNCHED();
+    unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(workspace);
+    unsigned long long* colkey = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + keys);
     PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys, st));
-    if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, mrow, q_rnorm, bank_rnorm,
-                                rowkey, colkey, nullptr, 1.0f, cluster, st))
+    if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, qm.mrow, qm.tv, qm.rowmap, q_rnorm,
+                                bank_rnorm, rowkey, colkey, nullptr, 1.0f, cluster, st))
         return rc;
-    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, mrow, q_rnorm, N, T,
+    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, qm.mrow, q_rnorm, qm.rank, qm.fm, N, T,
                                                                       1.0f / (float)(H * H), sim_avg, score_t2s,
                                                                       idx_t2s, idx_s2t);
     PP_LAUNCHED();
@@ -220,7 +222,7 @@ extern "C" int pp_match_similarity(const void* q_prep, const float* q_rnorm, con
     PP_LAUNCHED();
     // one "view" per detection: banks == detections, N = 1
     if (int rc = run_match_gemm(1, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                sim, 1.0f, cluster, st))
+                                nullptr, nullptr, sim, 1.0f, cluster, st))
         return rc;
     const long long total = (long long)B * T * T;
     int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
@@ -242,7 +244,7 @@ extern "C" int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, 
     const int T = H * W;
     // all-pairs products <f1[:, q], f2[:, key]> * scale straight into level 0: (N*H*W, 1, H, W) is row-major [q][key]
     if (int rc = run_match_gemm(1, f1_prep, f2_prep, N, nullptr, N, 1, T, Kp, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                static_cast<float*>(level_ptrs[0]), scale, cluster, st))
+                                nullptr, nullptr, static_cast<float*>(level_ptrs[0]), scale, cluster, st))
         return rc;
     int h = H, w = W;
     for (int l = 1; l < num_levels; ++l) {

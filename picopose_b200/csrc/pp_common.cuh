@@ -39,6 +39,17 @@ bool take_profile_events(cudaEvent_t* start, cudaEvent_t* stop);
         ::pp::count_launch();         \
     } while (0)
 
+// Query-side bookkeeping produced by pp_match_prepare_query (see mask_compact_kernel).
+// q_meta layout (4-byte elements): mrow[B*T] | rank[B*T] | rowmap[B*T] | tv[B] | fm[B]
+struct QueryMeta {
+    float* mrow;   // (B,T) nearest-resized query mask
+    int* rank;     // (B,T) compact row of patch t, -1 if masked
+    int* rowmap;   // (B,T) patch of compact row r
+    int* tv;       // (B)   number of unmasked patches
+    int* fm;       // (B)   first masked patch, -1 if none
+};
+QueryMeta split_query_meta(void* q_meta, int B, int T);
+
 // Verifies the current device is sm_100 (cached per device).
 int require_sm100();
 int sm_count();

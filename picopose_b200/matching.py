@@ -23,6 +23,7 @@ import torch
 from . import _lib
 
 _WORKSPACE_LIMIT = int(os.environ.get("PICOPOSE_B200_WORKSPACE_MB", "1024")) << 20
+_MAX_DETS_PER_LAUNCH = 1024   # tile-prefix table of the contraction kernel lives in shared memory
 
 
 def default_mode() -> str:
@@ -148,8 +149,9 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
         bank_index = bank_index.to(device=tar_feat.device, dtype=torch.int32).contiguous()
     N, T = bank.n_views, H * W
     dev = tar_feat.device
-    q, q_rn = prepare_features(tar_feat, bank.mode, is_query=True)  # (B, T, Kp), (B, T)
-    kp = q.shape[-1]
+    mid = _mode_id(bank.mode)
+    kp = lib.pp_match_kp(Cc, mid)
+    feat = _as_f32(tar_feat)
     mask = _as_f32(tar_mask)
     Hm, Wm = mask.shape[-2:]
     sim_avg = torch.empty(B, N, dtype=torch.float32, device=dev)
@@ -161,13 +163,20 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
     cl = default_cluster() if cluster is None else cluster
     # bound the scratch (two 64-bit keys per (b, n, t)) by slicing the detection batch
     per_det = max(1, lib.pp_match_scores_workspace(1, N, T))
-    chunk = max(1, min(B, _WORKSPACE_LIMIT // per_det))
+    chunk = max(1, min(B, _WORKSPACE_LIMIT // per_det, _MAX_DETS_PER_LAUNCH))
     ws = torch.empty(lib.pp_match_scores_workspace(chunk, N, T), dtype=torch.uint8, device=dev)
+    q = torch.empty(chunk, T, kp, dtype=torch.bfloat16, device=dev)
+    q_rn = torch.empty(chunk, T, dtype=torch.float32, device=dev)
+    q_meta = torch.empty(lib.pp_match_query_meta_bytes(chunk, T), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         st = _lib.stream_of(tar_feat)
         for b0 in range(0, B, chunk):
             b1 = min(B, b0 + chunk)
             nb = b1 - b0
+            # query side: mask resize + compaction of the unmasked patches + cast/transposition + inverse norms
+            _lib.check(lib.pp_match_prepare_query(_lib.ptr(feat[b0:b1]), _lib.ptr(mask[b0:b1]), nb, Cc, H, W, Hm, Wm, mid,
+                                                  _lib.ptr(q), _lib.ptr(q_rn), _lib.ptr(q_meta), st),
+                       "pp_match_prepare_query")
             if bank_index is not None:
                 bidx, n_banks = _lib.ptr(bank_index[b0:b1]), bank.n_banks
                 bank_ptr, bank_rn = _lib.ptr(bank.prepared), _lib.ptr(bank.rnorm)
@@ -175,8 +184,7 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
                 bidx, n_banks = 0, nb
                 bank_ptr, bank_rn = _lib.ptr(bank.prepared[b0:b1]), _lib.ptr(bank.rnorm[b0:b1])
             _lib.check(lib.pp_match_scores(
-                _lib.ptr(q[b0:b1]), _lib.ptr(q_rn[b0:b1]), bank_ptr, bank_rn, n_banks, bidx, _lib.ptr(mask[b0:b1]),
-                nb, N, H, W, kp, Hm, Wm,
+                _lib.ptr(q), _lib.ptr(q_rn), _lib.ptr(q_meta), bank_ptr, bank_rn, n_banks, bidx, nb, N, H, W, kp,
                 _lib.ptr(sim_avg[b0:b1]), _lib.ptr(sc[b0:b1]) if want_indices else 0,
                 _lib.ptr(it[b0:b1]) if want_indices else 0, _lib.ptr(is_[b0:b1]) if want_indices else 0,
                 _lib.ptr(ws), ws.numel(), cl, st), "pp_match_scores")
