@@ -198,8 +198,10 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t total_tiles = compact ? tile_prefix[p.B] : p.total_tiles;
     auto decode = [&](uint32_t tile) { return compact ? decode_tile_prefix(tile, p, tile_prefix) : decode_tile(tile, p); };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ===================== TMA producer (every CTA) =====================
+        // The whole warp walks the loop (converged code keeps addresses and descriptors in uniform registers);
+        // one elected lane issues the copies and the barrier arrivals.
         int stage = 0;
         uint32_t phase = 0;
         for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -212,21 +214,24 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 mbar_wait(empty_bar(stage), phase ^ 1u, p.fault, 1, stage);
                 const uint32_t da = smem_a + stage * A_STAGE_BYTES;
                 const uint32_t db = smem_b + stage * Cfg::B_STAGE_BYTES;
-                if (CL == 1) {
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                    ptx::tma_load_2d(&tmap_a, full_bar(stage), da, kb * BLOCK_K, a_row);
-                    ptx::tma_load_2d(&tmap_b, full_bar(stage), db, kb * BLOCK_K, b_row);
-                } else {
-                    ptx::tma_load_2d_pair(&tmap_a, full_bar(stage), da, kb * BLOCK_K, a_row);
-                    ptx::tma_load_2d_pair(&tmap_b, full_bar(stage), db, kb * BLOCK_K, b_row);
-                    if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CL);
-                    else ptx::mbar_arrive_cluster(full_bar(stage), 0);
+                if (ptx::elect_one_sync()) {
+                    if (CL == 1) {
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                        ptx::tma_load_2d(&tmap_a, full_bar(stage), da, kb * BLOCK_K, a_row);
+                        ptx::tma_load_2d(&tmap_b, full_bar(stage), db, kb * BLOCK_K, b_row);
+                    } else {
+                        ptx::tma_load_2d_pair(&tmap_a, full_bar(stage), da, kb * BLOCK_K, a_row);
+                        ptx::tma_load_2d_pair(&tmap_b, full_bar(stage), db, kb * BLOCK_K, b_row);
+                        if (leader) ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CL);
+                        else ptx::mbar_arrive_cluster(full_bar(stage), 0);
+                    }
                 }
+                __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1 && lane == 0 && leader) {
-        // ===================== MMA issuer (leader CTA, one thread) =====================
+    } else if (warp == 1 && leader) {
+        // ===================== MMA issuer (leader CTA; converged warp, one elected lane issues) =====================
         constexpr uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, BLOCK_N);
         int stage = 0;
         uint32_t phase = 0;
@@ -242,14 +247,17 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 ptx::tc_fence_after();
                 const uint64_t adesc = ptx::smem_desc_sw128(smem_a + stage * A_STAGE_BYTES);
                 const uint64_t bdesc = ptx::smem_desc_sw128(smem_b + stage * Cfg::B_STAGE_BYTES);
+                if (ptx::elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    // advance 16 elements = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-                    ptx::umma_bf16<CL>(adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), tmem_d,
-                                       (kb > 0 || k > 0) ? 1u : 0u, idesc);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 elements = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+                        ptx::umma_bf16<CL>(adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), tmem_d,
+                                           (kb > 0 || k > 0) ? 1u : 0u, idesc);
+                    }
+                    ptx::umma_commit<CL>(empty_bar(stage));  // smem slot reusable once these MMAs retire
+                    if (kb == p.num_k_blocks - 1) ptx::umma_commit<CL>(tfull_bar(as));
                 }
-                ptx::umma_commit<CL>(empty_bar(stage));  // smem slot reusable once these MMAs retire
-                if (kb == p.num_k_blocks - 1) ptx::umma_commit<CL>(tfull_bar(as));
+                __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
