@@ -288,7 +288,11 @@ def run_ours(args):
         flops_exec = 2.0 * (hi - lo) * rows_exec * CFG["H"] ** 2 * CFG["C"]
         peak_tf, peak_gbs, peak_src = measured_peaks()
         ms_step = ms_total / args.steps
-        achieved = flops / (gemm_avg_ms * 1e-3) / 1e12
+        # roofline.achieved counts the tensor work really issued: masked query patches are rows of zeros in the
+        # reference and are dropped before the contraction, so the dense formula 2*B*N*T*S*C would read above the
+        # hardware peak; the dense-formula rate is reported beside it as algorithmic_*.
+        achieved = flops_exec / (gemm_avg_ms * 1e-3) / 1e12
+        algorithmic = flops / (gemm_avg_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
@@ -323,13 +327,14 @@ def run_ours(args):
                          "peak_source": "%s burst bf16 (MEASURED_PEAKS.json)" % peak_src if peak_src == "measured"
                          else "fallback 1.59 PFLOP/s",
                          "kernel_ms": gemm_avg_ms, "kernel_share_of_step": gemm_avg_ms / ms_step,
-                         "flops_per_launch": flops,
-                         "executed_flops_per_launch": flops_exec,
-                         "executed_tflops": flops_exec / (gemm_avg_ms * 1e-3) / 1e12,
-                         "executed_frac": flops_exec / (gemm_avg_ms * 1e-3) / 1e12 / peak_tf,
-                         "note": "achieved = algorithmic 2*B*N*T*S*C (SURVEY 8(d)) / kernel time; masked query patches "
-                                 "(%d of %d rows unmasked) are rows of zeros in the reference and are dropped before the "
-                                 "tensor cores, executed_* counts only the MMA work really issued"
+                         "flops_per_launch": flops_exec,
+                         "algorithmic_flops_per_launch": flops,
+                         "algorithmic_tflops": algorithmic,
+                         "algorithmic_frac": algorithmic / peak_tf,
+                         "note": "achieved = MMA FLOPs issued / kernel time: 2*N*S*C per unmasked query row, rows padded to "
+                                 "the 256-row CTA-pair tile (%d of %d query rows unmasked; masked patches are rows of "
+                                 "zeros in the reference and never reach the tensor cores). algorithmic_* uses the dense "
+                                 "SURVEY 8(d) formula 2*B*N*T*S*C and may exceed the peak for that reason"
                                  % (rows_unmasked, world * CFG["H"] ** 2)},
             "warm_bank": {"value": world * 1e3 / (warm_ms_total / args.steps), "unit": "detections/s",
                           "note": "template bank normalised/cast once and kept resident (TemplateBank); not the headline"},
