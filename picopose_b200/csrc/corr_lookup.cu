@@ -433,7 +433,7 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
             case 5: return launch_banded<5, 4>(p, st);
             case 6: return launch_banded<6, 5>(p, st);
             case 7: return launch_banded<7, 5>(p, st);
-            case 8: return launch_banded<8, 6>(p, st);
+            case 8: return launch_banded<8, 3>(p, st);
             default: break;
         }
     }

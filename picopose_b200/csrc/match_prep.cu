@@ -49,24 +49,18 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
     const int* seg_tab = is_query ? SEG_Q : SEG_B;
     const int nchunks = (C + PREP_CT - 1) / PREP_CT;
 
-    // thread owns patch `lane` and channels 64*j + 8*warp + i of chunk j
-    float cur[8], nxt[8];
+    // thread owns patch `lane` and channels 64*j + 8*warp + i of chunk j; loads run two chunks ahead of the
+    // transposition (three register buffers, rotated by a 3x unrolled loop) to cover the global latency
+    auto load_chunk = [&](float (&dst)[8], int j) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = warp * 8 + i;
-        cur[i] = c < C ? __ldg(x + (size_t)c * P) : 0.f;
-        nxt[i] = 0.f;
-    }
-    float ss = 0.f;
-    for (int j = 0; j < nchunks; ++j) {
-        const int c0 = j * PREP_CT;
-        if (j + 1 < nchunks) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = c0 + PREP_CT + warp * 8 + i;
-                nxt[i] = c < C ? __ldg(x + (size_t)c * P) : 0.f;
-            }
+        for (int i = 0; i < 8; ++i) {
+            const int c = j * PREP_CT + warp * 8 + i;
+            dst[i] = (j < nchunks && c < C) ? __ldg(x + (size_t)c * P) : 0.f;
         }
+    };
+    float ss = 0.f;
+    auto process = [&](const float (&cur)[8], int j) {
+        const int c0 = j * PREP_CT;
         __align__(16) __nv_bfloat16 part[NPARTS][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -97,8 +91,21 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
                 }
             }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    };
+    float b0[8], b1[8], b2[8];
+    load_chunk(b0, 0);
+    load_chunk(b1, 1);
+    for (int j = 0; j < nchunks; j += 3) {
+        load_chunk(b2, j + 2);
+        process(b0, j);
+        if (j + 1 < nchunks) {
+            load_chunk(b0, j + 3);
+            process(b1, j + 1);
+        }
+        if (j + 2 < nchunks) {
+            load_chunk(b1, j + 4);
+            process(b2, j + 2);
+        }
     }
     // ---- inverse norm per patch: 1 / max(||x||, 1e-12)  (F.normalize's clamp_min(eps)) ----
     s_part[warp][lane] = ss;
@@ -138,33 +145,44 @@ mask_compact_kernel(const float* __restrict__ mask, int Hm, int Wm, int H, int W
     if (threadIdx.x == 0) s_fm = 0x7fffffff;
     __syncthreads();
     int base = 0;
-    for (int t0 = 0; t0 < T; t0 += 256) {
-        const int t = t0 + threadIdx.x;
-        float m = 0.f;
-        if (t < T) {
-            const int y = t / W, x = t - y * W;
-            m = mask[((size_t)b * Hm + nearest_src(y, Hm, H)) * Wm + nearest_src(x, Wm, W)];
-        }
-        const bool on = t < T && m != 0.f;
-        const unsigned ball = __ballot_sync(0xffffffffu, on);
-        if (lane == 0) s_warp[warp] = __popc(ball);
-        __syncthreads();
-        int before = 0, total = 0;
+    for (int t00 = 0; t00 < T; t00 += 4 * 256) {
+        // four 256-patch slabs per trip: all mask loads are issued before the first scan step needs them
+        float mv[4];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const int c = s_warp[w];
-            if (w < warp) before += c;
-            total += c;
+        for (int u = 0; u < 4; ++u) {
+            const int t = t00 + u * 256 + threadIdx.x;
+            mv[u] = 0.f;
+            if (t < T) {
+                const int y = t / W, x = t - y * W;
+                mv[u] = __ldg(mask + ((size_t)b * Hm + nearest_src(y, Hm, H)) * Wm + nearest_src(x, Wm, W));
+            }
         }
-        const int r = base + before + __popc(ball & ((1u << lane) - 1u));
-        if (t < T) {
-            mrow[(size_t)b * T + t] = m;
-            rank[(size_t)b * T + t] = on ? r : -1;
-            if (on) rowmap[(size_t)b * T + r] = t;
-            else atomicMin(&s_fm, t);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t00 + u * 256 + threadIdx.x;
+            if (t00 + u * 256 >= T) break;  // block-uniform
+            const float m = mv[u];
+            const bool on = t < T && m != 0.f;
+            const unsigned ball = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) s_warp[warp] = __popc(ball);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int c = s_warp[w];
+                if (w < warp) before += c;
+                total += c;
+            }
+            const int r = base + before + __popc(ball & ((1u << lane) - 1u));
+            if (t < T) {
+                mrow[(size_t)b * T + t] = m;
+                rank[(size_t)b * T + t] = on ? r : -1;
+                if (on) rowmap[(size_t)b * T + r] = t;
+                else atomicMin(&s_fm, t);
+            }
+            base += total;
+            __syncthreads();
         }
-        base += total;
-        __syncthreads();
     }
     if (threadIdx.x == 0) {
         tv[b] = base;
