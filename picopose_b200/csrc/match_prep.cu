@@ -51,11 +51,16 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
 
     // thread owns patch `lane` and channels 64*j + 8*warp + i of chunk j; loads run two chunks ahead of the
     // transposition (three register buffers, rotated by a 3x unrolled loop) to cover the global latency
+    const size_t strideP = (size_t)P;
     auto load_chunk = [&](float (&dst)[8], int j) {
+        if (j >= nchunks) return;                                    // block-uniform
+        const float* xc = x + (size_t)(j * PREP_CT + warp * 8) * strideP;
+        if ((j + 1) * PREP_CT <= C) {                                // full chunk: no per-channel bounds checks
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = j * PREP_CT + warp * 8 + i;
-            dst[i] = (j < nchunks && c < C) ? __ldg(x + (size_t)c * P) : 0.f;
+            for (int i = 0; i < 8; ++i) dst[i] = __ldg(xc + i * strideP);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = (j * PREP_CT + warp * 8 + i < C) ? __ldg(xc + i * strideP) : 0.f;
         }
     };
     float ss = 0.f;
@@ -85,9 +90,14 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
         if (p0 + row < P && u < n_units) {
             const int orow = rank ? rank[(size_t)g * P + p0 + row] : p0 + row;
             if (orow >= 0) {
-                for (int s = 0; s < nseg; ++s) {
-                    const uint4 val = *reinterpret_cast<const uint4*>(&s_tile[j & 1][seg_tab[s]][row][(u ^ (row & 7)) * 8]);
-                    *reinterpret_cast<uint4*>(out_g + (size_t)orow * Kp + (size_t)s * C + c0 + u * 8) = val;
+                __nv_bfloat16* dst = out_g + (size_t)orow * Kp + c0 + u * 8;
+                if (NPARTS == 1) {  // bf16 mode: one segment
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&s_tile[j & 1][0][row][(u ^ (row & 7)) * 8]);
+                } else {
+                    for (int s = 0; s < nseg; ++s) {
+                        const uint4 val = *reinterpret_cast<const uint4*>(&s_tile[j & 1][seg_tab[s]][row][(u ^ (row & 7)) * 8]);
+                        *reinterpret_cast<uint4*>(dst + (size_t)s * C) = val;
+                    }
                 }
             }
         }
