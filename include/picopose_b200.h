@@ -111,18 +111,27 @@ PP_API size_t pp_match_scores_workspace(int B, int N, int T);
  *   bank_prep, bank_rnorm : (n_banks, N, T, Kp) bf16 / (n_banks, N, T) fp32   prepared template banks
  *   bank_of_det : (B,) int32 device array, bank used by detection b; NULL = identity (n_banks == B)
  *   sim_avg   : (B, N) fp32 out
- *   optional outs (NULL to skip): score_t2s (B,N,T) fp32, idx_t2s (B,N,T) int32, idx_s2t (B,N,T) int32
+ *   optional outs (NULL to skip): score_t2s (B,N,T) fp32, idx_t2s (B,N,T) int32, idx_s2t (B,N,T) int32,
+ *   mutual_nn (B,N,T) uint8 = 1 where query patch t and template patch idx_t2s[t] are mutual nearest neighbours
  *   cluster   : 0 = default, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
  */
 PP_API int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* q_meta, const void* bank_prep,
                     const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H, int W, int Kp,
-                    float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
+                    float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t, uint8_t* mutual_nn,
                     void* workspace, size_t workspace_bytes, int cluster, void* stream);
 
 /* Row-wise top-k (descending, lowest index first on ties).  Replaces torch.topk, utils/matching.py:68.
  *   scores (B,N) fp32 -> out_score (B,k) fp32, out_idx (B,k) int64 (+ idx_offset, for sharded banks). */
 PP_API int pp_topk(const float* scores, int B, int N, int k, int64_t idx_offset,
             float* out_score, int64_t* out_idx, void* stream);
+
+/* Multi-GPU merge of sharded template banks: pp_topk_pairs writes each rank's local top-k as (score, global index)
+ * pairs of doubles, (B, k, 2), padded with (-inf, -1) when the shard holds fewer than k views -- one tensor to
+ * all-gather; pp_topk_merge reduces the gathered (R, B, k_in, 2) lists to the global top-k of every row
+ * (ties: lowest rank, then lowest slot).  Together they replace torch.topk over the full view axis, utils/matching.py:68. */
+PP_API int pp_topk_pairs(const float* scores, int B, int N, int k, int64_t idx_offset, double* out_pairs, void* stream);
+PP_API int pp_topk_merge(const double* pairs, int R, int B, int k_in, int k, float* out_score, int64_t* out_idx,
+                  void* stream);
 
 /* Stage-2 input volume.  Replaces matching_features_similarity, utils/matching.py:6-26.
  *   q_prep/q_rnorm, s_prep/s_rnorm : (B, T, Kp) / (B, T) prepared query / template features; src_mask (B,Hm,Wm) fp32

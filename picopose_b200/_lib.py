@@ -31,9 +31,11 @@ SIGNATURES = {
     "pp_match_scores_workspace": (_sz, [_i, _i, _i]),
     "pp_match_query_meta_bytes": (_sz, [_i, _i]),
     "pp_match_prepare_query": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "pp_match_scores": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz,
+    "pp_match_scores": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                              _i, _vp]),
     "pp_topk": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
+    "pp_topk_pairs": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp]),
+    "pp_topk_merge": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_match_similarity_workspace": (_sz, [_i, _i]),
     "pp_match_similarity": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pp_correlation_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), _i, _vp]),

@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256)
 finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
                        const float* __restrict__ mrow, const float* __restrict__ ra, const int* __restrict__ rank,
                        const int* __restrict__ fm, int N, int T, float inv_hh, float* __restrict__ sim_avg,
-                       float* __restrict__ score_t2s, int32_t* __restrict__ idx_t2s, int32_t* __restrict__ idx_s2t) {
+                       float* __restrict__ score_t2s, int32_t* __restrict__ idx_t2s, int32_t* __restrict__ idx_s2t,
+                       uint8_t* __restrict__ mutual) {
     const size_t bn = blockIdx.x;
     const int b = (int)(bn / N);
     // masked query rows never entered the contraction; in the reference they are rows of zeros that take part in
@@ -54,6 +55,13 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
         if (score_t2s) score_t2s[bn * T + j] = sc;
         if (idx_t2s) idx_t2s[bn * T + j] = it;
         if (idx_s2t) idx_s2t[bn * T + j] = is;
+        if (mutual) {
+            // mutual nearest neighbours: query patch j -> template patch `it` and back to j (extra output; the
+            // reference only applies its argmax != 0 heuristic)
+            unsigned long long back = colkey[bn * T + it];
+            back = back > zero_key ? back : zero_key;
+            mutual[bn * T + j] = (on && rk && back && (int)key_index(back) == j) ? 1 : 0;
+        }
     }
     __shared__ float s_sum[8], s_cnt[8];
     for (int o = 16; o > 0; o >>= 1) {
@@ -72,7 +80,7 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
 // Row-wise top-k by repeated block arg-max; ties resolve to the lowest index (torch leaves them unspecified).
 __global__ void __launch_bounds__(256)
 topk_kernel(const float* __restrict__ scores, int N, int k, long long idx_offset, float* __restrict__ out_score,
-            long long* __restrict__ out_idx) {
+            long long* __restrict__ out_idx, double* __restrict__ out_pair, int kpad) {
     extern __shared__ unsigned long long s_keys[];  // N packed keys + 8 partials
     unsigned long long* s_red = s_keys + N;
     const int b = blockIdx.x;
@@ -90,11 +98,49 @@ topk_kernel(const float* __restrict__ scores, int N, int k, long long idx_offset
         if (threadIdx.x == 0) {
             for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_red[w] > best ? s_red[w] : best;
             const uint32_t idx = key_index(best);
-            out_score[(size_t)b * k + r] = key_value(best);
-            out_idx[(size_t)b * k + r] = (long long)idx + idx_offset;
+            if (out_score) out_score[(size_t)b * k + r] = key_value(best);
+            if (out_idx) out_idx[(size_t)b * k + r] = (long long)idx + idx_offset;
+            if (out_pair) {  // (score, index) as two doubles: one tensor to all-gather across ranks
+                out_pair[((size_t)b * kpad + r) * 2 + 0] = (double)key_value(best);
+                out_pair[((size_t)b * kpad + r) * 2 + 1] = (double)((long long)idx + idx_offset);
+            }
             s_keys[idx] = 0ull;  // remove the winner
         }
         __syncthreads();
+    }
+    if (out_pair && threadIdx.x < kpad - k) {  // shard with fewer than kpad views: pad with (-inf, -1)
+        out_pair[((size_t)b * kpad + k + threadIdx.x) * 2 + 0] = -INFINITY;
+        out_pair[((size_t)b * kpad + k + threadIdx.x) * 2 + 1] = -1.0;
+    }
+}
+
+// Merge of per-rank candidate lists (R, B, k_in) of (score, index) pairs into the global top-k of each row:
+// one warp per row, ties go to the lowest rank / slot (= lowest global view index for contiguous shards).
+__global__ void __launch_bounds__(32)
+topk_merge_kernel(const double* __restrict__ pairs, int R, int B, int k_in, int k, float* __restrict__ out_score,
+                  long long* __restrict__ out_idx) {
+    extern __shared__ unsigned long long s_keys[];
+    const int b = blockIdx.x, lane = threadIdx.x, n = R * k_in;
+    for (int i = lane; i < n; i += 32) {
+        const int r = i / k_in, j = i - r * k_in;
+        s_keys[i] = pack_key((float)pairs[(((size_t)r * B + b) * k_in + j) * 2] + 0.0f, (uint32_t)i);
+    }
+    __syncwarp();
+    for (int o = 0; o < k; ++o) {
+        unsigned long long best = 0ull;
+        for (int i = lane; i < n; i += 32) best = s_keys[i] > best ? s_keys[i] : best;
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, sft);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) {
+            const uint32_t pos = key_index(best);
+            const int r = pos / k_in, j = pos - r * k_in;
+            out_score[(size_t)b * k + o] = key_value(best);
+            out_idx[(size_t)b * k + o] = (long long)pairs[(((size_t)r * B + b) * k_in + j) * 2 + 1];
+            s_keys[pos] = 0ull;
+        }
+        __syncwarp();
     }
 }
 
@@ -144,7 +190,7 @@ extern "C" size_t pp_match_scores_workspace(int B, int N, int T) {
 extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* q_meta, const void* bank_prep,
                                const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H,
                                int W, int Kp, float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
-                               void* workspace, size_t workspace_bytes, int cluster, void* stream) {
+                               uint8_t* mutual_nn, void* workspace, size_t workspace_bytes, int cluster, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
     if (B == 0 || N == 0) return PP_OK;
@@ -168,7 +214,7 @@ extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const v
         return rc;
     finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, qm.mrow, q_rnorm, qm.rank, qm.fm, N, T,
                                                                       1.0f / (float)(H * H), sim_avg, score_t2s,
-                                                                      idx_t2s, idx_s2t);
+                                                                      idx_t2s, idx_s2t, mutual_nn);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -187,7 +233,37 @@ extern "C" int pp_topk(const float* scores, int B, int N, int k, int64_t idx_off
     if (smem > 48 * 1024)
         PP_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, N, k, (long long)idx_offset, out_score,
-                                                                    reinterpret_cast<long long*>(out_idx));
+                                                                    reinterpret_cast<long long*>(out_idx), nullptr, k);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_topk_pairs(const float* scores, int B, int N, int k, int64_t idx_offset, double* out_pairs,
+                             void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (B == 0 || k == 0) return PP_OK;
+    PP_CHECK_ARG(scores && out_pairs, "pp_topk_pairs: null pointer");
+    PP_CHECK_ARG(k > 0 && k <= 256 && N >= 0 && N <= 24000, "pp_topk_pairs: bad sizes (k=%d, N=%d)", k, N);
+    const int kl = k < N ? k : N;  // a shard may hold fewer than k views: the rest is padding
+    const size_t smem = ((size_t)N + 8) * sizeof(unsigned long long);
+    if (smem > 48 * 1024)
+        PP_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, N, kl, (long long)idx_offset, nullptr,
+                                                                    nullptr, out_pairs, k);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_topk_merge(const double* pairs, int R, int B, int k_in, int k, float* out_score, int64_t* out_idx,
+                             void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (B == 0 || k == 0) return PP_OK;
+    PP_CHECK_ARG(pairs && out_score && out_idx, "pp_topk_merge: null pointer");
+    PP_CHECK_ARG(R > 0 && k_in > 0 && k > 0 && k <= R * k_in && R * k_in <= 4096, "pp_topk_merge: bad sizes");
+    topk_merge_kernel<<<B, 32, (size_t)R * k_in * sizeof(unsigned long long), static_cast<cudaStream_t>(stream)>>>(
+        pairs, R, B, k_in, k, out_score, reinterpret_cast<long long*>(out_idx));
     PP_LAUNCHED();
     return PP_OK;
 }

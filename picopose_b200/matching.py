@@ -124,12 +124,14 @@ def _resolve_bank(src_feats, mode, B):
 
 def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *, mode: Optional[str] = None,
                     bank_index: Optional[torch.Tensor] = None, want_indices: bool = False,
-                    cluster: Optional[int] = None):
+                    want_mutual: bool = False, cluster: Optional[int] = None):
     """Dense scores sim_avg (B, N) of utils/matching.py:38-67.
 
     With want_indices also returns (score_t2s (B,N,T) f32, idx_t2s (B,N,T) i32, idx_s2t (B,N,T) i32): the
     bidirectional nearest-neighbour patch correspondences the reference computes at :50-51.
-    `bank_index` (B,) maps detections to banks of a shared TemplateBank.
+    want_mutual appends mutual_nn (B,N,T) uint8: 1 where query patch t and template patch idx_t2s[t] pick each
+    other (an extra the reference does not compute).  `bank_index` (B,) maps detections to banks of a shared
+    TemplateBank.
     """
     _lib.require_cuda(tar_feat, tar_mask)
     lib = _lib.load()
@@ -155,7 +157,10 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
     mask = _as_f32(tar_mask)
     Hm, Wm = mask.shape[-2:]
     sim_avg = torch.empty(B, N, dtype=torch.float32, device=dev)
-    sc = it = is_ = None
+    sc = it = is_ = mu = None
+    if want_mutual:
+        want_indices = True
+        mu = torch.empty(B, N, T, dtype=torch.uint8, device=dev)
     if want_indices:
         sc = torch.empty(B, N, T, dtype=torch.float32, device=dev)
         it = torch.empty(B, N, T, dtype=torch.int32, device=dev)
@@ -187,7 +192,9 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
                 _lib.ptr(q), _lib.ptr(q_rn), _lib.ptr(q_meta), bank_ptr, bank_rn, n_banks, bidx, nb, N, H, W, kp,
                 _lib.ptr(sim_avg[b0:b1]), _lib.ptr(sc[b0:b1]) if want_indices else 0,
                 _lib.ptr(it[b0:b1]) if want_indices else 0, _lib.ptr(is_[b0:b1]) if want_indices else 0,
-                _lib.ptr(ws), ws.numel(), cl, st), "pp_match_scores")
+                _lib.ptr(mu[b0:b1]) if want_mutual else 0, _lib.ptr(ws), ws.numel(), cl, st), "pp_match_scores")
+    if want_mutual:
+        return sim_avg, sc, it, is_, mu
     if want_indices:
         return sim_avg, sc, it, is_
     return sim_avg

@@ -2,8 +2,8 @@
 
 One process per GPU (torchrun).  Rank g keeps views [lo_g, hi_g) of every object's template bank
 (prepared bf16, resident), all ranks see the whole detection batch, each computes its local
-sim_avg[:, lo_g:hi_g] and a local top-k with GLOBAL view indices, and a single NCCL all-gather of the
-(B, k) score / index pairs over NVLink is merged identically on every rank.  Every (detection, view)
+sim_avg[:, lo_g:hi_g] and a local top-k with GLOBAL view indices packed as one (B, k, 2) tensor, and a single
+NCCL all-gather of those pairs over NVLink is merged identically on every rank by one small kernel.  Every (detection, view)
 score is independent (utils/matching.py:47-67); only topk (:68) couples views, hence one exchange.
 """
 from __future__ import annotations
@@ -21,52 +21,73 @@ def shard_range(n_views: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def _select_cuda(scores: torch.Tensor, k: int):
-    from .matching import topk_scores
-    return topk_scores(scores, k)
+def topk_pairs(sim: torch.Tensor, k: int, idx_offset: int = 0) -> torch.Tensor:
+    """Local top-k of (B, N_local) scores as one (B, k, 2) float64 tensor of (score, global index) pairs,
+    padded with (-inf, -1) when the shard has fewer than k views."""
+    from . import _lib
+    _lib.require_cuda(sim)
+    lib = _lib.load()
+    sim = sim.float().contiguous()
+    B, N = sim.shape
+    out = torch.empty(B, k, 2, dtype=torch.float64, device=sim.device)
+    if N == 0:
+        out[..., 0] = float("-inf")
+        out[..., 1] = -1
+        return out
+    with torch.cuda.device(sim.device):
+        _lib.check(lib.pp_topk_pairs(_lib.ptr(sim), B, N, k, idx_offset, _lib.ptr(out), _lib.stream_of(sim)),
+                   "pp_topk_pairs")
+    return out
 
 
-def merge_topk(local_score: torch.Tensor, local_idx: torch.Tensor, k: int, group=None,
-               select: Optional[Callable] = None):
-    """All-gathers per-rank candidates (B, k_local) and keeps the global top-k (sorted, ties -> lowest rank/slot).
+def _merge_cuda(gathered: torch.Tensor, k: int):
+    """gathered (R, B, k_in, 2) float64 on a CUDA device -> (score (B,k) f32, idx (B,k) i64)."""
+    from . import _lib
+    lib = _lib.load()
+    R, B, k_in, _ = gathered.shape
+    score = torch.empty(B, k, dtype=torch.float32, device=gathered.device)
+    idx = torch.empty(B, k, dtype=torch.int64, device=gathered.device)
+    with torch.cuda.device(gathered.device):
+        _lib.check(lib.pp_topk_merge(_lib.ptr(gathered), R, B, k_in, k, _lib.ptr(score), _lib.ptr(idx),
+                                     _lib.stream_of(gathered)), "pp_topk_merge")
+    return score, idx
 
-    Ranks whose shard holds fewer than k views pad with (-inf, -1).  `select(scores, k) -> (values, positions)`
-    defaults to the library's top-k kernel; tests on CPU/gloo inject a torch.topk-based one.
-    """
+
+def _merge_torch(gathered: torch.Tensor, k: int):
+    """Same selection rule in plain torch ops; used by the CPU/gloo tests of the exchange plumbing only."""
+    R, B, k_in, _ = gathered.shape
+    flat = gathered.permute(1, 0, 2, 3).reshape(B, R * k_in, 2)
+    order = torch.argsort(flat[..., 0], dim=1, descending=True, stable=True)[:, :k]   # stable: lowest rank/slot first
+    picked = torch.gather(flat, 1, order.unsqueeze(-1).expand(B, k, 2))
+    return picked[..., 0].float(), picked[..., 1].long()
+
+
+def merge_topk(local_pairs: torch.Tensor, k: int, group=None, merge: Optional[Callable] = None):
+    """One all-gather of every rank's (B, k, 2) candidate pairs, then the same merge on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    B, kl = local_score.shape
-    if kl < k:
-        pad_s = torch.full((B, k - kl), float("-inf"), dtype=local_score.dtype, device=local_score.device)
-        pad_i = torch.full((B, k - kl), -1, dtype=local_idx.dtype, device=local_idx.device)
-        local_score = torch.cat([local_score, pad_s], dim=1)
-        local_idx = torch.cat([local_idx, pad_i], dim=1)
-    local_score = local_score.contiguous()
-    local_idx = local_idx.contiguous()
+    B, k_in, _ = local_pairs.shape
+    local_pairs = local_pairs.contiguous()
     if world == 1:
-        all_s, all_i = local_score, local_idx
+        gathered = local_pairs.unsqueeze(0)
     else:
         # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
-        gs = torch.empty(world * B, k, dtype=local_score.dtype, device=local_score.device)
-        gi = torch.empty(world * B, k, dtype=local_idx.dtype, device=local_idx.device)
-        dist.all_gather_into_tensor(gs, local_score, group=group)
-        dist.all_gather_into_tensor(gi, local_idx, group=group)
-        all_s = gs.view(world, B, k).permute(1, 0, 2).reshape(B, world * k)
-        all_i = gi.view(world, B, k).permute(1, 0, 2).reshape(B, world * k)
-    select = select or _select_cuda
-    val, pos = select(all_s.contiguous(), k)
-    return val, torch.gather(all_i, 1, pos)
+        flat = torch.empty(world * B, k_in, 2, dtype=local_pairs.dtype, device=local_pairs.device)
+        dist.all_gather_into_tensor(flat, local_pairs, group=group)
+        gathered = flat.view(world, B, k_in, 2)
+    merge = merge or (_merge_cuda if local_pairs.is_cuda else _merge_torch)
+    return merge(gathered, k)
 
 
 class ShardedMatcher:
     """Template-sharded `matching_templates` over a process group."""
 
-    def __init__(self, n_views: int, group=None, select: Optional[Callable] = None):
+    def __init__(self, n_views: int, group=None, merge: Optional[Callable] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.n_views = n_views
         self.lo, self.hi = shard_range(n_views, self.rank, self.world)
-        self.select = select
+        self.merge = merge
         self.bank = None
 
     def load_bank(self, src_feats_shard: torch.Tensor, mode: Optional[str] = None):
@@ -81,12 +102,6 @@ class ShardedMatcher:
         from .matching import template_scores, topk_scores
         src = self.bank if src is None else src
         sim = template_scores(src, tar_feat, tar_mask, mode=mode, bank_index=bank_index)     # (B, hi-lo)
-        kl = min(topk, sim.shape[1])
-        if kl > 0:
-            s, i = topk_scores(sim, kl, idx_offset=self.lo)
-        else:
-            s = sim.new_empty(sim.shape[0], 0)
-            i = torch.empty(sim.shape[0], 0, dtype=torch.int64, device=sim.device)
-        if self.world == 1 and kl == topk:
-            return s, i                      # single rank: the local top-k is the answer, nothing to exchange
-        return merge_topk(s, i, topk, self.group, self.select)
+        if self.world == 1 and sim.shape[1] >= topk:
+            return topk_scores(sim, topk, idx_offset=self.lo)   # single rank: nothing to exchange
+        return merge_topk(topk_pairs(sim, topk, idx_offset=self.lo), topk, self.group, self.merge)

@@ -298,6 +298,21 @@ def test_matching_shared_bank_and_chunking(monkeypatch):
     assert torch.equal(ref.argmax(dim=1).cpu(), top1)
 
 
+def test_mutual_nearest_neighbour_output():
+    from picopose_b200.matching import template_scores
+    src, tar, _ = synth.planted_match_inputs(2, 4, 64, 8, seed=5)
+    mask = synth.bernoulli_mask(2, 224, 0.8, 9)
+    _, _, it_ref, is_ref = OM.template_scores(src, tar, mask, want_indices=True)
+    _, _, it, is_, mu = template_scores(src.to(DEV), tar.to(DEV), mask.to(DEV), mode="fp32", want_mutual=True)
+    m = OM.nearest_mask(mask, 8, 8)                                    # (B,T)
+    T = 64
+    back = torch.gather(is_ref, 2, it_ref)                             # idx_s2t[idx_t2s[t]]
+    expect = (back == torch.arange(T).view(1, 1, T)) & (m.view(2, 1, T) != 0)
+    assert torch.equal(it.cpu().long(), it_ref) and torch.equal(is_.cpu().long(), is_ref)
+    assert torch.equal(mu.cpu().bool(), expect)
+    assert int(mu.sum()) > 0
+
+
 def test_matching_config2_properties():
     """BASELINE config 2 at full size (1 x 162 x 1024 x 32^2): the planted ranking is recovered in both
     arithmetic modes, both CTA groupings agree bit for bit, and reruns are deterministic."""
@@ -392,6 +407,24 @@ def test_stage3_level_end_to_end():
     warp_ref = OL.bilinear_sample(f2, grid, align_corners=True)
     warp = bilinear_sample(f2.to(DEV), grid.to(DEV), align_corners=True)
     np.testing.assert_allclose(warp.cpu().numpy(), warp_ref.numpy(), rtol=0, atol=1e-5)
+
+
+def test_topk_pairs_and_merge():
+    """The multi-GPU exchange kernels on one device: shard a score matrix into 3 ragged 'ranks', take the local
+    top-k pairs, stack them as the all-gather would, merge -> equals torch.topk over the full row."""
+    from picopose_b200.sharded import _merge_cuda, _merge_torch, shard_range, topk_pairs
+    gen = torch.Generator().manual_seed(21)
+    full = torch.randn(7, 11, generator=gen).to(DEV)
+    k, world = 5, 3
+    parts = [topk_pairs(full[:, lo:hi].contiguous(), k, idx_offset=lo)
+             for lo, hi in (shard_range(11, r, world) for r in range(world))]
+    gathered = torch.stack(parts)                                   # (R, B, k, 2): shards hold 4, 4, 3 < k views
+    assert bool((gathered[2, :, 3:, 1] == -1).all()) and bool(torch.isinf(gathered[2, :, 3:, 0]).all())
+    score, idx = _merge_cuda(gathered, k)
+    rs, ri = torch.topk(full, k, dim=1)
+    assert torch.equal(score, rs) and torch.equal(idx, ri)
+    s2, i2 = _merge_torch(gathered.cpu(), k)
+    assert torch.equal(s2, rs.cpu()) and torch.equal(i2, ri.cpu())
 
 
 def test_topk_matches_torch():

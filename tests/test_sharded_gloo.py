@@ -17,8 +17,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _cpu_select(scores, k):
-    return torch.topk(scores, k, dim=1)
+def _pairs(score, idx, k):
+    """(B, kl) local top-k -> (B, k, 2) float64 pairs padded with (-inf, -1), like pp_topk_pairs."""
+    B, kl = score.shape
+    out = torch.empty(B, k, 2, dtype=torch.float64)
+    out[..., 0] = float("-inf")
+    out[..., 1] = -1
+    out[:, :kl, 0] = score.double()
+    out[:, :kl, 1] = idx.double()
+    return out
 
 
 def _worker(rank, world, port, n_views, k, ret):
@@ -33,7 +40,7 @@ def _worker(rank, world, port, n_views, k, ret):
         local = full[:, lo:hi]
         kl = min(k, hi - lo)
         s, i = torch.topk(local, kl, dim=1)
-        val, idx = merge_topk(s, i + lo, k, select=_cpu_select)
+        val, idx = merge_topk(_pairs(s, i + lo, k), k)          # CPU tensors -> torch merge, gloo all-gather
         ref_v, ref_i = torch.topk(full, k, dim=1)
         ok = torch.equal(val, ref_v) and torch.equal(idx, ref_i)
         gathered = [None] * world
@@ -60,5 +67,5 @@ def test_merge_topk_single_process_no_group():
     from picopose_b200.sharded import merge_topk
     s = torch.tensor([[0.75, 0.5, 0.25]])
     i = torch.tensor([[4, 2, 7]])
-    v, idx = merge_topk(s, i, 2, select=_cpu_select)
+    v, idx = merge_topk(_pairs(s, i, 3), 2)
     assert v.tolist() == [[0.75, 0.5]] and idx.tolist() == [[4, 2]]
