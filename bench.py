@@ -210,9 +210,11 @@ def run_ours(args):
     sampler.start()
     barrier()
     t0.record()
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         lib.pp_profile_gemm_events(gemm_events[i][0].cuda_event, gemm_events[i][1].cuda_event)
         step(tar_d, mask_d, src_d)
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # time the host needs to enqueue one step
     t1.record()
     barrier()
     clocks = sampler.stop()
@@ -321,7 +323,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": world * 1e3 / (e2e_ms_total / args.steps), "unit": "detections/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "roofline": {"bound": "tensor", "kernel": "match_gemm_kernel", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                          "peak_source": "%s burst bf16 (MEASURED_PEAKS.json)" % peak_src if peak_src == "measured"

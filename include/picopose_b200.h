@@ -125,6 +125,16 @@ PP_API int pp_match_scores(const void* q_prep, const float* q_rnorm, const void*
 PP_API int pp_topk(const float* scores, int B, int N, int k, int64_t idx_offset,
             float* out_score, int64_t* out_idx, void* stream);
 
+/* One-call form of the stage-1 ranking against prepared banks: pp_match_prepare_query + pp_match_scores + pp_topk
+ * with a single caller-provided workspace.  Replaces matching_templates, utils/matching.py:29-69, for banks that
+ * were prepared once with pp_match_prepare (the reference re-normalises them on every call, :43).
+ *   out_score (B,k) fp32, out_idx (B,k) int64; sim_avg_out (B,N) fp32 optional dense scores (NULL to skip). */
+PP_API size_t pp_match_templates_workspace(int B, int N, int C, int H, int W, int mode);
+PP_API int pp_match_templates(const float* tar_feat, const float* tar_mask, const void* bank_prep, const float* bank_rnorm,
+                       int64_t n_banks, const int32_t* bank_of_det, int B, int N, int C, int H, int W, int Hm, int Wm,
+                       int mode, int k, float* out_score, int64_t* out_idx, float* sim_avg_out,
+                       void* workspace, size_t workspace_bytes, int cluster, void* stream);
+
 /* Multi-GPU merge of sharded template banks: pp_topk_pairs writes each rank's local top-k as (score, global index)
  * pairs of doubles, (B, k, 2), padded with (-inf, -1) when the shard holds fewer than k views -- one tensor to
  * all-gather; pp_topk_merge reduces the gathered (R, B, k_in, 2) lists to the global top-k of every row

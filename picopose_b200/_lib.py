@@ -34,6 +34,9 @@ SIGNATURES = {
     "pp_match_scores": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                              _i, _vp]),
     "pp_topk": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp]),
+    "pp_match_templates_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "pp_match_templates": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz,
+                                _i, _vp]),
     "pp_topk_pairs": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp]),
     "pp_topk_merge": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_match_similarity_workspace": (_sz, [_i, _i]),

@@ -335,3 +335,56 @@ extern "C" int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, 
     }
     return PP_OK;
 }
+
+// ---- one-call stage-1 ranking against prepared banks (keeps the host side to a single library call) ----------
+namespace pp {
+struct MatchWs {
+    size_t q_prep, q_rnorm, q_meta, sim_avg, keys, total;
+};
+static MatchWs match_templates_layout(int B, int N, int T, int Kp) {
+    MatchWs w;
+    size_t off = 0;
+    w.q_prep = off;  off += align_up((size_t)B * T * Kp * 2, 256);
+    w.q_rnorm = off; off += align_up((size_t)B * T * 4, 256);
+    w.q_meta = off;  off += align_up(pp_match_query_meta_bytes(B, T), 256);
+    w.sim_avg = off; off += align_up((size_t)B * N * 4, 256);
+    w.keys = off;    off += pp_match_scores_workspace(B, N, T);
+    w.total = off;
+    return w;
+}
+}  // namespace pp
+
+extern "C" size_t pp_match_templates_workspace(int B, int N, int C, int H, int W, int mode) {
+    const int Kp = pp_match_kp(C, mode);
+    if (B < 0 || N < 0 || H <= 0 || W <= 0 || Kp <= 0) return 0;
+    return pp::match_templates_layout(B, N, H * W, Kp).total;
+}
+
+extern "C" int pp_match_templates(const float* tar_feat, const float* tar_mask, const void* bank_prep,
+                                  const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N,
+                                  int C, int H, int W, int Hm, int Wm, int mode, int k, float* out_score,
+                                  int64_t* out_idx, float* sim_avg_out, void* workspace, size_t workspace_bytes,
+                                  int cluster, void* stream) {
+    using namespace pp;
+    if (B == 0) return PP_OK;
+    const int Kp = pp_match_kp(C, mode);
+    PP_CHECK_ARG(Kp > 0, "pp_match_templates: bad feature dim %d / mode %d", C, mode);
+    PP_CHECK_ARG(k >= 0 && k <= N, "pp_match_templates: selected index k out of range (k=%d, N=%d)", k, N);
+    const int T = H * W;
+    const MatchWs w = match_templates_layout(B, N, T, Kp);
+    if (!workspace || workspace_bytes < w.total)
+        return fail(PP_ERR_WORKSPACE, "pp_match_templates: workspace of %zu bytes needed, %zu given", w.total,
+                    workspace_bytes);
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_templates: workspace must be 256-byte aligned");
+    char* ws = static_cast<char*>(workspace);
+    float* sim_avg = sim_avg_out ? sim_avg_out : reinterpret_cast<float*>(ws + w.sim_avg);
+    if (int rc = pp_match_prepare_query(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
+                                        reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, stream))
+        return rc;
+    if (int rc = pp_match_scores(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep,
+                                 bank_rnorm, n_banks, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr,
+                                 nullptr, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster, stream))
+        return rc;
+    if (k > 0 && out_score && out_idx) return pp_topk(sim_avg, B, N, k, 0, out_score, out_idx, stream);
+    return PP_OK;
+}

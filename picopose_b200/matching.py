@@ -122,6 +122,60 @@ def _resolve_bank(src_feats, mode, B):
     return TemplateBank.from_features(src_feats, mode), None
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs microseconds)."""
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+def _check_bank(bank, bank_index, tar_feat):
+    B, Cc, H, W = tar_feat.shape
+    if H != W:
+        raise AssertionError("matching_templates expects a square patch grid (H == W)")
+    if bank.device != tar_feat.device:
+        raise RuntimeError("template bank and query features live on different devices")
+    if (bank.C, bank.H, bank.W) != (Cc, H, W):
+        raise ValueError(f"bank features {(bank.C, bank.H, bank.W)} do not match the query {(Cc, H, W)}")
+    if bank_index is None and bank.n_banks != B:
+        raise ValueError(f"{bank.n_banks} banks for {B} detections: pass bank_index")
+    if bank_index is not None:
+        bank_index = bank_index.to(device=tar_feat.device, dtype=torch.int32).contiguous()
+    return bank_index
+
+
+def _match_one_call(bank, tar_feat, tar_mask, bank_index, k, cluster, want_sim):
+    """Single library call: query prologue + contraction + finalisation (+ top-k).  None if the batch must be chunked."""
+    lib = _lib.load()
+    B, Cc, H, W = tar_feat.shape
+    N, T = bank.n_views, H * W
+    mid = _mode_id(bank.mode)
+    need = lib.pp_match_templates_workspace(B, N, Cc, H, W, mid)
+    if B > _MAX_DETS_PER_LAUNCH or lib.pp_match_scores_workspace(B, N, T) > _WORKSPACE_LIMIT:
+        return None
+    dev = tar_feat.device
+    feat, mask = _as_f32(tar_feat), _as_f32(tar_mask)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    score = torch.empty(B, k, dtype=torch.float32, device=dev) if k else None
+    idx = torch.empty(B, k, dtype=torch.int64, device=dev) if k else None
+    sim = torch.empty(B, N, dtype=torch.float32, device=dev) if want_sim else None
+    cl = default_cluster() if cluster is None else cluster
+    with _on_device(dev):
+        _lib.check(lib.pp_match_templates(
+            feat.data_ptr(), mask.data_ptr(), bank.prepared.data_ptr(), bank.rnorm.data_ptr(), bank.n_banks,
+            _lib.ptr(bank_index), B, N, Cc, H, W, mask.shape[-2], mask.shape[-1], mid, k, _lib.ptr(score), _lib.ptr(idx),
+            _lib.ptr(sim), ws.data_ptr(), need, cl, _lib.stream_of(tar_feat)), "pp_match_templates")
+    return score, idx, sim
+
+
 def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *, mode: Optional[str] = None,
                     bank_index: Optional[torch.Tensor] = None, want_indices: bool = False,
                     want_mutual: bool = False, cluster: Optional[int] = None):
@@ -136,19 +190,12 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
     _lib.require_cuda(tar_feat, tar_mask)
     lib = _lib.load()
     B, Cc, H, W = tar_feat.shape
-    if H != W:
-        raise AssertionError("matching_templates expects a square patch grid (H == W)")
     bank, auto_index = _resolve_bank(src_feats, mode, B)
-    if bank_index is None:
-        bank_index = auto_index
-    if bank.device != tar_feat.device:
-        raise RuntimeError("template bank and query features live on different devices")
-    if (bank.C, bank.H, bank.W) != (Cc, H, W):
-        raise ValueError(f"bank features {(bank.C, bank.H, bank.W)} do not match the query {(Cc, H, W)}")
-    if bank_index is None and bank.n_banks != B:
-        raise ValueError(f"{bank.n_banks} banks for {B} detections: pass bank_index")
-    if bank_index is not None:
-        bank_index = bank_index.to(device=tar_feat.device, dtype=torch.int32).contiguous()
+    bank_index = _check_bank(bank, auto_index if bank_index is None else bank_index, tar_feat)
+    if not want_indices and not want_mutual:
+        out = _match_one_call(bank, tar_feat, tar_mask, bank_index, 0, cluster, True)
+        if out is not None:
+            return out[2]
     N, T = bank.n_views, H * W
     dev = tar_feat.device
     mid = _mode_id(bank.mode)
@@ -173,7 +220,7 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
     q = torch.empty(chunk, T, kp, dtype=torch.bfloat16, device=dev)
     q_rn = torch.empty(chunk, T, dtype=torch.float32, device=dev)
     q_meta = torch.empty(lib.pp_match_query_meta_bytes(chunk, T), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         st = _lib.stream_of(tar_feat)
         for b0 in range(0, B, chunk):
             b1 = min(B, b0 + chunk)
@@ -223,7 +270,15 @@ def matching_templates(src_feats, tar_feat, src_masks, tar_mask, topk=5, *, mode
     `src_masks` is accepted and ignored, as in the reference.  `src_feats` may also
     be a TemplateBank (pre-normalised once per object) with `bank_index` mapping detections to banks.
     """
-    sim_avg = template_scores(src_feats, tar_feat, tar_mask, mode=mode, bank_index=bank_index)
+    _lib.require_cuda(tar_feat, tar_mask)
+    bank, auto_index = _resolve_bank(src_feats, mode, tar_feat.shape[0])
+    bank_index = _check_bank(bank, auto_index if bank_index is None else bank_index, tar_feat)
+    if topk > bank.n_views:
+        raise RuntimeError(f"selected index k out of range (k={topk}, N={bank.n_views})")
+    out = _match_one_call(bank, tar_feat, tar_mask, bank_index, topk, None, False)
+    if out is not None:
+        return out[0], out[1]
+    sim_avg = template_scores(bank, tar_feat, tar_mask, bank_index=bank_index)
     return topk_scores(sim_avg, topk)
 
 

@@ -99,9 +99,10 @@ class ShardedMatcher:
 
     def match(self, src, tar_feat, tar_mask, topk=5, bank_index=None, mode=None):
         """src: this rank's shard, a TemplateBank or raw (B|n_banks, hi-lo, C, H, W) features."""
-        from .matching import template_scores, topk_scores
+        from .matching import matching_templates, template_scores
         src = self.bank if src is None else src
+        if self.world == 1:
+            # single rank: nothing to exchange, one library call ranks the whole bank
+            return matching_templates(src, tar_feat, None, tar_mask, topk, mode=mode, bank_index=bank_index)
         sim = template_scores(src, tar_feat, tar_mask, mode=mode, bank_index=bank_index)     # (B, hi-lo)
-        if self.world == 1 and sim.shape[1] >= topk:
-            return topk_scores(sim, topk, idx_offset=self.lo)   # single rank: nothing to exchange
         return merge_topk(topk_pairs(sim, topk, idx_offset=self.lo), topk, self.group, self.merge)
