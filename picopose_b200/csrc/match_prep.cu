@@ -30,19 +30,99 @@ constexpr int PREP_WARPS = PREP_THREADS / 32;
 constexpr int PREP_PT = 32;  // patches per block
 constexpr int PREP_CT = 64;  // channels per transposed chunk
 
-template <int NPARTS>
+// Query-mask bookkeeping (QM instances only).  mask (B,Hm,Wm) is nearest-resized to H x W (F.interpolate,
+// utils/matching.py:38-39) and the unmasked patches are ranked in order:
+//   mrow[b,t]   resized mask value            rank[b,t]  compact row of patch t, -1 if masked
+//   rowmap[b,r] patch of compact row r         tv[b]      number of unmasked patches
+//   fm[b]       first masked patch, -1 if none
+struct QueryMaskArgs {
+    const float* mask;
+    int Hm, Wm, H, W;
+    float* mrow;
+    int* rank;
+    int* rowmap;
+    int* tv;
+    int* fm;
+};
+
+template <int NPARTS, bool QM>
 __global__ void __launch_bounds__(PREP_THREADS)
 match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int nseg, int is_query,
-                     __nv_bfloat16* __restrict__ prep, float* __restrict__ rnorm, const int* __restrict__ rank) {
-    // rank != null: row compaction -- patch p of group g is written to row rank[g*P + p] (skipped if negative),
-    // so masked query patches never reach the tensor cores
+                     __nv_bfloat16* __restrict__ prep, float* __restrict__ rnorm, const QueryMaskArgs qm) {
+    // QM: row compaction -- patch p of detection g is written to row rank(p) = number of unmasked patches before
+    // it (skipped if masked), so masked query patches never reach the tensor cores.  Every block recounts the
+    // detection's mask itself (P values), so the prologue stays a single launch with no inter-block dependency.
     // [buffer][part][patch][64 channels] bf16, 16-byte units XOR-swizzled by (patch & 7)
     __shared__ __align__(16) __nv_bfloat16 s_tile[2][NPARTS][PREP_PT][PREP_CT];
     __shared__ float s_part[PREP_WARPS][PREP_PT];
+    __shared__ int s_rank[PREP_PT];
+    __shared__ int s_cnt[PREP_WARPS][2];
+    __shared__ int s_fm;
 
     const int g = blockIdx.y;
     const int p0 = blockIdx.x * PREP_PT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tv_total = 0;
+    if (QM) {
+        auto mask_at = [&](int t) {
+            const int y = t / qm.W, xx = t - y * qm.W;
+            return __ldg(qm.mask + ((size_t)g * qm.Hm + nearest_src(y, qm.Hm, qm.H)) * qm.Wm + nearest_src(xx, qm.Wm, qm.W));
+        };
+        if (threadIdx.x == 0) s_fm = 0x7fffffff;
+        __syncthreads();
+        int before = 0, total = 0, first_masked = 0x7fffffff;   // unmasked patches in [0, p0) and in [0, P)
+        for (int t = threadIdx.x; t < P; t += PREP_THREADS) {
+            const bool on = mask_at(t) != 0.f;
+            total += on;
+            before += on && t < p0;
+            if (!on) first_masked = min(first_masked, t);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            before += __shfl_xor_sync(0xffffffffu, before, o);
+            total += __shfl_xor_sync(0xffffffffu, total, o);
+            first_masked = min(first_masked, __shfl_xor_sync(0xffffffffu, first_masked, o));
+        }
+        if (lane == 0) {
+            s_cnt[warp][0] = before;
+            s_cnt[warp][1] = total;
+            atomicMin(&s_fm, first_masked);
+        }
+        __syncthreads();
+        before = 0;
+#pragma unroll
+        for (int w = 0; w < PREP_WARPS; ++w) {
+            before += s_cnt[w][0];
+            tv_total += s_cnt[w][1];
+        }
+        if (warp == 0) {
+            const int t = p0 + lane;
+            const float m = t < P ? mask_at(t) : 0.f;
+            const bool on = t < P && m != 0.f;
+            const unsigned ball = __ballot_sync(0xffffffffu, on);
+            const int r = before + __popc(ball & ((1u << lane) - 1u));
+            s_rank[lane] = on ? r : -1;
+            if (t < P) {
+                qm.mrow[(size_t)g * P + t] = m;
+                qm.rank[(size_t)g * P + t] = on ? r : -1;
+                if (on) qm.rowmap[(size_t)g * P + r] = t;
+            }
+            if (blockIdx.x == 0 && lane == 0) {
+                qm.tv[g] = tv_total;
+                qm.fm[g] = s_fm == 0x7fffffff ? -1 : s_fm;
+            }
+        }
+        __syncthreads();
+        // compact rows past the last unmasked patch, up to the next 256-row tile boundary, are read by the
+        // contraction's TMA but stand for no patch: keep them zero (blocks share the <= 255 rows round-robin)
+        const int tv_pad = min(P, (tv_total + 255) / 256 * 256);
+        __nv_bfloat16* og = prep + (size_t)g * P * Kp;
+        for (int r = tv_total + blockIdx.x; r < tv_pad; r += gridDim.x) {
+            for (int i = threadIdx.x * 8; i < Kp; i += PREP_THREADS * 8)
+                *reinterpret_cast<uint4*>(og + (size_t)r * Kp + i) = make_uint4(0u, 0u, 0u, 0u);
+            if (threadIdx.x == 0) rnorm[(size_t)g * P + r] = 0.f;
+        }
+    }
     const bool live = p0 + lane < P;
     const float* x = feats + (size_t)g * C * P + (live ? p0 + lane : P - 1);
     __nv_bfloat16* out_g = prep + (size_t)g * P * Kp;
@@ -88,7 +168,7 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
         const int row = warp * 4 + (lane >> 3);
         const int u = lane & 7;
         if (p0 + row < P && u < n_units) {
-            const int orow = rank ? rank[(size_t)g * P + p0 + row] : p0 + row;
+            const int orow = QM ? s_rank[row] : p0 + row;
             if (orow >= 0) {
                 __nv_bfloat16* dst = out_g + (size_t)orow * Kp + c0 + u * 8;
                 if (NPARTS == 1) {  // bf16 mode: one segment
@@ -124,7 +204,7 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < PREP_WARPS; ++w) t += s_part[w][lane];
-        const int orow = rank ? rank[(size_t)g * P + p0 + lane] : p0 + lane;
+        const int orow = QM ? s_rank[lane] : p0 + lane;
         if (orow >= 0) rnorm[(size_t)g * P + orow] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
     }
     // ---- zero the K padding [nseg*C, Kp) ----
@@ -133,70 +213,10 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
         for (int i = threadIdx.x; i < PREP_PT * npad; i += PREP_THREADS) {
             const int row = i / npad, k = i - row * npad;
             if (p0 + row < P) {
-                const int orow = rank ? rank[(size_t)g * P + p0 + row] : p0 + row;
+                const int orow = QM ? s_rank[row] : p0 + row;
                 if (orow >= 0) out_g[(size_t)orow * Kp + pad0 + k] = __float2bfloat16_rn(0.f);
             }
         }
-    }
-}
-
-// Query-mask bookkeeping, one block per detection.  mask (B,Hm,Wm) is nearest-resized to H x W
-// (F.interpolate, utils/matching.py:38-39) and the unmasked patches are ranked in order:
-//   mrow[b,t]   resized mask value            rank[b,t]  compact row of patch t, -1 if masked
-//   rowmap[b,r] patch of compact row r         tv[b]      number of unmasked patches
-//   fm[b]       first masked patch, -1 if none
-__global__ void __launch_bounds__(256)
-mask_compact_kernel(const float* __restrict__ mask, int Hm, int Wm, int H, int W, float* __restrict__ mrow,
-                    int* __restrict__ rank, int* __restrict__ rowmap, int* __restrict__ tv, int* __restrict__ fm) {
-    __shared__ int s_warp[8];
-    __shared__ int s_fm;
-    const int b = blockIdx.x, T = H * W;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_fm = 0x7fffffff;
-    __syncthreads();
-    int base = 0;
-    for (int t00 = 0; t00 < T; t00 += 4 * 256) {
-        // four 256-patch slabs per trip: all mask loads are issued before the first scan step needs them
-        float mv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int t = t00 + u * 256 + threadIdx.x;
-            mv[u] = 0.f;
-            if (t < T) {
-                const int y = t / W, x = t - y * W;
-                mv[u] = __ldg(mask + ((size_t)b * Hm + nearest_src(y, Hm, H)) * Wm + nearest_src(x, Wm, W));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int t = t00 + u * 256 + threadIdx.x;
-            if (t00 + u * 256 >= T) break;  // block-uniform
-            const float m = mv[u];
-            const bool on = t < T && m != 0.f;
-            const unsigned ball = __ballot_sync(0xffffffffu, on);
-            if (lane == 0) s_warp[warp] = __popc(ball);
-            __syncthreads();
-            int before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const int c = s_warp[w];
-                if (w < warp) before += c;
-                total += c;
-            }
-            const int r = base + before + __popc(ball & ((1u << lane) - 1u));
-            if (t < T) {
-                mrow[(size_t)b * T + t] = m;
-                rank[(size_t)b * T + t] = on ? r : -1;
-                if (on) rowmap[(size_t)b * T + r] = t;
-                else atomicMin(&s_fm, t);
-            }
-            base += total;
-            __syncthreads();
-        }
-    }
-    if (threadIdx.x == 0) {
-        tv[b] = base;
-        fm[b] = s_fm == 0x7fffffff ? -1 : s_fm;
     }
 }
 
@@ -229,9 +249,10 @@ extern "C" int pp_match_prepare(const float* feats, int64_t G, int C, int P, int
         const float* f = feats + (size_t)g0 * C * P;
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(prepared) + (size_t)g0 * P * Kp;
         float* rn = rnorm + (size_t)g0 * P;
-        if (nparts == 1) match_prepare_kernel<1><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, nullptr);
-        else if (nparts == 2) match_prepare_kernel<2><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, nullptr);
-        else match_prepare_kernel<3><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, nullptr);
+        const QueryMaskArgs none{};
+        if (nparts == 1) match_prepare_kernel<1, false><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, none);
+        else if (nparts == 2) match_prepare_kernel<2, false><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, none);
+        else match_prepare_kernel<3, false><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, none);
         PP_LAUNCHED();
     }
     return PP_OK;
@@ -271,17 +292,14 @@ extern "C" int pp_match_prepare_query(const float* tar_feat, const float* tar_ma
     const int T = H * W;
     const int Kp = pp_match_kp(C, mode);
     const QueryMeta m = split_query_meta(q_meta, B, T);
-    mask_compact_kernel<<<B, 256, 0, st>>>(tar_mask, Hm, Wm, H, W, m.mrow, m.rank, m.rowmap, m.tv, m.fm);
-    PP_LAUNCHED();
-    // compact rows beyond tv[b] are never written: keep them finite
-    PP_CUDA(cudaMemsetAsync(q_prep, 0, (size_t)B * T * Kp * 2, st));
-    PP_CUDA(cudaMemsetAsync(q_rnorm, 0, (size_t)B * T * 4, st));
+    // one launch: mask resize + compaction bookkeeping + cast/transposition of the unmasked patches + inverse norms
+    const QueryMaskArgs qa{tar_mask, Hm, Wm, H, W, m.mrow, m.rank, m.rowmap, m.tv, m.fm};
     const int nseg = mode_segments(mode), nparts = mode_parts(mode);
     dim3 grid((T + PREP_PT - 1) / PREP_PT, B);
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(q_prep);
-    if (nparts == 1) match_prepare_kernel<1><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, m.rank);
-    else if (nparts == 2) match_prepare_kernel<2><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, m.rank);
-    else match_prepare_kernel<3><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, m.rank);
+    if (nparts == 1) match_prepare_kernel<1, true><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, qa);
+    else if (nparts == 2) match_prepare_kernel<2, true><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, qa);
+    else match_prepare_kernel<3, true><<<grid, PREP_THREADS, 0, st>>>(tar_feat, C, T, Kp, nseg, 1, o, q_rnorm, qa);
     PP_LAUNCHED();
     return PP_OK;
 }

@@ -29,7 +29,8 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
                        const float* __restrict__ mrow, const float* __restrict__ ra, const int* __restrict__ rank,
                        const int* __restrict__ fm, int N, int T, float inv_hh, float* __restrict__ sim_avg,
                        float* __restrict__ score_t2s, int32_t* __restrict__ idx_t2s, int32_t* __restrict__ idx_s2t,
-                       uint8_t* __restrict__ mutual) {
+                       uint8_t* __restrict__ mutual, int k, int* __restrict__ done, float* __restrict__ topk_score,
+                       long long* __restrict__ topk_idx) {
     const size_t bn = blockIdx.x;
     const int b = (int)(bn / N);
     // masked query rows never entered the contraction; in the reference they are rows of zeros that take part in
@@ -70,10 +71,44 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
     }
     if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }
     __syncthreads();
+    __shared__ int s_last;
     if (threadIdx.x == 0) {
         float ts = 0.f, tc = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += s_sum[w]; tc += s_cnt[w]; }
         sim_avg[bn] = tc > 0.f ? ts * inv_hh : 0.f;  // divisor is H*H, not the valid count (:65-67)
+        s_last = 0;
+        if (k > 0) {
+            // the block that finishes a detection's last view ranks that detection (torch.topk, :68): no extra launch
+            __threadfence();
+            s_last = atomicAdd(done + b, 1) == N - 1;
+        }
+    }
+    if (k == 0) return;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    extern __shared__ unsigned long long s_keys[];  // N packed keys + 8 partials
+    unsigned long long* s_red = s_keys + N;
+    const volatile float* sv = sim_avg + (size_t)b * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_keys[i] = pack_key(sv[i] + 0.0f, (uint32_t)i);
+    __syncthreads();
+    for (int r = 0; r < k; ++r) {
+        unsigned long long best = 0ull;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) best = s_keys[i] > best ? s_keys[i] : best;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_red[w] > best ? s_red[w] : best;
+            const uint32_t idx = key_index(best);
+            topk_score[(size_t)b * k + r] = key_value(best);
+            topk_idx[(size_t)b * k + r] = (long long)idx;
+            s_keys[idx] = 0ull;
+        }
+        __syncthreads();
     }
 }
 
@@ -184,14 +219,15 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 extern "C" size_t pp_match_scores_workspace(int B, int N, int T) {
     if (B < 0 || N < 0 || T < 0) return 0;
     const size_t keys = (size_t)B * N * T * sizeof(unsigned long long);
-    return 2 * pp::align_up(keys, 256);
+    return 2 * pp::align_up(keys, 256) + pp::align_up((size_t)B * sizeof(int), 256);
 }
 
-extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* q_meta, const void* bank_prep,
-                               const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H,
-                               int W, int Kp, float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
-                               uint8_t* mutual_nn, void* workspace, size_t workspace_bytes, int cluster, void* stream) {
-    using namespace pp;
+namespace pp {
+static int match_scores_impl(const void* q_prep, const float* q_rnorm, const void* q_meta, const void* bank_prep,
+                             const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H,
+                             int W, int Kp, float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
+                             uint8_t* mutual_nn, int k, float* topk_score, int64_t* topk_idx, void* workspace,
+                             size_t workspace_bytes, int cluster, void* stream) {
     if (int rc = require_sm100()) return rc;
     if (B == 0 || N == 0) return PP_OK;
     PP_CHECK_ARG(q_prep && q_rnorm && q_meta && bank_prep && bank_rnorm && sim_avg, "pp_match_scores: null pointer");
@@ -208,15 +244,33 @@ extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const v
     const size_t keys = align_up((size_t)B * N * T * sizeof(unsigned long long), 256);
     unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(workspace);
     unsigned long long* colkey = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + keys);
-    PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys, st));
+    int* done = reinterpret_cast<int*>(static_cast<char*>(workspace) + 2 * keys);  // per-detection finished-view counters
+    PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys + align_up((size_t)B * sizeof(int), 256), st));
     if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, qm.mrow, qm.tv, qm.rowmap, q_rnorm,
                                 bank_rnorm, rowkey, colkey, nullptr, 1.0f, cluster, st))
         return rc;
-    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(rowkey, colkey, qm.mrow, q_rnorm, qm.rank, qm.fm, N, T,
-                                                                      1.0f / (float)(H * H), sim_avg, score_t2s,
-                                                                      idx_t2s, idx_s2t, mutual_nn);
+    size_t smem = 0;
+    if (k > 0) {
+        PP_CHECK_ARG(k <= N && N <= 24000 && topk_score && topk_idx, "top-k: need 0 < k <= N <= 24000 (k=%d, N=%d)", k, N);
+        smem = ((size_t)N + 8) * sizeof(unsigned long long);
+        if (smem > 48 * 1024)
+            PP_CUDA(cudaFuncSetAttribute(finalize_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, smem, st>>>(
+        rowkey, colkey, qm.mrow, q_rnorm, qm.rank, qm.fm, N, T, 1.0f / (float)(H * H), sim_avg, score_t2s, idx_t2s, idx_s2t,
+        mutual_nn, k, done, topk_score, reinterpret_cast<long long*>(topk_idx));
     PP_LAUNCHED();
     return PP_OK;
+}
+}  // namespace pp
+
+extern "C" int pp_match_scores(const void* q_prep, const float* q_rnorm, const void* q_meta, const void* bank_prep,
+                               const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H,
+                               int W, int Kp, float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
+                               uint8_t* mutual_nn, void* workspace, size_t workspace_bytes, int cluster, void* stream) {
+    return pp::match_scores_impl(q_prep, q_rnorm, q_meta, bank_prep, bank_rnorm, n_banks, bank_of_det, B, N, H, W, Kp,
+                                 sim_avg, score_t2s, idx_t2s, idx_s2t, mutual_nn, 0, nullptr, nullptr, workspace,
+                                 workspace_bytes, cluster, stream);
 }
 
 extern "C" int pp_topk(const float* scores, int B, int N, int k, int64_t idx_offset, float* out_score,
@@ -381,10 +435,9 @@ extern "C" int pp_match_templates(const float* tar_feat, const float* tar_mask, 
     if (int rc = pp_match_prepare_query(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
                                         reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, stream))
         return rc;
-    if (int rc = pp_match_scores(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep,
-                                 bank_rnorm, n_banks, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr,
-                                 nullptr, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster, stream))
-        return rc;
-    if (k > 0 && out_score && out_idx) return pp_topk(sim_avg, B, N, k, 0, out_score, out_idx, stream);
-    return PP_OK;
+    const bool rank_it = k > 0 && out_score && out_idx;
+    return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
+                             n_banks, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
+                             rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
+                             stream);
 }
