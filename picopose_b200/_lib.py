@@ -59,9 +59,14 @@ def load() -> C.CDLL:
         if _lib is not None:
             return _lib
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m picopose_b200.build` "
-                "(nvcc, sm_100a). picopose_b200 has no PyTorch/CPU fallback path.")
+            # not a fallback: the same CUDA sources are compiled in-tree when the toolchain is at hand
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing and could not be built ({exc}); run `python -m picopose_b200.build` "
+                    "(nvcc, sm_100a). picopose_b200 has no PyTorch/CPU fallback path.") from exc
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
