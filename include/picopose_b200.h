@@ -160,6 +160,18 @@ PP_API int pp_match_similarity(const void* q_prep, const float* q_rnorm, const v
 PP_API int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
                            int num_levels, void* const* level_ptrs, int cluster, void* stream);
 
+/* Fused CorrelationPyramid + CorrLookup (model/stage3/raft_decoder.py:30-53 followed by
+ * utils/corr_lookup.py:100-134, as called back to back in model/stage3/flow_decoder.py:59-61) that never builds the
+ * all-pairs volume: the window samples are blended from correlations with the (2r+3)^2 integer neighbours in the
+ * average-pooled FEATURE maps.
+ *   pp_windowed_correlation_prepare : feat (N,C,H,W) fp32 -> out (N, (H>>level)*(W>>level), C) fp32, 2^level x 2^level
+ *                                     average pooled, position-major.  Call with level 0 for feat1 and levels 0..L-1 for feat2.
+ *   pp_windowed_correlation         : f1t (N,H*W,C); f2t_levels[l] (HOST array of DEVICE pointers) from the call above;
+ *                                     flow (N,2,H,W) -> out (N, L*(2r+1)^2, H, W), same channel order as pp_corr_lookup. */
+PP_API int pp_windowed_correlation_prepare(const float* feat, int N, int C, int H, int W, int level, float* out, void* stream);
+PP_API int pp_windowed_correlation(const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
+                            int H, int W, int radius, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Correspondence glue.
  * pp_init_correspondences replaces compute_init_correspondences, utils/correspondence.py:10-26:

@@ -95,4 +95,10 @@ class CorrLookup(nn.Module):
             raise NotImplementedError(
                 "picopose_b200.CorrLookup implements the configuration PicoPose uses "
                 "(bilinear, zeros padding, align_corners=True)")
+        from .correlation import LazyCorrelationPyramid, windowed_correlation
+        if isinstance(corr_pyramid, LazyCorrelationPyramid):
+            if corr_pyramid.fusable(self.r):
+                # fused CorrelationPyramid + lookup: the all-pairs volume is never built
+                return windowed_correlation(corr_pyramid.feat1, corr_pyramid.feat2, flow, corr_pyramid.num_levels, self.r)
+            corr_pyramid = corr_pyramid.materialise()
         return corr_lookup(corr_pyramid, flow, self.r)

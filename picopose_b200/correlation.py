@@ -5,7 +5,8 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
-from typing import Optional, Sequence
+from collections.abc import Sequence
+from typing import Optional
 
 import torch
 import torch.nn as nn
@@ -40,6 +41,74 @@ def correlation_pyramid(feat1: torch.Tensor, feat2: torch.Tensor, num_levels: in
     return levels
 
 
+def fused_corr_enabled() -> bool:
+    return os.environ.get("PICOPOSE_B200_FUSED_CORR", "1") != "0"
+
+
+def windowed_correlation(feat1: torch.Tensor, feat2: torch.Tensor, flow: torch.Tensor, num_levels: int,
+                         radius: int) -> torch.Tensor:
+    """CorrLookup(radius)(CorrelationPyramid(num_levels)(feat1, feat2), flow) without the all-pairs volume.
+
+    -> (N, L*(2r+1)^2, H, W) fp32, same channel order and values (to ~1e-6) as the two-step path.
+    """
+    _lib.require_cuda(feat1, feat2, flow)
+    lib = _lib.load()
+    f1 = feat1.float().contiguous()
+    f2 = feat2.float().contiguous()
+    fl = flow.float().contiguous()
+    N, Cc, H, W = f1.shape
+    dev = f1.device
+    D = 2 * int(radius) + 1
+    with torch.cuda.device(dev):
+        st = _lib.stream_of(f1)
+        f1t = torch.empty(N, H * W, Cc, dtype=torch.float32, device=dev)
+        _lib.check(lib.pp_windowed_correlation_prepare(_lib.ptr(f1), N, Cc, H, W, 0, _lib.ptr(f1t), st),
+                   "pp_windowed_correlation_prepare")
+        levels = []
+        for l in range(num_levels):
+            t = torch.empty(N, (H >> l) * (W >> l), Cc, dtype=torch.float32, device=dev)
+            _lib.check(lib.pp_windowed_correlation_prepare(_lib.ptr(f2), N, Cc, H, W, l, _lib.ptr(t), st),
+                       "pp_windowed_correlation_prepare")
+            levels.append(t)
+        out = torch.empty(N, num_levels * D * D, H, W, dtype=torch.float32, device=dev)
+        ptrs = (C.c_void_p * num_levels)(*[t.data_ptr() for t in levels])
+        _lib.check(lib.pp_windowed_correlation(_lib.ptr(f1t), ptrs, num_levels, _lib.ptr(fl), N, Cc, H, W, int(radius),
+                                               _lib.ptr(out), st), "pp_windowed_correlation")
+    return out
+
+
+class LazyCorrelationPyramid(Sequence):
+    """What CorrelationPyramid.forward returns: the two feature maps, not yet multiplied.
+
+    CorrLookup recognises it and runs the fused windowed correlation (the 64 MiB/sample volume of
+    model/stage3/raft_decoder.py:43-47 is never built).  Any other consumer can still index / iterate it like
+    the reference's list of volumes; they are materialised on first use by the tensor-core path.
+    """
+
+    def __init__(self, feat1: torch.Tensor, feat2: torch.Tensor, num_levels: int):
+        self.feat1, self.feat2, self.num_levels = feat1, feat2, num_levels
+        self._volumes = None
+
+    def materialise(self):
+        if self._volumes is None:
+            self._volumes = correlation_pyramid(self.feat1, self.feat2, self.num_levels)
+        return self._volumes
+
+    def fusable(self, radius: int) -> bool:
+        Cc = self.feat1.shape[1]
+        return (self._volumes is None and 1 <= radius <= 8 and Cc % 4 == 0 and Cc <= 2048
+                and self.num_levels * (2 * radius + 1) ** 2 * 33 * 4 + 8 * Cc * 4 < 190 * 1024)
+
+    def __len__(self):
+        return self.num_levels
+
+    def __getitem__(self, i):
+        return self.materialise()[i]
+
+    def __iter__(self):
+        return iter(self.materialise())
+
+
 class CorrelationPyramid(nn.Module):
     """Drop-in for model/stage3/raft_decoder.py:14-53 (same constructor, parameter-free)."""
 
@@ -48,4 +117,6 @@ class CorrelationPyramid(nn.Module):
         self.num_levels = num_levels
 
     def forward(self, feat1: torch.Tensor, feat2: torch.Tensor) -> Sequence[torch.Tensor]:
+        if fused_corr_enabled():
+            return LazyCorrelationPyramid(feat1, feat2, self.num_levels)
         return correlation_pyramid(feat1, feat2, self.num_levels)

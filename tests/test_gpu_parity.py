@@ -368,10 +368,37 @@ def test_similarity_volume_native_size():
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=4e-3)
 
 
+@pytest.mark.parametrize("N,C,H,L,r,sigma", [
+    (2, 256, 16, 1, 2, 2.0), (1, 256, 32, 2, 2, 2.0), (1, 256, 64, 3, 2, 3.0),     # FlowDecoder ladder (r = int(4/2))
+    (1, 64, 32, 3, 4, 4.0), (1, 32, 24, 2, 3, 40.0), (1, 8, 12, 2, 1, 2.0), (1, 256, 16, 1, 8, 3.0),
+])
+def test_windowed_correlation_vs_oracle(N, C, H, L, r, sigma):
+    """Fused CorrelationPyramid + CorrLookup (no volume) against the oracle's two-step computation."""
+    from picopose_b200.corr_lookup import CorrLookup
+    from picopose_b200.correlation import CorrelationPyramid, LazyCorrelationPyramid
+    gen = torch.Generator().manual_seed(31 + r)
+    f1 = torch.randn(N, C, H, H, generator=gen)
+    f2 = torch.randn(N, C, H, H, generator=gen)
+    flow = sigma * torch.randn(N, 2, H, H, generator=gen)
+    flow[0, :, 0, 0] = 0.0                                             # integer coordinates
+    ref = OL.corr_lookup(OL.correlation_pyramid(f1, f2, L), flow, r)
+    pyr = CorrelationPyramid(num_levels=L)(f1.to(DEV), f2.to(DEV))
+    assert isinstance(pyr, LazyCorrelationPyramid) and len(pyr) == L
+    out = CorrLookup(radius=r)(pyr, flow.to(DEV))
+    assert pyr._volumes is None                                        # the volume was never built
+    assert tuple(out.shape) == tuple(ref.shape)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=3e-5)
+    # the lazy pyramid still behaves like the reference's list of volumes for any other consumer
+    vols = list(pyr)
+    assert vols[0].shape == (N * H * H, 1, H, H)
+    out2 = CorrLookup(radius=r)(vols, flow.to(DEV))
+    np.testing.assert_allclose(out2.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5)
+
+
 def test_correlation_pyramid():
-    from picopose_b200.correlation import CorrelationPyramid, correlation_pyramid
+    from picopose_b200.correlation import correlation_pyramid
     g = load("pyramid.npz")
-    pyr = CorrelationPyramid(num_levels=3)(cuda(g["f1"]), cuda(g["f2"]))
+    pyr = correlation_pyramid(cuda(g["f1"]), cuda(g["f2"]), 3)
     _lib.check_device_faults()
     for i, lvl in enumerate(pyr):
         assert tuple(lvl.shape) == g[f"lvl{i}"].shape
@@ -400,8 +427,10 @@ def test_stage3_level_end_to_end():
     flow = 2.0 * torch.randn(1, 2, H, H, generator=gen)
     ref_pyr = OL.correlation_pyramid(f1, f2, L)
     ref = OL.corr_lookup(ref_pyr, flow, r)
-    pyr = CorrelationPyramid(num_levels=L)(f1.to(DEV), f2.to(DEV))
+    pyr = CorrelationPyramid(num_levels=L)(f1.to(DEV), f2.to(DEV))          # lazy -> fused path
     out = CorrLookup(radius=r)(pyr, flow.to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5)
+    out = CorrLookup(radius=r)(pyr.materialise(), flow.to(DEV))            # explicit volumes -> lookup kernel
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5)
     grid = OL.coords_grid(1, H, H) + flow
     warp_ref = OL.bilinear_sample(f2, grid, align_corners=True)
