@@ -169,6 +169,9 @@ PP_API int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, int 
  *   pp_windowed_correlation         : f1t (N,H*W,C); f2t_levels[l] (HOST array of DEVICE pointers) from the call above;
  *                                     flow (N,2,H,W) -> out (N, L*(2r+1)^2, H, W), same channel order as pp_corr_lookup. */
 PP_API int pp_windowed_correlation_prepare(const float* feat, int N, int C, int H, int W, int level, float* out, void* stream);
+/* same for feat1 (level 0 -> f1t) and feat2 (levels 0..L-1 -> f2t_levels[l]) in one launch */
+PP_API int pp_windowed_correlation_prepare_all(const float* feat1, const float* feat2, int N, int C, int H, int W, int L,
+                                        float* f1t, void* const* f2t_levels, void* stream);
 PP_API int pp_windowed_correlation(const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
                             int H, int W, int radius, float* out, void* stream);
 

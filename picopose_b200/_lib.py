@@ -43,6 +43,7 @@ SIGNATURES = {
     "pp_match_similarity": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pp_correlation_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), _i, _vp]),
     "pp_windowed_correlation_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pp_windowed_correlation_prepare_all": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.POINTER(_vp), _vp]),
     "pp_windowed_correlation": (_i, [_vp, C.POINTER(_vp), _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_init_correspondences": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_stage3_correspondences": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),

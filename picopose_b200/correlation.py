@@ -62,16 +62,12 @@ def windowed_correlation(feat1: torch.Tensor, feat2: torch.Tensor, flow: torch.T
     with torch.cuda.device(dev):
         st = _lib.stream_of(f1)
         f1t = torch.empty(N, H * W, Cc, dtype=torch.float32, device=dev)
-        _lib.check(lib.pp_windowed_correlation_prepare(_lib.ptr(f1), N, Cc, H, W, 0, _lib.ptr(f1t), st),
-                   "pp_windowed_correlation_prepare")
-        levels = []
-        for l in range(num_levels):
-            t = torch.empty(N, (H >> l) * (W >> l), Cc, dtype=torch.float32, device=dev)
-            _lib.check(lib.pp_windowed_correlation_prepare(_lib.ptr(f2), N, Cc, H, W, l, _lib.ptr(t), st),
-                       "pp_windowed_correlation_prepare")
-            levels.append(t)
-        out = torch.empty(N, num_levels * D * D, H, W, dtype=torch.float32, device=dev)
+        levels = [torch.empty(N, (H >> l) * (W >> l), Cc, dtype=torch.float32, device=dev) for l in range(num_levels)]
         ptrs = (C.c_void_p * num_levels)(*[t.data_ptr() for t in levels])
+        # one launch: position-major copies of feat1 and of feat2 average-pooled to every level
+        _lib.check(lib.pp_windowed_correlation_prepare_all(_lib.ptr(f1), _lib.ptr(f2), N, Cc, H, W, num_levels,
+                                                           _lib.ptr(f1t), ptrs, st), "pp_windowed_correlation_prepare_all")
+        out = torch.empty(N, num_levels * D * D, H, W, dtype=torch.float32, device=dev)
         _lib.check(lib.pp_windowed_correlation(_lib.ptr(f1t), ptrs, num_levels, _lib.ptr(fl), N, Cc, H, W, int(radius),
                                                _lib.ptr(out), st), "pp_windowed_correlation")
     return out

@@ -7,9 +7,9 @@
 //     lookup[q, l, a, b] = sum_{4 taps} w_tap * < f1[:, q], pool_l(f2)[:, y_tap, x_tap] > / sqrt(C)
 // needs only the (D+2)^2 integer neighbours of the window origin in the l-times pooled FEATURE map.
 // pp_windowed_correlation_prepare lays features out position-major ((N, H_l*W_l, C), pooled), so one
-// neighbour is one contiguous C-vector; windowed_corr_kernel gives each warp a query: lanes split the
-// channels (coalesced 16-byte loads, f1[q] staged in shared memory), a warp reduction yields the
-// neighbour's correlation, the D*D bilinear samples are blended from the (D+2)^2 grid exactly as
+// neighbour is one contiguous C-vector; windowed_corr_kernel gives each warp a query: 8-lane groups take one
+// neighbour each and split its channels (128 contiguous bytes per step, f1[q] staged in shared memory), three
+// shuffles finish the dot product, the D*D bilinear samples are blended from the (D+2)^2 grid exactly as
 // corr_lookup.cu does (same tap arithmetic), and a block's 32 queries leave through a shared tile so that
 // every output channel is stored as one coalesced 128-byte line.
 // Bandwidth-bound on L1/L2 (feature maps are a few MB); no GEMM shape to exploit -- 30x fewer FLOPs than
@@ -47,12 +47,24 @@ __device__ __forceinline__ void wc_axis_tap(float p, int size, int& i0, float& w
 
 // (N, C, H, W) -> (N, (H>>l)*(W>>l), C): 2^l x 2^l average pooling (what l AvgPool2d(2,2) steps do to the
 // volume, applied to the features instead) and transposition to position-major.
-__global__ void __launch_bounds__(256)
-wcorr_prepare_kernel(const float* __restrict__ f, int C, int H, int W, int level, float* __restrict__ out) {
+struct WPrepJobs {
+    const float* src[WC_MAX_LEVELS + 1];
+    float* dst[WC_MAX_LEVELS + 1];
+    int level[WC_MAX_LEVELS + 1];
+    int N;
+};
+
+// blockIdx.z = job * N + n: job 0 transposes feat1, job j >= 1 pools feat2 to level j-1 and transposes it
+__global__ void __launch_bounds__(256) wcorr_prepare_kernel(const WPrepJobs jobs, int C, int H, int W) {
     __shared__ float tile[32][33];
-    const int n = blockIdx.z;
+    const int job = blockIdx.z / jobs.N;
+    const int n = blockIdx.z - job * jobs.N;
+    const float* __restrict__ f = jobs.src[job];
+    float* __restrict__ out = jobs.dst[job];
+    const int level = jobs.level[job];
     const int hl = H >> level, wl = W >> level, P = hl * wl, s = 1 << level;
     const int pos0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    if (pos0 >= P) return;  // grid.x is sized for level 0
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const float inv = 1.0f / (float)(s * s);
     for (int cy = ty; cy < 32; cy += 8) {
@@ -92,9 +104,9 @@ __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCor
     const int hw0 = (blockIdx.x - n * p.groups_per_n) * WC_QUERIES;
 
     for (int qi = 0; qi < WC_QUERIES / WC_WARPS; ++qi) {
-        const int ql = warp * (WC_QUERIES / WC_WARPS) + qi;
+        const int ql = qi * WC_WARPS + warp;  // the 8 warps work on 8 neighbouring queries at a time (shared L1 footprint)
         const int hw = hw0 + ql;
-        if (hw >= p.HW) break;  // warp-uniform
+        if (hw >= p.HW) continue;  // warp-uniform
         const int qh = hw / p.W, qw = hw - qh * p.W;
         const float cx = __fadd_rn((float)qw, __ldg(p.flow + ((size_t)n * 2 + 0) * p.HW + hw));
         const float cy = __fadd_rn((float)qh, __ldg(p.flow + ((size_t)n * 2 + 1) * p.HW + hw));
@@ -121,32 +133,31 @@ __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCor
             const int xmin = s_xo[0], ymin = s_yo[0];
             const int gx = s_xo[D - 1] + 2 - xmin, gy = s_yo[D - 1] + 2 - ymin;  // grid of integer neighbours (<= G each)
             const float* f2n = p.f2t[l] + (size_t)n * Hl * Wl * p.C;
-            // correlation with every neighbour of the grid; 2 neighbours per trip for independent reduction chains
-            for (int idx = 0; idx < gx * gy; idx += 2) {
-                float acc[2] = {0.f, 0.f};
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int id = idx + u;
-                    const int gyi = id / gx, gxi = id - gyi * gx;
-                    const int x = xmin + gxi, y = ymin + gyi;
-                    if (id < gx * gy && (unsigned)x < (unsigned)Wl && (unsigned)y < (unsigned)Hl) {
-                        const float* v = f2n + (size_t)(y * Wl + x) * p.C;
-                        for (int c = lane * 4; c < p.C; c += 128) {
-                            const float4 a = *reinterpret_cast<const float4*>(f1s + c);
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(v + c));
-                            acc[u] = fmaf(a.x, b.x, acc[u]);
-                            acc[u] = fmaf(a.y, b.y, acc[u]);
-                            acc[u] = fmaf(a.z, b.z, acc[u]);
-                            acc[u] = fmaf(a.w, b.w, acc[u]);
-                        }
+            // correlation with every neighbour of the grid: 4 neighbours per trip, 8 lanes each (a lane group reads
+            // 128 contiguous bytes of its neighbour's feature vector per step; 3 shuffles finish the dot product)
+            const int grp = lane >> 3, gl = lane & 7;
+            const int npts = gx * gy;
+            for (int idx = 0; idx < npts; idx += 4) {
+                const int id = idx + grp;
+                const int gyi = id / gx, gxi = id - gyi * gx;
+                const int x = xmin + gxi, y = ymin + gyi;
+                float acc = 0.f;
+                if (id < npts && (unsigned)x < (unsigned)Wl && (unsigned)y < (unsigned)Hl) {
+                    const float* v = f2n + (size_t)(y * Wl + x) * p.C;
+#pragma unroll 4
+                    for (int c = gl * 4; c < p.C; c += 32) {
+                        const float4 a = *reinterpret_cast<const float4*>(f1s + c);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(v + c));
+                        acc = fmaf(a.x, b.x, acc);
+                        acc = fmaf(a.y, b.y, acc);
+                        acc = fmaf(a.z, b.z, acc);
+                        acc = fmaf(a.w, b.w, acc);
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
-                    acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o);
-                }
-                if (lane < 2 && idx + lane < gx * gy) vals[idx + lane] = (lane == 0 ? acc[0] : acc[1]) * p.scale;
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (gl == 0 && id < npts) vals[id] = acc * p.scale;
             }
             __syncwarp();
             // D*D bilinear samples from the grid (separable blend, as in corr_lookup.cu)
@@ -194,7 +205,38 @@ extern "C" int pp_windowed_correlation_prepare(const float* feat, int N, int C, 
                  "pp_windowed_correlation_prepare: bad shape");
     const int P = (H >> level) * (W >> level);
     dim3 grid((P + 31) / 32, (C + 31) / 32, N);
-    wcorr_prepare_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, C, H, W, level, out);
+    WPrepJobs jobs{};
+    jobs.src[0] = feat;
+    jobs.dst[0] = out;
+    jobs.level[0] = level;
+    jobs.N = N;
+    wcorr_prepare_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs, C, H, W);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_windowed_correlation_prepare_all(const float* feat1, const float* feat2, int N, int C, int H, int W, int L,
+                                                   float* f1t, void* const* f2t_levels, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (N == 0) return PP_OK;
+    PP_CHECK_ARG(feat1 && feat2 && f1t && f2t_levels, "pp_windowed_correlation_prepare_all: null pointer");
+    PP_CHECK_ARG(L >= 1 && L <= WC_MAX_LEVELS && N > 0 && (long long)N * (L + 1) <= 65535 && C > 0 && H > 0 && W > 0 &&
+                     (H >> (L - 1)) > 0 && (W >> (L - 1)) > 0,
+                 "pp_windowed_correlation_prepare_all: bad shape");
+    WPrepJobs jobs{};
+    jobs.N = N;
+    jobs.src[0] = feat1;
+    jobs.dst[0] = f1t;
+    jobs.level[0] = 0;
+    for (int l = 0; l < L; ++l) {
+        PP_CHECK_ARG(f2t_levels[l], "pp_windowed_correlation_prepare_all: null level %d", l);
+        jobs.src[l + 1] = feat2;
+        jobs.dst[l + 1] = static_cast<float*>(f2t_levels[l]);
+        jobs.level[l + 1] = l;
+    }
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N * (L + 1));
+    wcorr_prepare_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs, C, H, W);
     PP_LAUNCHED();
     return PP_OK;
 }
