@@ -125,3 +125,57 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["metric"] == "detections/sec"
+
+
+REFERENCE = os.environ.get("PICOPOSE_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "model", "stage3")),
+                    reason="reference tree not present (it never is on the GPU box)")
+def test_reference_flow_decoder_builds_on_the_overlay():
+    """With the real reference tree: the UNMODIFIED model/stage3/flow_decoder.py imports through the overlay and its
+    FlowDecoder ends up holding our CorrLookup / CorrelationPyramid modules (mmcv is stubbed: conv stacks only)."""
+    import types
+    from picopose_b200 import launcher
+
+    def ours(k):
+        return k in ("utils", "model", "mmcv") or k.startswith(("utils.", "model.", "mmcv."))
+    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if ours(k)}
+    try:
+        for k in list(sys.modules):
+            if ours(k):
+                del sys.modules[k]
+        mmcv, cnn = types.ModuleType("mmcv"), types.ModuleType("mmcv.cnn")
+
+        class ConvModule(torch.nn.Module):
+            def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, act_cfg=dict(type="ReLU"), **kw):
+                super().__init__()
+                self.conv = torch.nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding)
+                self.act = torch.nn.ReLU() if act_cfg is not None else torch.nn.Identity()
+
+            def forward(self, x):
+                return self.act(self.conv(x))
+
+        cnn.ConvModule = ConvModule
+        mmcv.cnn = cnn
+        sys.modules["mmcv"], sys.modules["mmcv.cnn"] = mmcv, cnn
+        launcher.install_overlay(REFERENCE)
+        fd = importlib.import_module("model.stage3.flow_decoder")
+        assert fd.__file__.startswith(REFERENCE)                         # the reference's own file
+        dec = fd.FlowDecoder(num_levels=3, radius=4)
+        assert [type(m).__module__ for m in dec.corr_lookup] == ["picopose_b200.corr_lookup"] * 3
+        assert [type(m).__module__ for m in dec.corr_block] == ["picopose_b200.correlation"] * 3
+        assert dec.corr_lookup[0].r == 2                                  # flow_decoder.py:24 halves the radius
+        assert type(dec.encoder[0]).__module__ == "model.stage3._reference_raft_decoder"
+        m = importlib.import_module("utils.matching")
+        c = importlib.import_module("utils.correspondence")
+        assert m.matching_templates.__module__ == "picopose_b200.matching"
+        assert c.compute_stage3_correspondences.__module__ == "picopose_b200.correspondence"
+        tu = importlib.import_module("utils.torch_utils")
+        assert tu.__file__.startswith(REFERENCE)
+    finally:
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if ours(k):
+                del sys.modules[k]
+        sys.modules.update(saved_mods)
