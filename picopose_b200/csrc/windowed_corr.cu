@@ -16,7 +16,13 @@
 // the all-pairs product and nothing but features and the (B, L*D*D, H, W) result touches HBM.
 #include "pp_common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace pp {
+
+int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
+                       int H, int W, float* out, cudaStream_t st, bool* handled);  // windowed_corr_tiled.cu
 
 constexpr int WC_MAX_LEVELS = 8;
 constexpr int WC_QUERIES = 32;  // queries per block (one output line)
@@ -86,15 +92,89 @@ __global__ void __launch_bounds__(256) wcorr_prepare_kernel(const WPrepJobs jobs
     }
 }
 
-template <int R>
+// Faster form of the above for L <= 4, C % 4 == 0, W % 4 == 0: a block takes one 8 x 8 patch of positions and 64
+// channels of one sample, reads it ONCE (float4 along x) and writes every level from shared memory (float4
+// along c): feat1 -> level 0 only, feat2 -> levels 0 .. L-1, each level pooled from the one below it like the
+// reference's repeated AvgPool2d(2, 2).
+struct WPatchArgs {
+    const float* src[2];            // feat1, feat2 (N, C, H, W)
+    float* dst[2][4];               // [which][level]: (N, (H>>l)*(W>>l), C)
+    int levels[2];                  // 1, L
+    int N, C, H, W, patches_x;
+};
+
+__global__ void __launch_bounds__(256) wcorr_prepare_patch_kernel(const WPatchArgs a) {
+    __shared__ float t0[64][65];   // [c][8*8 positions]
+    __shared__ float t1[64][17];   // 4*4
+    __shared__ float t2[64][5];    // 2*2
+    __shared__ float t3[64][2];    // 1
+    const int tid = threadIdx.x;
+    const int which = blockIdx.z / a.N, n = blockIdx.z - which * a.N;
+    const int py0 = (blockIdx.x / a.patches_x) * 8, px0 = (blockIdx.x % a.patches_x) * 8;
+    const int c0 = blockIdx.y * 64;
+    const int C = a.C, H = a.H, W = a.W;
+    const float* __restrict__ src = a.src[which] + ((size_t)n * C + c0) * H * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int idx = tid + 256 * j;
+        const int c = idx >> 4, r = (idx >> 1) & 7, half = idx & 1;
+        const int y = py0 + r, x = px0 + half * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c < C && y < H && x < W) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * H * W + (size_t)y * W + x));
+        float* d = &t0[c][r * 8 + half * 4];
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    const int L = a.levels[which];
+    if (L > 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = tid + 256 * j, c = idx & 63, pp = idx >> 6, py = pp >> 2, px = pp & 3;
+            const float* s0 = &t0[c][(2 * py) * 8 + 2 * px];
+            t1[c][pp] = 0.25f * ((s0[0] + s0[1]) + (s0[8] + s0[9]));
+        }
+        __syncthreads();
+    }
+    if (L > 2) {
+        const int c = tid & 63, pp = tid >> 6, py = pp >> 1, px = pp & 1;
+        const float* s1 = &t1[c][(2 * py) * 4 + 2 * px];
+        t2[c][pp] = 0.25f * ((s1[0] + s1[1]) + (s1[4] + s1[5]));
+        __syncthreads();
+    }
+    if (L > 3) {
+        if (tid < 64) t3[tid][0] = 0.25f * ((t2[tid][0] + t2[tid][1]) + (t2[tid][2] + t2[tid][3]));
+        __syncthreads();
+    }
+    for (int l = 0; l < L; ++l) {
+        const int side = 8 >> l, npos = side * side;
+        const int Hl = H >> l, Wl = W >> l, Y0 = py0 >> l, X0 = px0 >> l;
+        float* __restrict__ dst = a.dst[which][l] + (size_t)n * Hl * Wl * C + c0;
+        const float* tl = l == 0 ? &t0[0][0] : l == 1 ? &t1[0][0] : l == 2 ? &t2[0][0] : &t3[0][0];
+        const int stride = l == 0 ? 65 : l == 1 ? 17 : l == 2 ? 5 : 2;
+        for (int idx = tid; idx < npos * 16; idx += 256) {
+            const int pos = idx >> 4, c4 = (idx & 15) * 4;
+            const int y = Y0 + pos / side, x = X0 + pos % side;
+            if (y < Hl && x < Wl && c0 + c4 < C) {
+                const float* tc = tl + (size_t)c4 * stride + pos;
+                *reinterpret_cast<float4*>(dst + ((size_t)y * Wl + x) * C + c4) = make_float4(tc[0], tc[stride], tc[2 * stride], tc[3 * stride]);
+            }
+        }
+    }
+}
+
+// CV > 0: C == 32*CV and the warp keeps f1[:, q] in registers (lane gl of every 8-lane group holds channels
+// gl*4 + 32*j); CV == 0: any C % 4 == 0, f1[:, q] staged in shared memory.
+template <int R, int CV>
 __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCorrParams p) {
     constexpr int D = 2 * R + 1, G = D + 2, DD = D * D;
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, gl = lane & 7;
     const int rows = p.L * DD;
-    float* out_tile = smem;                                   // [rows][33]
-    float* f1s = smem + (((size_t)rows * 33 + 3) & ~(size_t)3) + (size_t)warp * p.C;   // after the tile: [warps][C]
-    float* vals = smem + (((size_t)rows * 33 + 3) & ~(size_t)3) + (size_t)WC_WARPS * p.C + warp * (G * G + 4 * D);
+    const int f1_words = CV > 0 ? 0 : WC_WARPS * p.C;
+    float* out_tile = smem;                                                       // [rows][33]
+    float* f1s = smem + (((size_t)rows * 33 + 3) & ~(size_t)3) + (size_t)warp * (CV > 0 ? 0 : p.C);   // [warps][C] (CV == 0)
+    float* vals = smem + (((size_t)rows * 33 + 3) & ~(size_t)3) + f1_words + warp * (G * G + 4 * D);
     int* s_xo = reinterpret_cast<int*>(vals + G * G);
     int* s_yo = s_xo + D;
     float* s_xw = reinterpret_cast<float*>(s_yo + D);
@@ -110,11 +190,16 @@ __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCor
         const int qh = hw / p.W, qw = hw - qh * p.W;
         const float cx = __fadd_rn((float)qw, __ldg(p.flow + ((size_t)n * 2 + 0) * p.HW + hw));
         const float cy = __fadd_rn((float)qh, __ldg(p.flow + ((size_t)n * 2 + 1) * p.HW + hw));
-        // stage f1[:, q]: lane keeps channels lane*4 + 128*j in its own 16-byte slots
         const float* f1q = p.f1t + ((size_t)n * p.HW + hw) * p.C;
-        __syncwarp();
-        for (int c = lane * 4; c < p.C; c += 128) *reinterpret_cast<float4*>(f1s + c) = __ldg(reinterpret_cast<const float4*>(f1q + c));
-        __syncwarp();
+        float4 a[CV > 0 ? CV : 1];
+        if (CV > 0) {
+#pragma unroll
+            for (int j = 0; j < CV; ++j) a[j] = __ldg(reinterpret_cast<const float4*>(f1q + gl * 4 + 32 * j));
+        } else {
+            __syncwarp();
+            for (int c = lane * 4; c < p.C; c += 128) *reinterpret_cast<float4*>(f1s + c) = __ldg(reinterpret_cast<const float4*>(f1q + c));
+            __syncwarp();
+        }
 
         for (int l = 0; l < p.L; ++l) {
             const int Hl = p.hl[l], Wl = p.wl[l];
@@ -132,26 +217,44 @@ __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCor
             __syncwarp();
             const int xmin = s_xo[0], ymin = s_yo[0];
             const int gx = s_xo[D - 1] + 2 - xmin, gy = s_yo[D - 1] + 2 - ymin;  // grid of integer neighbours (<= G each)
-            const float* f2n = p.f2t[l] + (size_t)n * Hl * Wl * p.C;
+            const float rgx = 1.0f / (float)gx;
+            const float* f2n = p.f2t[l] + (size_t)n * Hl * Wl * p.C + gl * 4;
             // correlation with every neighbour of the grid: 4 neighbours per trip, 8 lanes each (a lane group reads
             // 128 contiguous bytes of its neighbour's feature vector per step; 3 shuffles finish the dot product)
-            const int grp = lane >> 3, gl = lane & 7;
             const int npts = gx * gy;
+#pragma unroll 2
             for (int idx = 0; idx < npts; idx += 4) {
                 const int id = idx + grp;
-                const int gyi = id / gx, gxi = id - gyi * gx;
+                const int gyi = (int)(((float)id + 0.5f) * rgx);  // id / gx, exact for these small integers
+                const int gxi = id - gyi * gx;
                 const int x = xmin + gxi, y = ymin + gyi;
+                const bool ok = id < npts && (unsigned)x < (unsigned)Wl && (unsigned)y < (unsigned)Hl;
                 float acc = 0.f;
-                if (id < npts && (unsigned)x < (unsigned)Wl && (unsigned)y < (unsigned)Hl) {
+                if (CV > 0) {
+                    // always load (key 0 when the neighbour is outside the map) and discard: no predicated zero-fill
+                    const float4* v = reinterpret_cast<const float4*>(f2n + (size_t)(ok ? y * Wl + x : 0) * p.C);
+                    float4 b[CV > 0 ? CV : 1];
+#pragma unroll
+                    for (int j = 0; j < CV; ++j) b[j] = __ldg(v + 8 * j);
+                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < CV; ++j) {
+                        s4.x = fmaf(a[j].x, b[j].x, s4.x);
+                        s4.y = fmaf(a[j].y, b[j].y, s4.y);
+                        s4.z = fmaf(a[j].z, b[j].z, s4.z);
+                        s4.w = fmaf(a[j].w, b[j].w, s4.w);
+                    }
+                    acc = ok ? (s4.x + s4.y) + (s4.z + s4.w) : 0.f;
+                } else if (ok) {
                     const float* v = f2n + (size_t)(y * Wl + x) * p.C;
 #pragma unroll 4
-                    for (int c = gl * 4; c < p.C; c += 32) {
-                        const float4 a = *reinterpret_cast<const float4*>(f1s + c);
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(v + c));
-                        acc = fmaf(a.x, b.x, acc);
-                        acc = fmaf(a.y, b.y, acc);
-                        acc = fmaf(a.z, b.z, acc);
-                        acc = fmaf(a.w, b.w, acc);
+                    for (int c = 0; c + gl * 4 < p.C; c += 32) {
+                        const float4 av = *reinterpret_cast<const float4*>(f1s + gl * 4 + c);
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(v + c));
+                        acc = fmaf(av.x, bv.x, acc);
+                        acc = fmaf(av.y, bv.y, acc);
+                        acc = fmaf(av.z, bv.z, acc);
+                        acc = fmaf(av.w, bv.w, acc);
                     }
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -162,10 +265,10 @@ __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCor
             __syncwarp();
             // D*D bilinear samples from the grid (separable blend, as in corr_lookup.cu)
             for (int k = lane; k < DD; k += 32) {
-                const int a = k / D, b = k - a * D;
-                const float* t0 = vals + (s_yo[b] - ymin) * gx + (s_xo[a] - xmin);
-                const float wx1 = s_xw[a], wx0 = __fsub_rn(1.0f, wx1);
-                const float wy1 = s_yw[b], wy0 = __fsub_rn(1.0f, wy1);
+                const int ai = k / D, bi = k - ai * D;
+                const float* t0 = vals + (s_yo[bi] - ymin) * gx + (s_xo[ai] - xmin);
+                const float wx1 = s_xw[ai], wx0 = __fsub_rn(1.0f, wx1);
+                const float wy1 = s_yw[bi], wy0 = __fsub_rn(1.0f, wy1);
                 const float h0 = fmaf(t0[1], wx1, t0[0] * wx0);
                 const float h1 = fmaf(t0[gx + 1], wx1, t0[gx] * wx0);
                 out_tile[(size_t)(l * DD + k) * 33 + ql] = fmaf(h1, wy1, h0 * wy0);
@@ -181,16 +284,29 @@ __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCor
     }
 }
 
-template <int R>
-static int launch_wcorr(const WCorrParams& p, cudaStream_t st) {
+template <int R, int CV>
+static int launch_wcorr_cv(const WCorrParams& p, cudaStream_t st) {
     constexpr int D = 2 * R + 1, G = D + 2;
-    const size_t words = (((size_t)p.L * D * D * 33 + 3) & ~(size_t)3) + (size_t)WC_WARPS * p.C + (size_t)WC_WARPS * (G * G + 4 * D);
+    const size_t words = (((size_t)p.L * D * D * 33 + 3) & ~(size_t)3) + (CV > 0 ? 0 : (size_t)WC_WARPS * p.C) +
+                         (size_t)WC_WARPS * (G * G + 4 * D);
     const size_t smem = words * sizeof(float);
     PP_CHECK_ARG(smem <= 200 * 1024, "pp_windowed_correlation: %zu bytes of shared memory needed (levels x window too large)", smem);
-    PP_CUDA(cudaFuncSetAttribute(windowed_corr_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    windowed_corr_kernel<R><<<p.N * p.groups_per_n, WC_WARPS * 32, smem, st>>>(p);
+    PP_CUDA(cudaFuncSetAttribute(windowed_corr_kernel<R, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    windowed_corr_kernel<R, CV><<<p.N * p.groups_per_n, WC_WARPS * 32, smem, st>>>(p);
     PP_LAUNCHED();
     return PP_OK;
+}
+
+template <int R>
+static int launch_wcorr(const WCorrParams& p, cudaStream_t st) {
+    if (getenv("PICOPOSE_WCORR_SMEM_F1")) return launch_wcorr_cv<R, 0>(p, st);  // tuning aid
+    switch (p.C) {  // the feature widths PicoPose uses get register-resident f1
+        case 256: return launch_wcorr_cv<R, 8>(p, st);
+        case 128: return launch_wcorr_cv<R, 4>(p, st);
+        case 64: return launch_wcorr_cv<R, 2>(p, st);
+        case 32: return launch_wcorr_cv<R, 1>(p, st);
+        default: return launch_wcorr_cv<R, 0>(p, st);
+    }
 }
 
 }  // namespace pp
@@ -224,6 +340,33 @@ extern "C" int pp_windowed_correlation_prepare_all(const float* feat1, const flo
     PP_CHECK_ARG(L >= 1 && L <= WC_MAX_LEVELS && N > 0 && (long long)N * (L + 1) <= 65535 && C > 0 && H > 0 && W > 0 &&
                      (H >> (L - 1)) > 0 && (W >> (L - 1)) > 0,
                  "pp_windowed_correlation_prepare_all: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(feat1) | reinterpret_cast<uintptr_t>(feat2) | reinterpret_cast<uintptr_t>(f1t)) & 15) == 0;
+    if (L <= 4 && C % 4 == 0 && W % 4 == 0 && aligned && 2LL * N <= 65535) {
+        WPatchArgs a{};
+        a.src[0] = feat1;
+        a.src[1] = feat2;
+        a.dst[0][0] = f1t;
+        a.levels[0] = 1;
+        a.levels[1] = L;
+        bool ok = true;
+        for (int l = 0; l < L; ++l) {
+            PP_CHECK_ARG(f2t_levels[l], "pp_windowed_correlation_prepare_all: null level %d", l);
+            a.dst[1][l] = static_cast<float*>(f2t_levels[l]);
+            ok = ok && (reinterpret_cast<uintptr_t>(f2t_levels[l]) & 15) == 0;
+        }
+        if (ok) {
+            a.N = N;
+            a.C = C;
+            a.H = H;
+            a.W = W;
+            a.patches_x = (W + 7) / 8;
+            dim3 grid(a.patches_x * ((H + 7) / 8), (C + 63) / 64, 2 * N);
+            wcorr_prepare_patch_kernel<<<grid, 256, 0, st>>>(a);
+            PP_LAUNCHED();
+            return PP_OK;
+        }
+    }
     WPrepJobs jobs{};
     jobs.N = N;
     jobs.src[0] = feat1;
@@ -272,6 +415,17 @@ extern "C" int pp_windowed_correlation(const float* f1t, const void* const* f2t_
     p.scale = 1.0f / sqrtf((float)C);
     p.groups_per_n = (p.HW + WC_QUERIES - 1) / WC_QUERIES;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // The tiled kernel (windowed_corr_tiled.cu) when it covers the problem and there are enough 8 x 8 tiles to
+    // occupy the GPU; PICOPOSE_WCORR_KERNEL=tiled|direct forces a choice (tests, tools/bench_stage3.py).
+    int want_tiled = -1;
+    if (const char* e = getenv("PICOPOSE_WCORR_KERNEL")) want_tiled = strcmp(e, "tiled") == 0 ? 1 : strcmp(e, "direct") == 0 ? 0 : -1;
+    const long long tiles = (long long)N * ((W + 7) / 8) * ((H + 7) / 8);
+    if (want_tiled == 1 || (want_tiled < 0 && tiles >= 96)) {
+        bool handled = false;
+        if (int rc = launch_wcorr_tiled(radius, f1t, f2t_levels, L, flow, N, C, H, W, out, st, &handled)) return rc;
+        if (handled) return PP_OK;
+        PP_CHECK_ARG(want_tiled != 1, "pp_windowed_correlation: the tiled kernel does not cover radius %d, C %d, L %d", radius, C, L);
+    }
     switch (radius) {
         case 1: return launch_wcorr<1>(p, st);
         case 2: return launch_wcorr<2>(p, st);

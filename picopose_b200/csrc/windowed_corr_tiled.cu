@@ -1,0 +1,442 @@
+// Fused stage-3 correlation, tiled variant: same result as windowed_corr.cu::windowed_corr_kernel (see that
+// file for the maths and the reference lines), different data movement.
+//
+// The per-query kernel pulls every neighbour vector through L1 once per query: 36 KB per query and level at
+// r = 2, C = 256, and a 4-line LDG costs the L1 wavefront queue ~8 cycles, which is what bounds it.  Here a
+// block owns an 8 x 8 tile of queries.  Per level it asks TMA for ONE RS x RS region of the position-major key
+// map, centred on the tile's mean window, 32 channels at a time (4-D box {32, RS, RS, 1}; coordinates may lie
+// outside the map, TMA zero-fills, which is exactly the lookup's zero padding), double buffered behind
+// mbarriers, together with the tile's own 32-channel slice of f1.  A query whose window lies inside the
+// region takes all its dot products from shared memory (conflict-free 128-byte rows, no bounds checks); one
+// that does not (an outlier flow) reads global memory like the per-query kernel, so any flow field works.
+// Accumulators stay in registers across the C/32 chunks: lane group g of a warp owns neighbours g, g+4, ...
+// of each of the warp's 4 queries.  Taps and region origins of every level are computed up front so that the
+// chunk pipeline runs across level boundaries without draining.
+#include "pp_common.cuh"
+#include "pp_ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace pp {
+
+// called from windowed_corr.cu
+int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
+                       int H, int W, float* out, cudaStream_t st, bool* handled);
+
+namespace {
+
+constexpr int WT_WARPS = 16;
+constexpr int WT_THREADS = WT_WARPS * 32;
+constexpr int WT_QPW = 4;                  // queries per warp
+constexpr int WT_TQ = WT_WARPS * WT_QPW;   // 64 queries: 8 x 8
+constexpr int WT_CH = 32;                  // channels per chunk: one 128-byte row per key
+constexpr int WT_MAX_LEVELS = 4;
+constexpr long long WT_TIMEOUT_CYCLES = 4000000000LL;
+
+struct WTileMaps {
+    CUtensorMap f1;                  // (N, H, W, C) position-major query features
+    CUtensorMap f2[WT_MAX_LEVELS];   // level l: (N, H>>l, W>>l, C)
+};
+
+struct WTileParams {
+    const float* f1t;
+    const float* f2t[WT_MAX_LEVELS];
+    int hl[WT_MAX_LEVELS], wl[WT_MAX_LEVELS];
+    const float* flow;  // (N, 2, H, W)
+    float* out;         // (N, L*D*D, H, W)
+    int N, C, H, W, HW, L;
+    float scale;
+    int tiles_x, tiles_y;
+};
+
+// same arithmetic as corr_lookup.cu::axis_tap / windowed_corr.cu::wc_axis_tap
+__device__ __forceinline__ void wt_axis_tap(float p, int size, int& i0, float& w1) {
+    float den = (float)(size > 1 ? size - 1 : 1);
+    float g = __fsub_rn(__fdiv_rn(__fmul_rn(p, 2.0f), den), 1.0f);
+    float i = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+    float f = floorf(i);
+    w1 = __fsub_rn(i, f);
+    f = fminf(fmaxf(f, -2.0f), (float)size);
+    i0 = (f == f) ? (int)f : -2;
+    if (!(w1 >= 0.0f && w1 <= 1.0f)) w1 = 0.0f;
+}
+
+__device__ __forceinline__ void tma_load_4d(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            dst),
+        "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ void wt_wait(uint32_t bar, uint32_t parity) {
+    if (ptx::mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > WT_TIMEOUT_CYCLES) __trap();  // a lost TMA transaction must not hang the GPU
+    }
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int R>
+struct WT {
+    static constexpr int D = 2 * R + 1, G = D + 2, DD = D * D, GG = G * G;
+    static constexpr int W1 = D + 1;            // side of a regular window's neighbour grid
+    static constexpr int TRIPS = W1 * W1 / 4;   // 4 neighbours per trip (W1 is even)
+    static constexpr int PER = (W1 % 4 == 0) ? 1 : (W1 % 2 == 0 ? W1 / 2 : W1);   // trips after which (row advance, column) repeats
+    static constexpr int ROWS_PER = PER * 4 / W1;
+    static constexpr int RS0 = 8 + W1 + 10;     // region side at level 0: tile + window + slack for the flow's spread
+    static constexpr int RS1 = 4 + 1 + W1 + 6;  // at pooled levels the tile and the spread shrink
+    static constexpr int KEY_WORDS = RS0 * RS0 * WT_CH;
+    static constexpr int F1_WORDS = WT_TQ * WT_CH;
+    static constexpr uint32_t STAGE_BYTES = (KEY_WORDS + F1_WORDS) * 4;
+    static size_t smem_bytes(int L) {
+        size_t w = 2 * (size_t)(KEY_WORDS + F1_WORDS);          // two stages, 128-byte rows
+        w += ((size_t)L * DD * (WT_TQ + 1) + 3) & ~(size_t)3;   // out tile
+        w += (size_t)WT_TQ * GG;                                // per-query correlation grid
+        w += (size_t)L * WT_TQ * 4 * D;                         // taps of every level
+        w += 4 * WT_MAX_LEVELS + 4;                             // region statistics / origins, barriers
+        w += (size_t)WT_MAX_LEVELS * WT_TQ + 4;                 // deferred (level, query) list
+        return w * 4 + 128;                                     // + alignment slack
+    }
+};
+
+// One 32-channel chunk of the regular in-region queries of a warp: per neighbour one 16-byte shared load and four
+// FMAs; the shared addresses are per-lane bases (set at level start) plus compile-time offsets.
+template <int R, int RS, int STAGE>
+__device__ __forceinline__ void wt_chunk(const uint32_t (&base)[WT_QPW][WT<R>::PER], const bool (&fast)[WT_QPW],
+                                         float (&acc)[WT_QPW][WT<R>::TRIPS], uint32_t f1_addr) {
+    using T = WT<R>;
+#pragma unroll
+    for (int qi = 0; qi < WT_QPW; ++qi) {
+        if (fast[qi]) {  // warp-uniform
+            const float4 a = lds128(f1_addr + STAGE * T::STAGE_BYTES + qi * WT_CH * 4);
+#pragma unroll
+            for (int t = 0; t < T::TRIPS; ++t) {
+                const float4 v = lds128(base[qi][t % T::PER] + STAGE * T::STAGE_BYTES + (t / T::PER) * T::ROWS_PER * RS * WT_CH * 4);
+                acc[qi][t] = fmaf(a.x, v.x, fmaf(a.y, v.y, fmaf(a.z, v.z, fmaf(a.w, v.w, acc[qi][t]))));
+            }
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(WT_THREADS, 1)
+windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTileParams p) {
+    using T = WT<R>;
+    constexpr int D = T::D, DD = T::DD, GG = T::GG, W1 = T::W1, TRIPS = T::TRIPS, PER = T::PER, TQ = WT_TQ, QPW = WT_QPW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = lane >> 3, gl = lane & 7;
+    const int L = p.L, rows = L * DD;
+    float* stage0 = smem;                                      // [2][keys RS x RS x 32 | f1 TQ x 32]
+    float* out_tile = smem + 2 * (T::KEY_WORDS + T::F1_WORDS);  // [rows][TQ + 1]
+    float* vals = out_tile + (((size_t)rows * (TQ + 1) + 3) & ~(size_t)3);   // [TQ][GG]
+    int* s_xo = reinterpret_cast<int*>(vals + (size_t)TQ * GG);              // [L][TQ][D]
+    int* s_yo = s_xo + L * TQ * D;
+    float* s_xw = reinterpret_cast<float*>(s_yo + L * TQ * D);
+    float* s_yw = s_xw + L * TQ * D;
+    int* s_red = reinterpret_cast<int*>(s_yw + L * TQ * D);                  // [MAX_LEVELS][4]: sums, count -> origin
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 4 * WT_MAX_LEVELS);
+    int* s_nslow = reinterpret_cast<int*>(s_bar + 2);
+    int* s_slow = s_nslow + 4;                                               // [MAX_LEVELS * TQ]
+    const uint32_t bar0 = ptx::smem_u32(s_bar), bar1 = bar0 + 8;
+    const uint32_t stage_u32 = ptx::smem_u32(stage0);
+
+    int b = blockIdx.x;
+    const int tx = b % p.tiles_x;
+    b /= p.tiles_x;
+    const int ty = b % p.tiles_y;
+    const int n = b / p.tiles_y;
+
+    if (tid == 0) {
+        ptx::mbar_init(bar0, 1);
+        ptx::mbar_init(bar1, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&maps.f1);
+        for (int l = 0; l < L; ++l) ptx::prefetch_tensormap(&maps.f2[l]);
+    }
+    if (tid < 4 * WT_MAX_LEVELS) s_red[tid] = 0;
+    if (tid == 32) *s_nslow = 0;
+    __syncthreads();
+
+    // ---- taps and window extents of every level; the tile's mean window per level ----
+    int q_hw[QPW];
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) {
+        const int ql = warp * QPW + qi;
+        const int qh = ty * 8 + (ql >> 3), qw = tx * 8 + (ql & 7);
+        const bool ok = qh < p.H && qw < p.W;
+        q_hw[qi] = ok ? qh * p.W + qw : -1;
+        float cx = 0.f, cy = 0.f;
+        if (ok) {
+            cx = __fadd_rn((float)qw, __ldg(p.flow + ((size_t)n * 2 + 0) * p.HW + q_hw[qi]));
+            cy = __fadd_rn((float)qh, __ldg(p.flow + ((size_t)n * 2 + 1) * p.HW + q_hw[qi]));
+        }
+        for (int l = 0; l < L; ++l) {
+            const float inv = 1.0f / (float)(1 << l);
+            const int base = (l * TQ + ql) * D;
+            if (lane < D) {
+                int i0;
+                float w1;
+                wt_axis_tap(__fadd_rn(__fmul_rn(cx, inv), (float)(lane - R)), p.wl[l], i0, w1);
+                s_xo[base + lane] = i0;
+                s_xw[base + lane] = w1;
+                wt_axis_tap(__fadd_rn(__fmul_rn(cy, inv), (float)(lane - R)), p.hl[l], i0, w1);
+                s_yo[base + lane] = i0;
+                s_yw[base + lane] = w1;
+            }
+            __syncwarp();
+            if (lane == 0 && ok) {
+                atomicAdd(&s_red[l * 4 + 0], s_xo[base] + s_xo[base + D - 1] + 2);  // 2 * window centre
+                atomicAdd(&s_red[l * 4 + 1], s_yo[base] + s_yo[base + D - 1] + 2);
+                atomicAdd(&s_red[l * 4 + 2], 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < L) {
+        const float cnt = (float)max(s_red[tid * 4 + 2], 1);
+        const float rs = (float)(tid == 0 ? T::RS0 : T::RS1);
+        const int X0 = (int)floorf((float)s_red[tid * 4 + 0] / (2.0f * cnt) - 0.5f * rs + 0.5f);
+        const int Y0 = (int)floorf((float)s_red[tid * 4 + 1] / (2.0f * cnt) - 0.5f * rs + 0.5f);
+        s_red[tid * 4 + 0] = X0;
+        s_red[tid * 4 + 1] = Y0;
+    }
+    __syncthreads();
+
+    const int nch = p.C / WT_CH;
+    const int total = L * nch;
+    auto issue = [&](int it) {  // thread 0: TMA of chunk `it` into stage it & 1
+        const int l = it / nch, c = it - l * nch;
+        const int rs = l == 0 ? T::RS0 : T::RS1;
+        const uint32_t bar = (it & 1) ? bar1 : bar0;
+        const uint32_t st = stage_u32 + (uint32_t)(it & 1) * T::STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(bar, (uint32_t)(rs * rs + TQ) * WT_CH * 4);
+        tma_load_4d(&maps.f2[l], bar, st, c * WT_CH, s_red[l * 4 + 0], s_red[l * 4 + 1], n);
+        tma_load_4d(&maps.f1, bar, st + T::KEY_WORDS * 4, c * WT_CH, tx * 8, ty * 8, n);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (total > 1) issue(1);
+    }
+
+    // D*D bilinear samples of query ql at level bl from its neighbour grid vq (row stride gs), as corr_lookup.cu does
+    auto blend = [&](int bl, int ql, const float* vq, int x0, int y0, int gs) {
+        const int tb = (bl * TQ + ql) * D;
+        for (int k = lane; k < DD; k += 32) {
+            const int ai = k / D, bi = k - ai * D;
+            const float* t0 = vq + (s_yo[tb + bi] - y0) * gs + (s_xo[tb + ai] - x0);
+            const float wx1 = s_xw[tb + ai], wx0 = __fsub_rn(1.0f, wx1);
+            const float wy1 = s_yw[tb + bi], wy0 = __fsub_rn(1.0f, wy1);
+            const float h0 = fmaf(t0[1], wx1, t0[0] * wx0);
+            const float h1 = fmaf(t0[gs + 1], wx1, t0[gs] * wx0);
+            out_tile[(size_t)(bl * DD + k) * (TQ + 1) + ql] = fmaf(h1, wy1, h0 * wy0);
+        }
+    };
+
+    int xmin[QPW], ymin[QPW], gx[QPW], gy[QPW];
+    bool fast[QPW];
+    uint32_t base[QPW][PER];
+    float acc[QPW][TRIPS];
+    const uint32_t f1_addr = stage_u32 + T::KEY_WORDS * 4 + (uint32_t)(warp * QPW) * WT_CH * 4 + gl * 16;
+    int l = 0, c = 0;
+    for (int it = 0; it < total; ++it) {
+        if (c == 0) {  // level start: which of this warp's queries have a regular window inside the staged region
+            const int rs = l == 0 ? T::RS0 : T::RS1;
+            const int X0 = s_red[l * 4 + 0], Y0 = s_red[l * 4 + 1];
+#pragma unroll
+            for (int qi = 0; qi < QPW; ++qi) {
+                const int tb = (l * TQ + warp * QPW + qi) * D;
+                xmin[qi] = s_xo[tb];
+                ymin[qi] = s_yo[tb];
+                gx[qi] = s_xo[tb + D - 1] + 2 - xmin[qi];
+                gy[qi] = s_yo[tb + D - 1] + 2 - ymin[qi];
+                // regular (or border-clamped, hence smaller) window whose W1 x W1 grid lies inside the staged region
+                fast[qi] = q_hw[qi] >= 0 && gx[qi] <= W1 && gy[qi] <= W1 && xmin[qi] >= X0 && xmin[qi] + W1 <= X0 + rs &&
+                           ymin[qi] >= Y0 && ymin[qi] + W1 <= Y0 + rs;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int id = 4 * j + grp, gyi = id / W1, gxi = id % W1;
+                    base[qi][j] = stage_u32 + (uint32_t)(((ymin[qi] - Y0 + gyi) * rs + (xmin[qi] - X0 + gxi)) * WT_CH * 4 + gl * 16);
+                }
+#pragma unroll
+                for (int t = 0; t < TRIPS; ++t) acc[qi][t] = 0.f;
+            }
+        }
+        wt_wait((it & 1) ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+        if (l == 0) {
+            if (it & 1) wt_chunk<R, T::RS0, 1>(base, fast, acc, f1_addr);
+            else wt_chunk<R, T::RS0, 0>(base, fast, acc, f1_addr);
+        } else {
+            if (it & 1) wt_chunk<R, T::RS1, 1>(base, fast, acc, f1_addr);
+            else wt_chunk<R, T::RS1, 0>(base, fast, acc, f1_addr);
+        }
+        __syncthreads();  // everyone is done with this stage
+        if (tid == 0 && it + 2 < total) issue(it + 2);
+
+        if (c == nch - 1) {  // level end: finish the dot products, blend the D*D samples of each query
+#pragma unroll
+            for (int qi = 0; qi < QPW; ++qi) {
+                if (q_hw[qi] < 0) continue;  // warp-uniform
+                const int ql = warp * QPW + qi;
+                if (!fast[qi]) {
+                    // stretched window (float round trip) or an outlier flow outside the staged region: deferred, so
+                    // that its global-memory latency does not hold up the block's pipeline
+                    if (lane == 0) s_slow[atomicAdd(s_nslow, 1)] = (l << 16) | ql;
+                    continue;
+                }
+                float* vq = vals + (size_t)ql * GG;
+#pragma unroll
+                for (int t = 0; t < TRIPS; ++t) {
+                    float s = acc[qi][t];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    if (gl == 0) vq[t * 4 + grp] = s * p.scale;
+                }
+                __syncwarp();
+                blend(l, ql, vq, xmin[qi], ymin[qi], W1);
+                __syncwarp();
+            }
+            c = 0;
+            ++l;
+        } else {
+            ++c;
+        }
+    }
+    __syncthreads();
+    // deferred queries, one per warp at a time, the per-query kernel's way (straight from global memory)
+    const int nslow = *s_nslow;
+    for (int i = warp; i < nslow; i += WT_WARPS) {
+        const int sl = s_slow[i] >> 16, ql = s_slow[i] & 0xFFFF;
+        const int qh = ty * 8 + (ql >> 3), qw = tx * 8 + (ql & 7);
+        const int Hl = p.hl[sl], Wl = p.wl[sl];
+        const int tb = (sl * TQ + ql) * D;
+        const int x0 = s_xo[tb], y0 = s_yo[tb];
+        const int sgx = s_xo[tb + D - 1] + 2 - x0, sgy = s_yo[tb + D - 1] + 2 - y0;
+        const float* f1q = p.f1t + ((size_t)n * p.HW + qh * p.W + qw) * p.C + gl * 4;
+        const float* f2n = p.f2t[sl] + (size_t)n * Hl * Wl * p.C + gl * 4;
+        float* vq = vals + (size_t)warp * GG;  // the fast path is done with `vals`: one scratch grid per warp
+        const int npts = sgx * sgy;
+        const float rgx = 1.0f / (float)sgx;
+        for (int idx = 0; idx < npts; idx += 4) {
+            const int id = idx + grp;
+            const int gyi = (int)(((float)id + 0.5f) * rgx), gxi = id - gyi * sgx;  // id / sgx, exact for these small integers
+            const int x = x0 + gxi, y = y0 + gyi;
+            float s = 0.f;
+            if (id < npts && (unsigned)x < (unsigned)Wl && (unsigned)y < (unsigned)Hl) {
+                const float* v = f2n + (size_t)(y * Wl + x) * p.C;
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+                for (int cc = 0; cc < p.C; cc += 32) {
+                    const float4 av = __ldg(reinterpret_cast<const float4*>(f1q + cc));
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(v + cc));
+                    s4.x = fmaf(av.x, bv.x, s4.x);
+                    s4.y = fmaf(av.y, bv.y, s4.y);
+                    s4.z = fmaf(av.z, bv.z, s4.z);
+                    s4.w = fmaf(av.w, bv.w, s4.w);
+                }
+                s = (s4.x + s4.y) + (s4.z + s4.w);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (gl == 0 && id < npts) vq[id] = s * p.scale;
+        }
+        __syncwarp();
+        blend(sl, ql, vq, x0, y0, sgx);
+        __syncwarp();
+    }
+    __syncthreads();
+    // out[n, row, tile]: 8-float (32-byte sector) runs, 8 of them per row
+    float* out_n = p.out + (size_t)n * rows * p.HW;
+    for (int row = warp; row < rows; row += WT_WARPS) {
+#pragma unroll
+        for (int q0 = 0; q0 < TQ; q0 += 32) {
+            const int ql = q0 + lane;
+            const int qh = ty * 8 + (ql >> 3), qw = tx * 8 + (ql & 7);
+            if (qh < p.H && qw < p.W) __stcs(out_n + (size_t)row * p.HW + qh * p.W + qw, out_tile[(size_t)row * (TQ + 1) + ql]);
+        }
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// (N, Hm, Wm, C) fp32, box {32, bw, bh, 1}, no swizzle, zero fill outside
+int make_map(CUtensorMap* map, const void* base, int N, int Hm, int Wm, int C, int bw, int bh) {
+    auto fn = encode_fn();
+    if (!fn) return fail(PP_ERR_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wm, (cuuint64_t)Hm, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Wm * C * 4, (cuuint64_t)Hm * Wm * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)WT_CH, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PP_ERR_LAUNCH, "cuTensorMapEncodeTiled (windowed correlation) failed with CUresult %d", (int)r);
+    return PP_OK;
+}
+
+template <int R>
+int launch(const WTileMaps& maps, const WTileParams& p, cudaStream_t st) {
+    const size_t smem = WT<R>::smem_bytes(p.L);
+    auto kern = windowed_corr_tiled_kernel<R>;
+    PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<p.N * p.tiles_x * p.tiles_y, WT_THREADS, smem, st>>>(maps, p);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+}  // namespace
+
+// Runs the tiled kernel when it covers the problem (*handled = true); otherwise leaves it to the per-query kernel.
+int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
+                       int H, int W, float* out, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (radius < 1 || radius > 2 || L > WT_MAX_LEVELS || C % WT_CH != 0) return PP_OK;
+    const size_t smem = radius == 1 ? WT<1>::smem_bytes(L) : WT<2>::smem_bytes(L);
+    if (smem > 220 * 1024) return PP_OK;
+    WTileMaps maps;
+    WTileParams p{};
+    if (int rc = make_map(&maps.f1, f1t, N, H, W, C, 8, 8)) return rc;
+    for (int l = 0; l < L; ++l) {
+        const int rs = radius == 1 ? (l == 0 ? WT<1>::RS0 : WT<1>::RS1) : (l == 0 ? WT<2>::RS0 : WT<2>::RS1);
+        if (int rc = make_map(&maps.f2[l], f2t_levels[l], N, H >> l, W >> l, C, rs, rs)) return rc;
+        p.f2t[l] = static_cast<const float*>(f2t_levels[l]);
+        p.hl[l] = H >> l;
+        p.wl[l] = W >> l;
+    }
+    p.f1t = f1t;
+    p.flow = flow;
+    p.out = out;
+    p.N = N;
+    p.C = C;
+    p.H = H;
+    p.W = W;
+    p.HW = H * W;
+    p.L = L;
+    p.scale = 1.0f / sqrtf((float)C);
+    p.tiles_x = (W + 7) / 8;
+    p.tiles_y = (H + 7) / 8;
+    *handled = true;
+    return radius == 1 ? launch<1>(maps, p, st) : launch<2>(maps, p, st);
+}
+
+}  // namespace pp

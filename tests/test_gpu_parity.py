@@ -371,11 +371,21 @@ def test_similarity_volume_native_size():
 @pytest.mark.parametrize("N,C,H,L,r,sigma", [
     (2, 256, 16, 1, 2, 2.0), (1, 256, 32, 2, 2, 2.0), (1, 256, 64, 3, 2, 3.0),     # FlowDecoder ladder (r = int(4/2))
     (1, 64, 32, 3, 4, 4.0), (1, 32, 24, 2, 3, 40.0), (1, 8, 12, 2, 1, 2.0), (1, 256, 16, 1, 8, 3.0),
+    (1, 64, 40, 2, 2, 30.0), (3, 32, 20, 2, 2, 2.0), (2, 96, 36, 3, 1, 1.0), (1, 32, 8, 1, 2, 0.5),
+    (1, 128, 16, 2, 2, 1.0), (1, 16, 13, 2, 2, 2.0), (1, 64, 48, 4, 2, 3.0),
 ])
-def test_windowed_correlation_vs_oracle(N, C, H, L, r, sigma):
-    """Fused CorrelationPyramid + CorrLookup (no volume) against the oracle's two-step computation."""
+@pytest.mark.parametrize("kernel", ["auto", "direct", "tiled"])
+def test_windowed_correlation_vs_oracle(N, C, H, L, r, sigma, kernel, monkeypatch):
+    """Fused CorrelationPyramid + CorrLookup (no volume) against the oracle's two-step computation, through the
+    per-query kernel (register- and shared-memory-resident query features: C in {32, 64, 128, 256} vs other
+    widths), the TMA-tiled kernel (in-region and far-flow queries), and what callers get (`auto`); both layout
+    kernels (patch kernel for L <= 4 and W % 4 == 0, per-level kernel otherwise)."""
     from picopose_b200.corr_lookup import CorrLookup
     from picopose_b200.correlation import CorrelationPyramid, LazyCorrelationPyramid
+    if kernel == "tiled" and (r > 2 or C % 32 or L > 4):
+        pytest.skip("the tiled kernel covers r <= 2, C % 32 == 0, L <= 4")
+    if kernel != "auto":
+        monkeypatch.setenv("PICOPOSE_WCORR_KERNEL", kernel)
     gen = torch.Generator().manual_seed(31 + r)
     f1 = torch.randn(N, C, H, H, generator=gen)
     f2 = torch.randn(N, C, H, H, generator=gen)

@@ -64,8 +64,21 @@ def main():
         t_two = timed(lambda: corr_lookup(correlation_pyramid(f1, f2, L), flow, r), a.iters)
         t_two_bf16 = timed(lambda: corr_lookup(correlation_pyramid(f1, f2, L, mode="bf16"), flow, r), a.iters)
         t_fused = timed(lambda: windowed_correlation(f1, f2, flow, L, r), a.iters)
+        t_kernel = {}
+        for kern in ("direct", "tiled"):
+            os.environ["PICOPOSE_WCORR_KERNEL"] = kern
+            try:
+                if float((windowed_correlation(f1, f2, flow, L, r) - ref).abs().max()) > 1e-4:
+                    raise AssertionError("kernel %s disagrees with the two-step path" % kern)
+                t_kernel[kern] = timed(lambda: windowed_correlation(f1, f2, flow, L, r), a.iters)
+            except RuntimeError:
+                t_kernel[kern] = None
+        del os.environ["PICOPOSE_WCORR_KERNEL"]
+        smooth = flow.mean(dim=(2, 3), keepdim=True) + 0.25 * flow          # a smooth field: what stage 2 hands over
+        t_smooth = timed(lambda: windowed_correlation(f1, f2, smooth, L, r), a.iters)
         row = {"level": "%dx%d, L=%d, r=%d, N=%d, C=%d" % (H, H, L, r, N, C), "torch_matmul_plus_lookup_ms": t_torch,
                "pyramid_fp32mode_plus_lookup_ms": t_two, "pyramid_bf16_plus_lookup_ms": t_two_bf16, "fused_ms": t_fused,
+               "fused_direct_kernel_ms": t_kernel["direct"], "fused_tiled_kernel_ms": t_kernel["tiled"], "fused_smooth_flow_ms": t_smooth,
                "max_abs_err_two_step_vs_torch": e2, "max_abs_err_fused_vs_torch": ef,
                "volume_bytes_avoided": sum(N * H * H * (H >> i) * (H >> i) * 4 for i in range(L))}
         rows.append(row)
