@@ -420,7 +420,7 @@ extern "C" int pp_windowed_correlation(const float* f1t, const void* const* f2t_
     int want_tiled = -1;
     if (const char* e = getenv("PICOPOSE_WCORR_KERNEL")) want_tiled = strcmp(e, "tiled") == 0 ? 1 : strcmp(e, "direct") == 0 ? 0 : -1;
     const long long tiles = (long long)N * ((W + 7) / 8) * ((H + 7) / 8);
-    if (want_tiled == 1 || (want_tiled < 0 && tiles >= 96)) {
+    if (want_tiled == 1 || (want_tiled < 0 && tiles >= 48)) {
         bool handled = false;
         if (int rc = launch_wcorr_tiled(radius, f1t, f2t_levels, L, flow, N, C, H, W, out, st, &handled)) return rc;
         if (handled) return PP_OK;
