@@ -236,14 +236,24 @@ def run_ours(args):
     up_done = [torch.cuda.Event() for _ in range(2)]
     used = [torch.cuda.Event() for _ in range(2)]
 
+    # N > 1: detection d arrives at rank d's host; each rank uploads only its own detection and the batch is
+    # assembled GPU-to-GPU (ShardedMatcher.gather_queries, NCCL over NVLink) -- not world x the bytes over PCIe.
+    own = [(torch.empty_like(tar_d[rank:rank + 1]), torch.empty_like(mask_d[rank:rank + 1])) for _ in range(2)]
+    own_tar_h, own_mask_h = tar_h[rank:rank + 1], mask_h[rank:rank + 1]
+
     def e2e_loop(n):
         for it in range(n):
             sl = it & 1
             with torch.cuda.stream(copy_stream):
                 if it >= 2:
                     copy_stream.wait_event(used[sl])       # the kernels that read this buffer two steps ago are done
-                bufs[sl][0].copy_(tar_h, non_blocking=True)
-                bufs[sl][1].copy_(mask_h, non_blocking=True)
+                if world == 1:
+                    bufs[sl][0].copy_(tar_h, non_blocking=True)
+                    bufs[sl][1].copy_(mask_h, non_blocking=True)
+                else:
+                    own[sl][0].copy_(own_tar_h, non_blocking=True)
+                    own[sl][1].copy_(own_mask_h, non_blocking=True)
+                    matcher.gather_queries(own[sl][0], own[sl][1], out=bufs[sl])   # ordered after the uploads, off the main stream
                 up_done[sl].record(copy_stream)
             main_stream.wait_event(up_done[sl])
             s, i, _ = step(bufs[sl][0], bufs[sl][1], src_d)
@@ -317,8 +327,10 @@ def run_ours(args):
                 "parallelism": "1 GPU" if world == 1 else "template bank sharded x%d + NCCL all-gather top-k merge" % world,
                 "l2": "per-step inputs (%.0f MB fp32 template features) exceed the 126 MB L2; no explicit flush"
                       % (src_d.numel() * 4 / 1e6),
-                "e2e_inputs": "query features + mask copied from pinned host memory every step; template features are "
-                              "device-resident fp32 (as in run_test.py:121-134) and re-prepared every step",
+                "e2e_inputs": ("query features + mask copied from pinned host memory every step; template features are "
+                               "device-resident fp32 (as in run_test.py:121-134) and re-prepared every step"
+                               + ("" if world == 1 else "; each rank uploads its own detection (h2d_bytes_per_step is the "
+                                  "whole job's) and the batch is all-gathered over NVLink inside the timed region")),
             },
             "clocks": clocks,
             "e2e": {"value": world * 1e3 / (e2e_ms_total / args.steps), "unit": "detections/s",

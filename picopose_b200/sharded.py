@@ -1,7 +1,8 @@
 """Multi-GPU stage-1 matching: template-axis sharding + one all-gather top-k merge.
 
 One process per GPU (torchrun).  Rank g keeps views [lo_g, hi_g) of every object's template bank
-(prepared bf16, resident), all ranks see the whole detection batch, each computes its local
+(prepared bf16, resident), all ranks see the whole detection batch (a rank's own detections come from its
+host, the others' over NVLink: `ShardedMatcher.gather_queries`), each computes its local
 sim_avg[:, lo_g:hi_g] and a local top-k with GLOBAL view indices packed as one (B, k, 2) tensor, and a single
 NCCL all-gather of those pairs over NVLink is merged identically on every rank by one small kernel.  Every (detection, view)
 score is independent (utils/matching.py:47-67); only topk (:68) couples views, hence one exchange.
@@ -96,6 +97,21 @@ class ShardedMatcher:
         assert src_feats_shard.shape[1] == self.hi - self.lo
         self.bank = TemplateBank.from_features(src_feats_shard, mode)
         return self.bank
+
+    def gather_queries(self, tar_local: torch.Tensor, mask_local: torch.Tensor, out=None):
+        """Each rank received its own detections' query features (b, C, H, W) and masks (b, Hm, Wm) from its host;
+        every rank needs the whole batch (template-axis sharding), so the queries travel GPU-to-GPU: two
+        all-gathers over NVLink instead of every rank uploading world x the data over PCIe.
+        -> (tar (world*b, C, H, W), mask (world*b, Hm, Wm)), rank-major; `out` = optional preallocated pair."""
+        if self.world == 1:
+            return tar_local, mask_local
+        tar_local, mask_local = tar_local.contiguous(), mask_local.contiguous()
+        if out is None:
+            out = (tar_local.new_empty((self.world * tar_local.shape[0],) + tuple(tar_local.shape[1:])),
+                   mask_local.new_empty((self.world * mask_local.shape[0],) + tuple(mask_local.shape[1:])))
+        dist.all_gather_into_tensor(out[0], tar_local, group=self.group)
+        dist.all_gather_into_tensor(out[1], mask_local, group=self.group)
+        return out
 
     def match(self, src, tar_feat, tar_mask, topk=5, bank_index=None, mode=None):
         """src: this rank's shard, a TemplateBank or raw (B|n_banks, hi-lo, C, H, W) features."""

@@ -43,6 +43,17 @@ def _worker(rank, world, port, n_views, k, ret):
         val, idx = merge_topk(_pairs(s, i + lo, k), k)          # CPU tensors -> torch merge, gloo all-gather
         ref_v, ref_i = torch.topk(full, k, dim=1)
         ok = torch.equal(val, ref_v) and torch.equal(idx, ref_i)
+        # query exchange: each rank holds its own detection, gather_queries assembles the rank-major batch
+        from picopose_b200.sharded import ShardedMatcher
+        m = ShardedMatcher(n_views)
+        assert (m.lo, m.hi) == (lo, hi)
+        tar_all = torch.arange(world * 2 * 3 * 2 * 2, dtype=torch.float32).view(world * 2, 3, 2, 2)
+        mask_all = (torch.arange(world * 2 * 4 * 4).view(world * 2, 4, 4) % 3 == 0).float()
+        t, mk = m.gather_queries(tar_all[2 * rank:2 * rank + 2], mask_all[2 * rank:2 * rank + 2])
+        ok = ok and torch.equal(t, tar_all) and torch.equal(mk, mask_all)
+        pre = (torch.empty_like(tar_all), torch.empty_like(mask_all))
+        t2, _ = m.gather_queries(tar_all[2 * rank:2 * rank + 2], mask_all[2 * rank:2 * rank + 2], out=pre)
+        ok = ok and t2 is pre[0] and torch.equal(pre[0], tar_all) and torch.equal(pre[1], mask_all)
         gathered = [None] * world
         dist.all_gather_object(gathered, (ok, idx.tolist()))
         if rank == 0:
