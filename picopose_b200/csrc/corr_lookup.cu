@@ -300,23 +300,28 @@ __global__ void __launch_bounds__(128) corr_lookup_generic_kernel(const LookupPa
 }
 
 // ---- generic bilinear sampler (F.grid_sample bilinear / zeros) -----------------------------
-__global__ void bilinear_sample_kernel(const float* __restrict__ feat, const float* __restrict__ grid,
-                                       int N, int C, int Hf, int Wf, int Ho, int Wo, int grid_chw,
-                                       int align_corners, int scale, float* __restrict__ out) {
-    // one thread per output pixel, loops over channels: reads of the 4 taps are coalesced across
-    // neighbouring pixels when the sampling field is smooth (feature warping by a flow field).
+// A thread takes one output pixel and BS_CPT channels (blockIdx.y picks the channel chunk): the tap arithmetic is
+// done once per BS_CPT channels, the 4 * BS_CPT tap loads are independent, and for every channel the reads of
+// neighbouring pixels are coalesced when the sampling field is smooth (feature warping by a flow field) and
+// the stores always are.
+constexpr int BS_CPT = 8;
+__global__ void __launch_bounds__(128) bilinear_sample_kernel(const float* __restrict__ feat, const float* __restrict__ grid,
+                                                              int N, int C, int Hf, int Wf, int Ho, int Wo, int grid_chw,
+                                                              int align_corners, int scale, float* __restrict__ out) {
     const long long total = (long long)N * Ho * Wo;
+    const int c0 = blockIdx.y * BS_CPT;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i / ((long long)Ho * Wo));
         const int pix = (int)(i - (long long)n * Ho * Wo);
         float gx, gy;
         if (grid_chw) {
-            gx = grid[((size_t)n * 2 + 0) * Ho * Wo + pix];
-            gy = grid[((size_t)n * 2 + 1) * Ho * Wo + pix];
+            gx = __ldg(grid + ((size_t)n * 2 + 0) * Ho * Wo + pix);
+            gy = __ldg(grid + ((size_t)n * 2 + 1) * Ho * Wo + pix);
         } else {
-            gx = grid[((size_t)n * Ho * Wo + pix) * 2 + 0];
-            gy = grid[((size_t)n * Ho * Wo + pix) * 2 + 1];
+            const float2 g2 = __ldg(reinterpret_cast<const float2*>(grid) + (size_t)n * Ho * Wo + pix);
+            gx = g2.x;
+            gy = g2.y;
         }
         if (scale) {
             gx = __fsub_rn(__fdiv_rn(__fmul_rn(gx, 2.0f), (float)(Wf > 1 ? Wf - 1 : 1)), 1.0f);
@@ -341,15 +346,26 @@ __global__ void bilinear_sample_kernel(const float* __restrict__ feat, const flo
         const float w10 = (okx0 && oky1) ? wx0 * wy1 : 0.f, w11 = (okx1 && oky1) ? wx1 * wy1 : 0.f;
         const int xa = min(max(x0, 0), Wf - 1), xb = min(max(x0 + 1, 0), Wf - 1);
         const int ya = min(max(y0, 0), Hf - 1), yb = min(max(y0 + 1, 0), Hf - 1);
-        const float* f = feat + (size_t)n * C * Hf * Wf;
-        float* o = out + (size_t)n * C * Ho * Wo + pix;
-        for (int c = 0; c < C; ++c) {
-            const float* fc = f + (size_t)c * Hf * Wf;
-            float acc = fc[ya * Wf + xa] * w00;
-            acc = fmaf(fc[ya * Wf + xb], w01, acc);
-            acc = fmaf(fc[yb * Wf + xa], w10, acc);
-            acc = fmaf(fc[yb * Wf + xb], w11, acc);
-            o[(size_t)c * Ho * Wo] = acc;
+        const size_t plane = (size_t)Hf * Wf, oplane = (size_t)Ho * Wo;
+        const float* f = feat + ((size_t)n * C + c0) * plane;
+        float* o = out + ((size_t)n * C + c0) * oplane + pix;
+        const int o00 = ya * Wf + xa, o01 = ya * Wf + xb, o10 = yb * Wf + xa, o11 = yb * Wf + xb;
+        float v00[BS_CPT], v01[BS_CPT], v10[BS_CPT], v11[BS_CPT];
+#pragma unroll
+        for (int c = 0; c < BS_CPT; ++c) {
+            const float* fc = f + (size_t)(c0 + c < C ? c : 0) * plane;   // clamp: the tail chunk re-reads its first channel
+            v00[c] = __ldg(fc + o00);
+            v01[c] = __ldg(fc + o01);
+            v10[c] = __ldg(fc + o10);
+            v11[c] = __ldg(fc + o11);
+        }
+#pragma unroll
+        for (int c = 0; c < BS_CPT; ++c) {
+            float acc = v00[c] * w00;
+            acc = fmaf(v01[c], w01, acc);
+            acc = fmaf(v10[c], w10, acc);
+            acc = fmaf(v11[c], w11, acc);
+            if (c0 + c < C) __stcs(o + (size_t)c * oplane, acc);
         }
     }
 }
@@ -460,10 +476,12 @@ extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, i
     PP_CHECK_ARG(feat && grid && out, "pp_bilinear_sample: null pointer");
     PP_CHECK_ARG(N > 0 && C > 0 && Hf > 0 && Wf > 0 && Ho > 0 && Wo > 0, "pp_bilinear_sample: bad shape");
     const long long total = (long long)N * Ho * Wo;
+    PP_CHECK_ARG((C + BS_CPT - 1) / BS_CPT <= 65535, "pp_bilinear_sample: too many channels");
+    PP_CHECK_ARG(grid_chw || (reinterpret_cast<uintptr_t>(grid) & 7) == 0, "pp_bilinear_sample: grid must be 8-byte aligned");
     int grid_dim = (int)((total + 127) / 128);
-    const int cap = sm_count() * 16;
+    const int cap = sm_count() * 64;
     if (grid_dim > cap) grid_dim = cap;
-    bilinear_sample_kernel<<<grid_dim, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    bilinear_sample_kernel<<<dim3(grid_dim, (C + BS_CPT - 1) / BS_CPT), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         feat, grid, N, C, Hf, Wf, Ho, Wo, grid_chw, align_corners, scale, out);
     PP_LAUNCHED();
     return PP_OK;
