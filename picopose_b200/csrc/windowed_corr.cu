@@ -299,7 +299,6 @@ static int launch_wcorr_cv(const WCorrParams& p, cudaStream_t st) {
 
 template <int R>
 static int launch_wcorr(const WCorrParams& p, cudaStream_t st) {
-    if (getenv("PICOPOSE_WCORR_SMEM_F1")) return launch_wcorr_cv<R, 0>(p, st);  // tuning aid
     switch (p.C) {  // the feature widths PicoPose uses get register-resident f1
         case 256: return launch_wcorr_cv<R, 8>(p, st);
         case 128: return launch_wcorr_cv<R, 4>(p, st);

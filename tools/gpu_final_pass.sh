@@ -1,5 +1,9 @@
+#!/bin/bash
+# One gpurun call that re-validates and re-measures everything on a single B200: GPU tests, smoke, both bench arms,
+# the lookup sweep, the ncu launch list and an `ncu --set full` capture of one whole timed step (outputs in gpurun_out/).
+#   gpurun --timeout 1800 -- 'bash tools/gpu_final_pass.sh'
 set -x
-cd /root/repo
+cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 600 python bench.py > gpurun_out/bench_r1q.json 2> gpurun_out/bench_r1q.err; tail -c 3000 gpurun_out/bench_r1q.json
