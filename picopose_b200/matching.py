@@ -114,6 +114,9 @@ def _resolve_bank(src_feats, mode, B):
     batch-expanded view (stride 0 over B) of one shared bank."""
     if isinstance(src_feats, TemplateBank):
         return src_feats, None
+    from .serving import BankHandle
+    if isinstance(src_feats, BankHandle):            # resident banks travelling through the reference's own loop
+        return src_feats.bank, src_feats.bank_index
     if src_feats.dim() != 5:
         raise ValueError("src_feats must be (B, N, C, H, W)")
     if src_feats.shape[0] > 1 and src_feats.stride(0) == 0:
@@ -148,6 +151,8 @@ def _check_bank(bank, bank_index, tar_feat):
     if bank_index is None and bank.n_banks != B:
         raise ValueError(f"{bank.n_banks} banks for {B} detections: pass bank_index")
     if bank_index is not None:
+        if bank_index.numel() != B:
+            raise ValueError(f"bank_index names {bank_index.numel()} banks for {B} detections")
         bank_index = bank_index.to(device=tar_feat.device, dtype=torch.int32).contiguous()
     return bank_index
 

@@ -477,3 +477,29 @@ def test_topk_matches_torch():
     assert torch.equal(score, torch.sort(s, dim=1, descending=True).values)
     with pytest.raises(RuntimeError):
         topk_scores(s, 643)
+
+
+def test_bank_handle_through_the_reference_loop():
+    """as_bank: resident prepared banks flowing through run_test.py's gather + picopose.py's normalize give the same
+    ranking as the dense fp32 features the reference passes."""
+    import torch.nn.functional as F
+    from picopose_b200.matching import matching_templates
+    from picopose_b200.serving import BankHandle, as_bank
+    gen = torch.Generator().manual_seed(5)
+    n_obj, N, C, H = 3, 12, 64, 16
+    feats = torch.randn(n_obj, N, C, H, H, generator=gen)
+    obj_idx = torch.tensor([2, 0, 2, 1])
+    tar = feats[obj_idx, torch.tensor([4, 7, 1, 9])] + 0.3 * torch.randn(4, C, H, H, generator=gen)
+    mask = synth.disc_mask(4)
+    templates_data = {"template_feature": as_bank(feats.to(DEV), mode="fp32")}
+    src = templates_data["template_feature"][obj_idx.to(DEV)].contiguous()
+    src = F.normalize(src, dim=2)
+    assert isinstance(src, BankHandle)
+    s, i = matching_templates(src, tar.to(DEV), None, mask.to(DEV), topk=3)
+    ref_s, ref_i = OM.matching_templates(F.normalize(feats[obj_idx], dim=2), tar, None, mask, topk=3)
+    assert i.cpu().tolist() == ref_i.tolist() and i[:, 0].cpu().tolist() == [4, 7, 1, 9]
+    np.testing.assert_allclose(s.cpu().numpy(), ref_s.numpy(), rtol=0, atol=1e-5)
+    d_s, d_i = matching_templates(F.normalize(feats[obj_idx], dim=2).to(DEV), tar.to(DEV), None, mask.to(DEV), topk=3, mode="fp32")
+    assert d_i.cpu().tolist() == i.cpu().tolist()
+    with pytest.raises(ValueError):
+        matching_templates(src[:3], tar.to(DEV), None, mask.to(DEV), topk=3)

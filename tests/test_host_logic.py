@@ -179,3 +179,29 @@ def test_reference_flow_decoder_builds_on_the_overlay():
             if ours(k):
                 del sys.modules[k]
         sys.modules.update(saved_mods)
+
+
+def test_bank_handle_passes_the_reference_loop_operations_through():
+    """BankHandle: what run_test.py:161-162 and model/picopose.py:99 do to the cached template features
+    is index bookkeeping on the handle; anything else raises instead of computing on data it does not have."""
+    import torch.nn.functional as F
+    from picopose_b200.serving import BankHandle
+
+    class FakeBank:
+        n_banks, n_views, C, H, W = 5, 7, 8, 4, 4
+        device = torch.device("cpu")
+
+    h = BankHandle(FakeBank())
+    assert tuple(h.shape) == (5, 7, 8, 4, 4) and h.dim() == 5 and h.dtype == torch.float32 and h.bank_index is None
+    templates_data = {"template_feature": h}
+    obj_idx = torch.tensor([[3, 1, 3]]).reshape(-1)
+    picked = templates_data["template_feature"][obj_idx].contiguous()        # run_test.py:161-162
+    assert isinstance(picked, BankHandle) and tuple(picked.shape) == (3, 7, 8, 4, 4)
+    assert picked.bank_index.tolist() == [3, 1, 3] and picked.bank is h.bank
+    assert F.normalize(picked, dim=2) is picked                              # model/picopose.py:99
+    assert picked[torch.tensor([2, 0])].bank_index.tolist() == [3, 3]        # indices compose
+    assert h[1:3].bank_index.tolist() == [1, 2] and picked.to("cpu") is picked and "BankHandle" in repr(picked)
+    for bad in (lambda: picked + 1, lambda: F.normalize(picked, dim=1), lambda: picked.sum(), lambda: picked[:, 0],
+                lambda: picked[0], lambda: torch.cat([picked, picked])):
+        with pytest.raises(NotImplementedError):
+            bad()
