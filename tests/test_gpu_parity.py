@@ -503,3 +503,74 @@ def test_bank_handle_through_the_reference_loop():
     assert d_i.cpu().tolist() == i.cpu().tolist()
     with pytest.raises(ValueError):
         matching_templates(src[:3], tar.to(DEV), None, mask.to(DEV), topk=3)
+
+
+def _fuzz_cases(n, seed):
+    rng = np.random.RandomState(seed)
+    cases = []
+    for i in range(n):
+        H = int(rng.choice([4, 6, 8, 10, 12, 16, 20]))
+        mode = str(rng.choice(["bf16", "fp32", "bf16x3"]))
+        # single-pass bf16 is specified for the reference's feature widths (384 / 1024), where rounding errors average
+        # out below MODE_TOL; narrow features only go through the split modes
+        C = int(rng.choice([64, 72, 128, 200] if mode == "bf16" else [8, 24, 40, 64, 72, 128, 200]))
+        cases.append(dict(B=int(rng.randint(1, 5)), N=int(rng.randint(1, 9)), C=C, H=H,
+                          mode=mode, cluster=int(rng.choice([1, 2])),
+                          mask=str(rng.choice(["disc", "bern", "bern_sparse", "ones", "one_patch", "mixed"])), seed=1000 + i))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(28, 7), ids=lambda c: "B%(B)d-N%(N)d-C%(C)d-H%(H)d-%(mode)s-cl%(cluster)d-%(mask)s" % c)
+def test_matching_fuzz(case):
+    """Seeded sweep over ragged shapes (T = 16 .. 400, K padding, 1 .. 8 views) and mask families, all checked with the
+    same gap-aware comparison as the fixed cases."""
+    B, N, C, H = case["B"], case["N"], case["C"], case["H"]
+    src, tar, _ = synth.planted_match_inputs(B, N, C, H, seed=case["seed"])
+    kind = case["mask"]
+    if kind == "disc":
+        mask = synth.disc_mask(B)
+    elif kind == "bern":
+        mask = synth.bernoulli_mask(B, 224, 0.7, case["seed"])
+    elif kind == "bern_sparse":
+        mask = synth.bernoulli_mask(B, 224, 0.08, case["seed"])
+    elif kind == "ones":
+        mask = torch.ones(B, 224, 224)
+    elif kind == "one_patch":                                       # a single unmasked query patch (not patch 0)
+        mask = torch.zeros(B, 224, 224)
+        step = 224 // H
+        mask[:, (H // 2) * step, (H - 1) * step] = 1.0
+    else:                                                           # per detection: all masked / all ones / disc ...
+        mask = torch.stack([(torch.zeros(224, 224), torch.ones(224, 224), synth.disc_mask(1)[0])[b % 3] for b in range(B)])
+    _check_match(src, tar, mask, min(5, N), case["mode"], case["cluster"])
+
+
+def test_lookup_and_windowed_fuzz():
+    """Seeded sweep of the stage-3 kernels over rectangular-free square maps of odd and even sizes, 1-3 levels, every
+    radius the native path uses, flows from sub-pixel to far outside the map."""
+    from picopose_b200.corr_lookup import corr_lookup
+    from picopose_b200.correlation import windowed_correlation
+    rng = np.random.RandomState(3)
+    for i in range(24):
+        H = int(rng.choice([5, 8, 9, 12, 16, 17, 24, 33]))
+        L = int(rng.randint(1, 4))
+        while (H >> (L - 1)) < 1:
+            L -= 1
+        r = int(rng.randint(1, 5))
+        N = int(rng.randint(1, 4))
+        C = int(rng.choice([4, 32, 64, 96]))
+        sigma = float(rng.choice([0.3, 2.0, 6.0, 50.0]))
+        gen = torch.Generator().manual_seed(200 + i)
+        f1 = torch.randn(N, C, H, H, generator=gen)
+        f2 = torch.randn(N, C, H, H, generator=gen)
+        flow = sigma * torch.randn(N, 2, H, H, generator=gen)
+        flow[0, :, 0, 0] = 0.0
+        if i % 4 == 0:                                              # far outside: every tap in the zero padding
+            flow[0, 0, H // 2, H // 2] = 3e8
+            flow[0, 1, 0, H - 1] = -7e5
+        pyr = OL.correlation_pyramid(f1, f2, L)
+        ref = OL.corr_lookup(pyr, flow, r)
+        out = corr_lookup([p.to(DEV) for p in pyr], flow.to(DEV), r)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5, err_msg=f"lookup case {i}")
+        fused = windowed_correlation(f1.to(DEV), f2.to(DEV), flow.to(DEV), L, r)
+        np.testing.assert_allclose(fused.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5,
+                                   err_msg=f"windowed case {i}: N={N} C={C} H={H} L={L} r={r} sigma={sigma}")
