@@ -3,15 +3,18 @@
 //
 // The per-query kernel pulls every neighbour vector through L1 once per query: 36 KB per query and level at
 // r = 2, C = 256, and a 4-line LDG costs the L1 wavefront queue ~8 cycles, which is what bounds it.  Here a
-// block owns an 8 x 8 tile of queries.  Per level it asks TMA for ONE RS x RS region of the position-major key
-// map, centred on the tile's mean window, 32 channels at a time (4-D box {32, RS, RS, 1}; coordinates may lie
-// outside the map, TMA zero-fills, which is exactly the lookup's zero padding), double buffered behind
-// mbarriers, together with the tile's own 32-channel slice of f1.  A query whose window lies inside the
+// block owns an 8 x 8 tile of queries (a warp a 2 x 2 sub-block).  Per level it asks TMA for ONE square region of
+// the position-major key map, 32 channels at a time (4-D box {32, RS, RS, 1}): RS = 16 placed around all the
+// tile's windows when they fit (smooth flow), else RS = 24 centred on the tile's mean window.  Coordinates may
+// lie outside the map: TMA zero-fills, which is exactly the lookup's zero padding.  Chunks are double buffered
+// behind mbarriers and carry the tile's own 32-channel slice of f1.  A query whose window lies inside the
 // region takes all its dot products from shared memory (conflict-free 128-byte rows, no bounds checks); one
-// that does not (an outlier flow) reads global memory like the per-query kernel, so any flow field works.
-// Accumulators stay in registers across the C/32 chunks: lane group g of a warp owns neighbours g, g+4, ...
-// of each of the warp's 4 queries.  Taps and region origins of every level are computed up front so that the
-// chunk pipeline runs across level boundaries without draining.
+// that does not (an outlier flow, or a window stretched by the float round trip) is deferred to a list and
+// served from global memory after the pipeline, one per warp, so any flow field works and a straggler cannot
+// stall the block.  Accumulators stay in registers across the C/32 chunks: lane group g of a warp owns
+// neighbours g, g+4, ... of each of the warp's 4 queries; at level end one 8-lane transpose-reduce finishes all
+// 36 dot products at once.  Taps and region origins of every level are computed up front so that the chunk
+// pipeline runs across level boundaries without draining.
 #include "pp_common.cuh"
 #include "pp_ptx.cuh"
 
@@ -35,7 +38,8 @@ constexpr long long WT_TIMEOUT_CYCLES = 4000000000LL;
 
 struct WTileMaps {
     CUtensorMap f1;                  // (N, H, W, C) position-major query features
-    CUtensorMap f2[WT_MAX_LEVELS];   // level l: (N, H>>l, W>>l, C)
+    CUtensorMap f2s[WT_MAX_LEVELS];  // level l: (N, H>>l, W>>l, C), small region box
+    CUtensorMap f2b[WT_MAX_LEVELS];  // same tensor, big region box
 };
 
 struct WTileParams {
@@ -82,6 +86,33 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float fma4(const float4& a, const float4& v, float acc) {
+    return fmaf(a.x, v.x, fmaf(a.y, v.y, fmaf(a.z, v.z, fmaf(a.w, v.w, acc))));
+}
+
+// Sums v[i] over the 8 lanes of a lane group for all NV values at once (NV % 8 == 0): three exchange stages,
+// each lane sends the half it does not keep.  Afterwards lane gl holds, in v[0 .. NV/8), the totals of indices
+// (gl & 4 ? NV/2 : 0) + (gl & 2 ? NV/4 : 0) + (gl & 1 ? NV/8 : 0) + j.  7/8 NV shuffles instead of 3 NV.
+template <int NV>
+__device__ __forceinline__ void group8_transpose_reduce(float (&v)[NV], int gl) {
+    static_assert(NV % 8 == 0, "NV must be a multiple of 8");
+    const bool h4 = gl & 4, h2 = gl & 2, h1 = gl & 1;
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) {
+        const float send = h4 ? v[i] : v[i + NV / 2], keep = h4 ? v[i + NV / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+        const float send = h2 ? v[i] : v[i + NV / 4], keep = h2 ? v[i + NV / 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < NV / 8; ++i) {
+        const float send = h1 ? v[i] : v[i + NV / 8], keep = h1 ? v[i + NV / 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+}
 
 template <int R>
 struct WT {
@@ -90,9 +121,9 @@ struct WT {
     static constexpr int TRIPS = W1 * W1 / 4;   // 4 neighbours per trip (W1 is even)
     static constexpr int PER = (W1 % 4 == 0) ? 1 : (W1 % 2 == 0 ? W1 / 2 : W1);   // trips after which (row advance, column) repeats
     static constexpr int ROWS_PER = PER * 4 / W1;
-    static constexpr int RS0 = 8 + W1 + 10;     // region side at level 0: tile + window + slack for the flow's spread
-    static constexpr int RS1 = 4 + 1 + W1 + 6;  // at pooled levels the tile and the spread shrink
-    static constexpr int KEY_WORDS = RS0 * RS0 * WT_CH;
+    static constexpr int RSS = 16;              // small region: fits the windows of a tile whose flow is smooth
+    static constexpr int RSB = 24;              // big region: tile + window + slack for a scattered flow
+    static constexpr int KEY_WORDS = RSB * RSB * WT_CH;
     static constexpr int F1_WORDS = WT_TQ * WT_CH;
     static constexpr uint32_t STAGE_BYTES = (KEY_WORDS + F1_WORDS) * 4;
     static size_t smem_bytes(int L) {
@@ -100,26 +131,30 @@ struct WT {
         w += ((size_t)L * DD * (WT_TQ + 1) + 3) & ~(size_t)3;   // out tile
         w += (size_t)WT_TQ * GG;                                // per-query correlation grid
         w += (size_t)L * WT_TQ * 4 * D;                         // taps of every level
-        w += 4 * WT_MAX_LEVELS + 4;                             // region statistics / origins, barriers
+        w += 8 * WT_MAX_LEVELS + 4;                             // region statistics / origins, barriers
         w += (size_t)WT_MAX_LEVELS * WT_TQ + 4;                 // deferred (level, query) list
         return w * 4 + 128;                                     // + alignment slack
     }
 };
 
-// One 32-channel chunk of the regular in-region queries of a warp: per neighbour one 16-byte shared load and four
-// FMAs; the shared addresses are per-lane bases (set at level start) plus compile-time offsets.
+// query qi of warp `warp`: the warps tile the 8 x 8 block with 2 x 2 sub-blocks
+__device__ __forceinline__ int wt_query(int warp, int qi) { return ((warp >> 2) * 2 + (qi >> 1)) * 8 + (warp & 3) * 2 + (qi & 1); }
+
+// One 32-channel chunk for a warp: every regular in-region query walks its own W1 x W1 grid, a neighbour costs one
+// 16-byte shared load and four FMAs.  Shared addresses are per-lane bases (set at level start) plus compile-time offsets.
 template <int R, int RS, int STAGE>
 __device__ __forceinline__ void wt_chunk(const uint32_t (&base)[WT_QPW][WT<R>::PER], const bool (&fast)[WT_QPW],
                                          float (&acc)[WT_QPW][WT<R>::TRIPS], uint32_t f1_addr) {
     using T = WT<R>;
+    constexpr uint32_t SB = STAGE * T::STAGE_BYTES;
 #pragma unroll
     for (int qi = 0; qi < WT_QPW; ++qi) {
         if (fast[qi]) {  // warp-uniform
-            const float4 a = lds128(f1_addr + STAGE * T::STAGE_BYTES + qi * WT_CH * 4);
+            const float4 a = lds128(f1_addr + SB + ((qi >> 1) * 8 + (qi & 1)) * WT_CH * 4);
 #pragma unroll
             for (int t = 0; t < T::TRIPS; ++t) {
-                const float4 v = lds128(base[qi][t % T::PER] + STAGE * T::STAGE_BYTES + (t / T::PER) * T::ROWS_PER * RS * WT_CH * 4);
-                acc[qi][t] = fmaf(a.x, v.x, fmaf(a.y, v.y, fmaf(a.z, v.z, fmaf(a.w, v.w, acc[qi][t]))));
+                const float4 v = lds128(base[qi][t % T::PER] + SB + (t / T::PER) * T::ROWS_PER * RS * WT_CH * 4);
+                acc[qi][t] = fma4(a, v, acc[qi][t]);
             }
         }
     }
@@ -130,8 +165,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
 windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTileParams p) {
     using T = WT<R>;
     constexpr int D = T::D, DD = T::DD, GG = T::GG, W1 = T::W1, TRIPS = T::TRIPS, PER = T::PER, TQ = WT_TQ, QPW = WT_QPW;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    constexpr int RSS = T::RSS, RSB = T::RSB;
+    extern __shared__ __align__(128) float smem[];  // TMA destinations need 128-byte alignment (checked below)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int grp = lane >> 3, gl = lane & 7;
     const int L = p.L, rows = L * DD;
@@ -142,8 +177,8 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
     int* s_yo = s_xo + L * TQ * D;
     float* s_xw = reinterpret_cast<float*>(s_yo + L * TQ * D);
     float* s_yw = s_xw + L * TQ * D;
-    int* s_red = reinterpret_cast<int*>(s_yw + L * TQ * D);                  // [MAX_LEVELS][4]: sums, count -> origin
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 4 * WT_MAX_LEVELS);
+    int* s_red = reinterpret_cast<int*>(s_yw + L * TQ * D);   // [MAX_LEVELS][8]: sum x, sum y, count, min x, max x, min y, max y
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 8 * WT_MAX_LEVELS);
     int* s_nslow = reinterpret_cast<int*>(s_bar + 2);
     int* s_slow = s_nslow + 4;                                               // [MAX_LEVELS * TQ]
     const uint32_t bar0 = ptx::smem_u32(s_bar), bar1 = bar0 + 8;
@@ -156,21 +191,24 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
     const int n = b / p.tiles_y;
 
     if (tid == 0) {
+        if (stage_u32 & 127u) __trap();
         ptx::mbar_init(bar0, 1);
         ptx::mbar_init(bar1, 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&maps.f1);
-        for (int l = 0; l < L; ++l) ptx::prefetch_tensormap(&maps.f2[l]);
     }
-    if (tid < 4 * WT_MAX_LEVELS) s_red[tid] = 0;
+    if (tid < 8 * WT_MAX_LEVELS) {
+        const int k = tid & 7;
+        s_red[tid] = (k == 3 || k == 5) ? 0x3fffffff : (k == 4 || k == 6) ? -0x3fffffff : 0;
+    }
     if (tid == 32) *s_nslow = 0;
     __syncthreads();
 
-    // ---- taps and window extents of every level; the tile's mean window per level ----
+    // ---- taps and window extents of every level; per level the tile's mean window and the box around all windows ----
     int q_hw[QPW];
 #pragma unroll
     for (int qi = 0; qi < QPW; ++qi) {
-        const int ql = warp * QPW + qi;
+        const int ql = wt_query(warp, qi);
         const int qh = ty * 8 + (ql >> 3), qw = tx * 8 + (ql & 7);
         const bool ok = qh < p.H && qw < p.W;
         q_hw[qi] = ok ? qh * p.W + qw : -1;
@@ -181,33 +219,49 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
         }
         for (int l = 0; l < L; ++l) {
             const float inv = 1.0f / (float)(1 << l);
-            const int base = (l * TQ + ql) * D;
+            const int tb = (l * TQ + ql) * D;
             if (lane < D) {
                 int i0;
                 float w1;
                 wt_axis_tap(__fadd_rn(__fmul_rn(cx, inv), (float)(lane - R)), p.wl[l], i0, w1);
-                s_xo[base + lane] = i0;
-                s_xw[base + lane] = w1;
+                s_xo[tb + lane] = i0;
+                s_xw[tb + lane] = w1;
                 wt_axis_tap(__fadd_rn(__fmul_rn(cy, inv), (float)(lane - R)), p.hl[l], i0, w1);
-                s_yo[base + lane] = i0;
-                s_yw[base + lane] = w1;
+                s_yo[tb + lane] = i0;
+                s_yw[tb + lane] = w1;
             }
             __syncwarp();
             if (lane == 0 && ok) {
-                atomicAdd(&s_red[l * 4 + 0], s_xo[base] + s_xo[base + D - 1] + 2);  // 2 * window centre
-                atomicAdd(&s_red[l * 4 + 1], s_yo[base] + s_yo[base + D - 1] + 2);
-                atomicAdd(&s_red[l * 4 + 2], 1);
+                const int x0 = s_xo[tb], y0 = s_yo[tb];
+                atomicAdd(&s_red[l * 8 + 0], x0 + s_xo[tb + D - 1] + 2);  // 2 * window centre
+                atomicAdd(&s_red[l * 8 + 1], y0 + s_yo[tb + D - 1] + 2);
+                atomicAdd(&s_red[l * 8 + 2], 1);
+                atomicMin(&s_red[l * 8 + 3], x0);
+                atomicMax(&s_red[l * 8 + 4], x0);
+                atomicMin(&s_red[l * 8 + 5], y0);
+                atomicMax(&s_red[l * 8 + 6], y0);
             }
         }
     }
     __syncthreads();
     if (tid < L) {
-        const float cnt = (float)max(s_red[tid * 4 + 2], 1);
-        const float rs = (float)(tid == 0 ? T::RS0 : T::RS1);
-        const int X0 = (int)floorf((float)s_red[tid * 4 + 0] / (2.0f * cnt) - 0.5f * rs + 0.5f);
-        const int Y0 = (int)floorf((float)s_red[tid * 4 + 1] / (2.0f * cnt) - 0.5f * rs + 0.5f);
-        s_red[tid * 4 + 0] = X0;
-        s_red[tid * 4 + 1] = Y0;
+        // small region when one RSS x RSS box holds every window of the tile (centred on them), else the big one
+        // around the mean window (outliers then go to the deferred list)
+        int* r = s_red + tid * 8;
+        const int bw = r[4] - r[3] + W1, bh = r[6] - r[5] + W1;
+        int X0, Y0, small = 0;
+        if (r[2] > 0 && bw <= RSS && bh <= RSS) {
+            small = 1;
+            X0 = r[3] - (RSS - bw) / 2;
+            Y0 = r[5] - (RSS - bh) / 2;
+        } else {
+            const float cnt = (float)max(r[2], 1);
+            X0 = (int)floorf((float)r[0] / (2.0f * cnt) - 0.5f * (float)RSB + 0.5f);
+            Y0 = (int)floorf((float)r[1] / (2.0f * cnt) - 0.5f * (float)RSB + 0.5f);
+        }
+        r[0] = X0;
+        r[1] = Y0;
+        r[2] = small;
     }
     __syncthreads();
 
@@ -215,11 +269,12 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
     const int total = L * nch;
     auto issue = [&](int it) {  // thread 0: TMA of chunk `it` into stage it & 1
         const int l = it / nch, c = it - l * nch;
-        const int rs = l == 0 ? T::RS0 : T::RS1;
+        const int small = s_red[l * 8 + 2];
+        const int rs = small ? RSS : RSB;
         const uint32_t bar = (it & 1) ? bar1 : bar0;
         const uint32_t st = stage_u32 + (uint32_t)(it & 1) * T::STAGE_BYTES;
         ptx::mbar_arrive_expect_tx(bar, (uint32_t)(rs * rs + TQ) * WT_CH * 4);
-        tma_load_4d(&maps.f2[l], bar, st, c * WT_CH, s_red[l * 4 + 0], s_red[l * 4 + 1], n);
+        tma_load_4d(small ? &maps.f2s[l] : &maps.f2b[l], bar, st, c * WT_CH, s_red[l * 8 + 0], s_red[l * 8 + 1], n);
         tma_load_4d(&maps.f1, bar, st + T::KEY_WORDS * 4, c * WT_CH, tx * 8, ty * 8, n);
     };
     if (tid == 0) {
@@ -241,70 +296,80 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
         }
     };
 
-    int xmin[QPW], ymin[QPW], gx[QPW], gy[QPW];
+    int xmin[QPW], ymin[QPW];
     bool fast[QPW];
+    bool small = false;
     uint32_t base[QPW][PER];
-    float acc[QPW][TRIPS];
-    const uint32_t f1_addr = stage_u32 + T::KEY_WORDS * 4 + (uint32_t)(warp * QPW) * WT_CH * 4 + gl * 16;
+    float acc[QPW][T::TRIPS];
+    const uint32_t f1_addr = stage_u32 + T::KEY_WORDS * 4 + (uint32_t)wt_query(warp, 0) * WT_CH * 4 + gl * 16;
     int l = 0, c = 0;
     for (int it = 0; it < total; ++it) {
         if (c == 0) {  // level start: which of this warp's queries have a regular window inside the staged region
-            const int rs = l == 0 ? T::RS0 : T::RS1;
-            const int X0 = s_red[l * 4 + 0], Y0 = s_red[l * 4 + 1];
+            small = s_red[l * 8 + 2] != 0;
+            const int rs = small ? RSS : RSB;
+            const int X0 = s_red[l * 8 + 0], Y0 = s_red[l * 8 + 1];
 #pragma unroll
             for (int qi = 0; qi < QPW; ++qi) {
-                const int tb = (l * TQ + warp * QPW + qi) * D;
+                const int tb = (l * TQ + wt_query(warp, qi)) * D;
                 xmin[qi] = s_xo[tb];
                 ymin[qi] = s_yo[tb];
-                gx[qi] = s_xo[tb + D - 1] + 2 - xmin[qi];
-                gy[qi] = s_yo[tb + D - 1] + 2 - ymin[qi];
+                const int gx = s_xo[tb + D - 1] + 2 - xmin[qi], gy = s_yo[tb + D - 1] + 2 - ymin[qi];
                 // regular (or border-clamped, hence smaller) window whose W1 x W1 grid lies inside the staged region
-                fast[qi] = q_hw[qi] >= 0 && gx[qi] <= W1 && gy[qi] <= W1 && xmin[qi] >= X0 && xmin[qi] + W1 <= X0 + rs &&
+                fast[qi] = q_hw[qi] >= 0 && gx <= W1 && gy <= W1 && xmin[qi] >= X0 && xmin[qi] + W1 <= X0 + rs &&
                            ymin[qi] >= Y0 && ymin[qi] + W1 <= Y0 + rs;
 #pragma unroll
                 for (int j = 0; j < PER; ++j) {
                     const int id = 4 * j + grp, gyi = id / W1, gxi = id % W1;
                     base[qi][j] = stage_u32 + (uint32_t)(((ymin[qi] - Y0 + gyi) * rs + (xmin[qi] - X0 + gxi)) * WT_CH * 4 + gl * 16);
                 }
-#pragma unroll
-                for (int t = 0; t < TRIPS; ++t) acc[qi][t] = 0.f;
             }
+#pragma unroll
+            for (int qi = 0; qi < QPW; ++qi)
+#pragma unroll
+                for (int t = 0; t < T::TRIPS; ++t) acc[qi][t] = 0.f;
         }
         wt_wait((it & 1) ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
-        if (l == 0) {
-            if (it & 1) wt_chunk<R, T::RS0, 1>(base, fast, acc, f1_addr);
-            else wt_chunk<R, T::RS0, 0>(base, fast, acc, f1_addr);
+        if (small) {
+            if (it & 1) wt_chunk<R, RSS, 1>(base, fast, acc, f1_addr);
+            else wt_chunk<R, RSS, 0>(base, fast, acc, f1_addr);
         } else {
-            if (it & 1) wt_chunk<R, T::RS1, 1>(base, fast, acc, f1_addr);
-            else wt_chunk<R, T::RS1, 0>(base, fast, acc, f1_addr);
+            if (it & 1) wt_chunk<R, RSB, 1>(base, fast, acc, f1_addr);
+            else wt_chunk<R, RSB, 0>(base, fast, acc, f1_addr);
         }
         __syncthreads();  // everyone is done with this stage
         if (tid == 0 && it + 2 < total) issue(it + 2);
 
         if (c == nch - 1) {  // level end: finish the dot products, blend the D*D samples of each query
+            {
+                // 4 x 9 partial sums, padded to 4 x 10: lane gl ends up with query gl >> 1, trips (gl & 1) * 5 + j
+                constexpr int TP = (TRIPS + 1) & ~1;
+                float v[QPW * TP];
+#pragma unroll
+                for (int qi = 0; qi < QPW; ++qi)
+#pragma unroll
+                    for (int t = 0; t < TP; ++t) v[qi * TP + t] = t < TRIPS ? acc[qi][t] : 0.f;
+                group8_transpose_reduce<QPW * TP>(v, gl);
+                float* vq = vals + (size_t)wt_query(warp, gl >> 1) * GG;
+#pragma unroll
+                for (int j = 0; j < TP / 2; ++j) {
+                    const int t = (gl & 1) * (TP / 2) + j;
+                    if (t < TRIPS) vq[t * 4 + grp] = v[j] * p.scale;
+                }
+            }
+            __syncwarp();
 #pragma unroll
             for (int qi = 0; qi < QPW; ++qi) {
                 if (q_hw[qi] < 0) continue;  // warp-uniform
-                const int ql = warp * QPW + qi;
+                const int ql = wt_query(warp, qi);
                 if (!fast[qi]) {
                     // stretched window (float round trip) or an outlier flow outside the staged region: deferred, so
                     // that its global-memory latency does not hold up the block's pipeline
                     if (lane == 0) s_slow[atomicAdd(s_nslow, 1)] = (l << 16) | ql;
                     continue;
                 }
-                float* vq = vals + (size_t)ql * GG;
-#pragma unroll
-                for (int t = 0; t < TRIPS; ++t) {
-                    float s = acc[qi][t];
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    if (gl == 0) vq[t * 4 + grp] = s * p.scale;
-                }
-                __syncwarp();
-                blend(l, ql, vq, xmin[qi], ymin[qi], W1);
-                __syncwarp();
+                blend(l, ql, vals + (size_t)ql * GG, xmin[qi], ymin[qi], W1);
             }
+            __syncwarp();
             c = 0;
             ++l;
         } else {
@@ -417,8 +482,8 @@ int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_leve
     WTileParams p{};
     if (int rc = make_map(&maps.f1, f1t, N, H, W, C, 8, 8)) return rc;
     for (int l = 0; l < L; ++l) {
-        const int rs = radius == 1 ? (l == 0 ? WT<1>::RS0 : WT<1>::RS1) : (l == 0 ? WT<2>::RS0 : WT<2>::RS1);
-        if (int rc = make_map(&maps.f2[l], f2t_levels[l], N, H >> l, W >> l, C, rs, rs)) return rc;
+        if (int rc = make_map(&maps.f2s[l], f2t_levels[l], N, H >> l, W >> l, C, WT<2>::RSS, WT<2>::RSS)) return rc;
+        if (int rc = make_map(&maps.f2b[l], f2t_levels[l], N, H >> l, W >> l, C, WT<2>::RSB, WT<2>::RSB)) return rc;
         p.f2t[l] = static_cast<const float*>(f2t_levels[l]);
         p.hl[l] = H >> l;
         p.wl[l] = W >> l;
