@@ -92,10 +92,9 @@ __global__ void __launch_bounds__(256) wcorr_prepare_kernel(const WPrepJobs jobs
     }
 }
 
-// Faster form of the above for L <= 4, C % 4 == 0, W % 4 == 0: a block takes one 8 x 8 patch of positions and 64
-// channels of one sample, reads it ONCE (float4 along x) and writes every level from shared memory (float4
-// along c): feat1 -> level 0 only, feat2 -> levels 0 .. L-1, each level pooled from the one below it like the
-// reference's repeated AvgPool2d(2, 2).
+// Faster form of the above for L <= 4, C % 4 == 0, W % 4 == 0: a block takes one 8 x 32 patch of positions and 32
+// channels of one sample, reads it ONCE and writes every level: feat1 -> level 0 only, feat2 -> levels 0 .. L-1,
+// each level pooled from the one below it like the reference's repeated AvgPool2d(2, 2).
 struct WPatchArgs {
     const float* src[2];            // feat1, feat2 (N, C, H, W)
     float* dst[2][4];               // [which][level]: (N, (H>>l)*(W>>l), C)
@@ -103,62 +102,84 @@ struct WPatchArgs {
     int N, C, H, W, patches_x;
 };
 
+constexpr int WP_COLS = 32, WP_CH = 32;   // patch: 8 rows x 32 columns of positions, 32 channels
+constexpr int WP_PITCH = WP_CH + 4;         // floats per position in shared memory: 16-byte rows, conflict-free both ways
 __global__ void __launch_bounds__(256) wcorr_prepare_patch_kernel(const WPatchArgs a) {
-    __shared__ float t0[64][65];   // [c][8*8 positions]
-    __shared__ float t1[64][17];   // 4*4
-    __shared__ float t2[64][5];    // 2*2
-    __shared__ float t3[64][2];    // 1
-    const int tid = threadIdx.x;
+    // In: warp = patch row, lane = column; per channel one coalesced 128-byte load per warp; a thread collects four
+    // channels of its position and writes them as one 16-byte shared store.  Out: a quarter warp reads the 32
+    // channels of a position as 128 contiguous shared bytes and stores them as one full line.  Pooled levels are
+    // computed from the staged level below.
+    __shared__ __align__(16) float s0[8 * WP_COLS][WP_PITCH];          // level 0: [position][channel]
+    __shared__ __align__(16) float s1[4 * (WP_COLS / 2)][WP_PITCH];    // level 1
+    __shared__ __align__(16) float s2[2 * (WP_COLS / 4)][WP_PITCH];    // level 2
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int which = blockIdx.z / a.N, n = blockIdx.z - which * a.N;
-    const int py0 = (blockIdx.x / a.patches_x) * 8, px0 = (blockIdx.x % a.patches_x) * 8;
-    const int c0 = blockIdx.y * 64;
+    const int py0 = (blockIdx.x / a.patches_x) * 8, px0 = (blockIdx.x % a.patches_x) * WP_COLS;
+    const int c0 = blockIdx.y * WP_CH;
     const int C = a.C, H = a.H, W = a.W;
-    const float* __restrict__ src = a.src[which] + ((size_t)n * C + c0) * H * W;
+    const int L = a.levels[which];
+    const size_t plane = (size_t)H * W;
+    {
+        const int y = py0 + warp, x = px0 + lane;
+        const bool in = y < H && x < W;
+        const float* __restrict__ src = a.src[which] + ((size_t)n * C + c0) * plane + (size_t)y * W + x;
+        float v[WP_CH];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int idx = tid + 256 * j;
-        const int c = idx >> 4, r = (idx >> 1) & 7, half = idx & 1;
-        const int y = py0 + r, x = px0 + half * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + c < C && y < H && x < W) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * H * W + (size_t)y * W + x));
-        float* d = &t0[c][r * 8 + half * 4];
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        for (int k = 0; k < WP_CH; ++k) v[k] = (in && c0 + k < C) ? __ldg(src + k * plane) : 0.f;
+#pragma unroll
+        for (int q = 0; q < WP_CH / 4; ++q)
+            *reinterpret_cast<float4*>(&s0[warp * WP_COLS + lane][q * 4]) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
     __syncthreads();
-    const int L = a.levels[which];
-    if (L > 1) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int idx = tid + 256 * j, c = idx & 63, pp = idx >> 6, py = pp >> 2, px = pp & 3;
-            const float* s0 = &t0[c][(2 * py) * 8 + 2 * px];
-            t1[c][pp] = 0.25f * ((s0[0] + s0[1]) + (s0[8] + s0[9]));
+    const int q = tid & 7, cc = c0 + q * 4;  // this thread's channel quad on the way out
+    for (int pos = tid >> 3; pos < 8 * WP_COLS; pos += 32) {
+        const int y = py0 + pos / WP_COLS, x = px0 + pos % WP_COLS;
+        if (y < H && x < W && cc < C)
+            __stcs(reinterpret_cast<float4*>(a.dst[which][0] + ((size_t)n * plane + (size_t)y * W + x) * C + cc),
+                   *reinterpret_cast<const float4*>(&s0[pos][q * 4]));
+    }
+    if (L <= 1) return;  // block-uniform
+    auto pool4 = [](const float4& q0, const float4& q1, const float4& q2, const float4& q3) {
+        return make_float4(0.25f * ((q0.x + q1.x) + (q2.x + q3.x)), 0.25f * ((q0.y + q1.y) + (q2.y + q3.y)),
+                           0.25f * ((q0.z + q1.z) + (q2.z + q3.z)), 0.25f * ((q0.w + q1.w) + (q2.w + q3.w)));
+    };
+    {   // level 1: 4 x 16 positions
+        const int H1 = H >> 1, W1 = W >> 1;
+        for (int pos = tid >> 3; pos < 4 * (WP_COLS / 2); pos += 32) {
+            const int Y = pos / (WP_COLS / 2), X = pos % (WP_COLS / 2);
+            const int i00 = (2 * Y) * WP_COLS + 2 * X;
+            const float4 o = pool4(*reinterpret_cast<const float4*>(&s0[i00][q * 4]), *reinterpret_cast<const float4*>(&s0[i00 + 1][q * 4]),
+                                   *reinterpret_cast<const float4*>(&s0[i00 + WP_COLS][q * 4]), *reinterpret_cast<const float4*>(&s0[i00 + WP_COLS + 1][q * 4]));
+            *reinterpret_cast<float4*>(&s1[pos][q * 4]) = o;
+            const int gy = (py0 >> 1) + Y, gx = (px0 >> 1) + X;
+            if (gy < H1 && gx < W1 && cc < C)
+                __stcs(reinterpret_cast<float4*>(a.dst[which][1] + ((size_t)n * H1 * W1 + (size_t)gy * W1 + gx) * C + cc), o);
         }
-        __syncthreads();
     }
-    if (L > 2) {
-        const int c = tid & 63, pp = tid >> 6, py = pp >> 1, px = pp & 1;
-        const float* s1 = &t1[c][(2 * py) * 4 + 2 * px];
-        t2[c][pp] = 0.25f * ((s1[0] + s1[1]) + (s1[4] + s1[5]));
-        __syncthreads();
-    }
-    if (L > 3) {
-        if (tid < 64) t3[tid][0] = 0.25f * ((t2[tid][0] + t2[tid][1]) + (t2[tid][2] + t2[tid][3]));
-        __syncthreads();
-    }
-    for (int l = 0; l < L; ++l) {
-        const int side = 8 >> l, npos = side * side;
-        const int Hl = H >> l, Wl = W >> l, Y0 = py0 >> l, X0 = px0 >> l;
-        float* __restrict__ dst = a.dst[which][l] + (size_t)n * Hl * Wl * C + c0;
-        const float* tl = l == 0 ? &t0[0][0] : l == 1 ? &t1[0][0] : l == 2 ? &t2[0][0] : &t3[0][0];
-        const int stride = l == 0 ? 65 : l == 1 ? 17 : l == 2 ? 5 : 2;
-        for (int idx = tid; idx < npos * 16; idx += 256) {
-            const int pos = idx >> 4, c4 = (idx & 15) * 4;
-            const int y = Y0 + pos / side, x = X0 + pos % side;
-            if (y < Hl && x < Wl && c0 + c4 < C) {
-                const float* tc = tl + (size_t)c4 * stride + pos;
-                *reinterpret_cast<float4*>(dst + ((size_t)y * Wl + x) * C + c4) = make_float4(tc[0], tc[stride], tc[2 * stride], tc[3 * stride]);
-            }
+    if (L <= 2) return;
+    __syncthreads();
+    {   // level 2: 2 x 8 positions
+        const int H2 = H >> 2, W2 = W >> 2;
+        for (int pos = tid >> 3; pos < 2 * (WP_COLS / 4); pos += 32) {
+            const int Y = pos / (WP_COLS / 4), X = pos % (WP_COLS / 4);
+            const int i00 = (2 * Y) * (WP_COLS / 2) + 2 * X;
+            const float4 o = pool4(*reinterpret_cast<const float4*>(&s1[i00][q * 4]), *reinterpret_cast<const float4*>(&s1[i00 + 1][q * 4]),
+                                   *reinterpret_cast<const float4*>(&s1[i00 + WP_COLS / 2][q * 4]), *reinterpret_cast<const float4*>(&s1[i00 + WP_COLS / 2 + 1][q * 4]));
+            *reinterpret_cast<float4*>(&s2[pos][q * 4]) = o;
+            const int gy = (py0 >> 2) + Y, gx = (px0 >> 2) + X;
+            if (gy < H2 && gx < W2 && cc < C)
+                __stcs(reinterpret_cast<float4*>(a.dst[which][2] + ((size_t)n * H2 * W2 + (size_t)gy * W2 + gx) * C + cc), o);
         }
+    }
+    if (L <= 3) return;
+    __syncthreads();
+    if (tid < 8 * (WP_COLS / 8)) {  // level 3: 1 x 4 positions
+        const int H3 = H >> 3, W3 = W >> 3, X = tid >> 3;
+        const float4 o = pool4(*reinterpret_cast<const float4*>(&s2[2 * X][q * 4]), *reinterpret_cast<const float4*>(&s2[2 * X + 1][q * 4]),
+                               *reinterpret_cast<const float4*>(&s2[WP_COLS / 4 + 2 * X][q * 4]), *reinterpret_cast<const float4*>(&s2[WP_COLS / 4 + 2 * X + 1][q * 4]));
+        const int gy = py0 >> 3, gx = (px0 >> 3) + X;
+        if (gy < H3 && gx < W3 && cc < C)
+            __stcs(reinterpret_cast<float4*>(a.dst[which][3] + ((size_t)n * H3 * W3 + (size_t)gy * W3 + gx) * C + cc), o);
     }
 }
 
@@ -359,8 +380,8 @@ extern "C" int pp_windowed_correlation_prepare_all(const float* feat1, const flo
             a.C = C;
             a.H = H;
             a.W = W;
-            a.patches_x = (W + 7) / 8;
-            dim3 grid(a.patches_x * ((H + 7) / 8), (C + 63) / 64, 2 * N);
+            a.patches_x = (W + WP_COLS - 1) / WP_COLS;
+            dim3 grid(a.patches_x * ((H + 7) / 8), (C + WP_CH - 1) / WP_CH, 2 * N);
             wcorr_prepare_patch_kernel<<<grid, 256, 0, st>>>(a);
             PP_LAUNCHED();
             return PP_OK;
