@@ -135,6 +135,17 @@ PP_API int pp_match_templates(const float* tar_feat, const float* tar_mask, cons
                        int mode, int k, float* out_score, int64_t* out_idx, float* sim_avg_out,
                        void* workspace, size_t workspace_bytes, int cluster, void* stream);
 
+/* matching_templates exactly as the reference calls it (utils/matching.py:29-69, from model/picopose.py:102): dense
+ * fp32 template features in, prepared on the way.  src_feats (G, N, C, H, W) with G == B (one bank per detection)
+ * or any G with bank_of_det (B,) (NULL: detection b uses bank b).  The bank prologue (pp_match_prepare) and the
+ * query prologue (pp_match_prepare_query) are independent, so they run concurrently on a forked internal stream
+ * that joins `stream` before the contraction.  bank_prep (G, N, H*W, Kp) bf16 and bank_rnorm (G, N, H*W) fp32 are
+ * caller-provided outputs (reusable with pp_match_templates afterwards); workspace as pp_match_templates. */
+PP_API int pp_match_templates_dense(const float* src_feats, int64_t G, const float* tar_feat, const float* tar_mask,
+                             const int32_t* bank_of_det, int B, int N, int C, int H, int W, int Hm, int Wm, int mode,
+                             int k, void* bank_prep, float* bank_rnorm, float* out_score, int64_t* out_idx,
+                             float* sim_avg_out, void* workspace, size_t workspace_bytes, int cluster, void* stream);
+
 /* Multi-GPU merge of sharded template banks: pp_topk_pairs writes each rank's local top-k as (score, global index)
  * pairs of doubles, (B, k, 2), padded with (-inf, -1) when the shard holds fewer than k views -- one tensor to
  * all-gather; pp_topk_merge reduces the gathered (R, B, k_in, 2) lists to the global top-k of every row

@@ -37,6 +37,8 @@ SIGNATURES = {
     "pp_match_templates_workspace": (_sz, [_i, _i, _i, _i, _i, _i]),
     "pp_match_templates": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz,
                                 _i, _vp]),
+    "pp_match_templates_dense": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _sz, _i, _vp]),
     "pp_topk_pairs": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp]),
     "pp_topk_merge": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_match_similarity_workspace": (_sz, [_i, _i]),

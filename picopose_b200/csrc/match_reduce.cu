@@ -2,6 +2,8 @@
 // and the stage-2 similarity-volume layout pass.  (Reference: utils/matching.py:16-17,38-39,54-68,23-25.)
 #include "pp_common.cuh"
 
+#include <cstdlib>
+
 namespace pp {
 
 int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n_banks, const int32_t* bank_of_det,
@@ -438,6 +440,71 @@ extern "C" int pp_match_templates(const float* tar_feat, const float* tar_mask, 
     const bool rank_it = k > 0 && out_score && out_idx;
     return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
                              n_banks, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
+                             rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
+                             stream);
+}
+
+namespace pp {
+// one forked stream + fork/join events per device, created on first use
+struct ForkJoin {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static ForkJoin g_fj[64];
+static int fork_join_for_current_device(ForkJoin** out) {
+    int dev = 0;
+    PP_CUDA(cudaGetDevice(&dev));
+    PP_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    ForkJoin& f = g_fj[dev];
+    if (!f.side) {
+        PP_CUDA(cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking));
+        PP_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+        PP_CUDA(cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming));
+    }
+    *out = &f;
+    return PP_OK;
+}
+}  // namespace pp
+
+extern "C" int pp_match_templates_dense(const float* src_feats, int64_t G, const float* tar_feat, const float* tar_mask,
+                                        const int32_t* bank_of_det, int B, int N, int C, int H, int W, int Hm, int Wm,
+                                        int mode, int k, void* bank_prep, float* bank_rnorm, float* out_score,
+                                        int64_t* out_idx, float* sim_avg_out, void* workspace, size_t workspace_bytes,
+                                        int cluster, void* stream) {
+    using namespace pp;
+    if (B == 0) return PP_OK;
+    const int Kp = pp_match_kp(C, mode);
+    PP_CHECK_ARG(Kp > 0, "pp_match_templates_dense: bad feature dim %d / mode %d", C, mode);
+    PP_CHECK_ARG(src_feats && bank_prep && bank_rnorm && G > 0, "pp_match_templates_dense: null pointer / no banks");
+    PP_CHECK_ARG(bank_of_det || G == B, "pp_match_templates_dense: %lld banks for %d detections need bank_of_det", (long long)G, B);
+    PP_CHECK_ARG(k >= 0 && k <= N, "pp_match_templates_dense: selected index k out of range (k=%d, N=%d)", k, N);
+    const int T = H * W;
+    const MatchWs w = match_templates_layout(B, N, T, Kp);
+    if (!workspace || workspace_bytes < w.total)
+        return fail(PP_ERR_WORKSPACE, "pp_match_templates_dense: workspace of %zu bytes needed, %zu given", w.total,
+                    workspace_bytes);
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_templates_dense: workspace must be 256-byte aligned");
+    char* ws = static_cast<char*>(workspace);
+    float* sim_avg = sim_avg_out ? sim_avg_out : reinterpret_cast<float*>(ws + w.sim_avg);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ForkJoin* fj = nullptr;
+    if (int rc = fork_join_for_current_device(&fj)) return rc;
+    // fork: the (small, latency-bound) query prologue runs beside the (large, bandwidth-bound) bank prologue
+    PP_CUDA(cudaEventRecord(fj->fork, st));
+    PP_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+    const int rc = pp_match_prepare_query(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
+                                          reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, fj->side);
+    const int rc2 = pp_match_prepare(src_feats, G * N, C, T, mode, 0, bank_prep, bank_rnorm, stream);
+    // join unconditionally so that the side stream never outlives the call's ordering on `stream`
+    const cudaError_t e1 = cudaEventRecord(fj->join, fj->side);
+    const cudaError_t e2 = cudaStreamWaitEvent(st, fj->join, 0);
+    if (rc) return rc;
+    if (rc2) return rc2;
+    PP_CUDA(e1);
+    PP_CUDA(e2);
+    const bool rank_it = k > 0 && out_score && out_idx;
+    return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
+                             G, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
                              rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
                              stream);
 }

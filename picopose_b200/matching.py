@@ -181,6 +181,51 @@ def _match_one_call(bank, tar_feat, tar_mask, bank_index, k, cluster, want_sim):
     return score, idx, sim
 
 
+def _match_dense_call(src_feats, tar_feat, tar_mask, mode, k, cluster, want_sim):
+    """matching_templates on dense fp32 template features in ONE library call (bank prologue and query prologue run
+    concurrently inside it).  None if the shapes need the chunked path."""
+    lib = _lib.load()
+    B, Cc, H, W = tar_feat.shape
+    G, N = src_feats.shape[0], src_feats.shape[1]
+    T = H * W
+    mode = default_mode() if mode is None else mode
+    mid = _mode_id(mode)
+    need = lib.pp_match_templates_workspace(B, N, Cc, H, W, mid)
+    if B > _MAX_DETS_PER_LAUNCH or lib.pp_match_scores_workspace(B, N, T) > _WORKSPACE_LIMIT or G * N > 65535:
+        return None
+    dev = tar_feat.device
+    src, feat, mask = _as_f32(src_feats), _as_f32(tar_feat), _as_f32(tar_mask)
+    kp = lib.pp_match_kp(Cc, mid)
+    prep = torch.empty(G, N, T, kp, dtype=torch.bfloat16, device=dev)
+    rnorm = torch.empty(G, N, T, dtype=torch.float32, device=dev)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    score = torch.empty(B, k, dtype=torch.float32, device=dev) if k else None
+    idx = torch.empty(B, k, dtype=torch.int64, device=dev) if k else None
+    sim = torch.empty(B, N, dtype=torch.float32, device=dev) if want_sim else None
+    bank_of_det = torch.zeros(B, dtype=torch.int32, device=dev) if (G == 1 and B > 1) else None
+    cl = default_cluster() if cluster is None else cluster
+    with _on_device(dev):
+        _lib.check(lib.pp_match_templates_dense(
+            src.data_ptr(), G, feat.data_ptr(), mask.data_ptr(), _lib.ptr(bank_of_det), B, N, Cc, H, W, mask.shape[-2],
+            mask.shape[-1], mid, k, prep.data_ptr(), rnorm.data_ptr(), _lib.ptr(score), _lib.ptr(idx), _lib.ptr(sim),
+            ws.data_ptr(), need, cl, _lib.stream_of(tar_feat)), "pp_match_templates_dense")
+    return score, idx, sim
+
+
+def _dense_features(src_feats, tar_feat):
+    """The reference's own call shape: a plain (B | 1-expanded, N, C, H, W) tensor on the query's device -> the tensor
+    to prepare ((1, ...) for a stride-0 batch view), else None (banks, handles and odd shapes take the general path)."""
+    from .serving import BankHandle
+    if not isinstance(src_feats, torch.Tensor) or isinstance(src_feats, BankHandle) or src_feats.dim() != 5:
+        return None
+    B, Cc, H, W = tar_feat.shape
+    if src_feats.device != tar_feat.device or tuple(src_feats.shape[2:]) != (Cc, H, W) or H != W:
+        return None
+    if src_feats.shape[0] > 1 and src_feats.stride(0) == 0:
+        return src_feats[:1]
+    return src_feats if src_feats.shape[0] == B else None
+
+
 def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *, mode: Optional[str] = None,
                     bank_index: Optional[torch.Tensor] = None, want_indices: bool = False,
                     want_mutual: bool = False, cluster: Optional[int] = None):
@@ -276,6 +321,13 @@ def matching_templates(src_feats, tar_feat, src_masks, tar_mask, topk=5, *, mode
     be a TemplateBank (pre-normalised once per object) with `bank_index` mapping detections to banks.
     """
     _lib.require_cuda(tar_feat, tar_mask)
+    dense = _dense_features(src_feats, tar_feat) if bank_index is None else None
+    if dense is not None:
+        if topk > dense.shape[1]:
+            raise RuntimeError(f"selected index k out of range (k={topk}, N={dense.shape[1]})")
+        out = _match_dense_call(dense, tar_feat, tar_mask, mode, topk, None, False)
+        if out is not None:
+            return out[0], out[1]
     bank, auto_index = _resolve_bank(src_feats, mode, tar_feat.shape[0])
     bank_index = _check_bank(bank, auto_index if bank_index is None else bank_index, tar_feat)
     if topk > bank.n_views:
