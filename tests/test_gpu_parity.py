@@ -574,3 +574,23 @@ def test_lookup_and_windowed_fuzz():
         fused = windowed_correlation(f1.to(DEV), f2.to(DEV), flow.to(DEV), L, r)
         np.testing.assert_allclose(fused.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5,
                                    err_msg=f"windowed case {i}: N={N} C={C} H={H} L={L} r={r} sigma={sigma}")
+
+
+def test_matching_templates_dense_call_paths(monkeypatch):
+    """matching_templates on dense features (one library call, concurrent prologues), on a stride-0 expanded bank,
+    through a prepared TemplateBank and through the chunked fallback all return the same ranking and scores."""
+    from picopose_b200 import matching as M
+    banks, tar, obj, top1 = synth.shared_bank_inputs(1, 9, 64, 8, B=4, seed=6)
+    mask = synth.disc_mask(4).to(DEV)
+    tar_d = tar.to(DEV)
+    dense = banks[:1].repeat(4, 1, 1, 1, 1).to(DEV)
+    s0, i0 = M.matching_templates(dense, tar_d, None, mask, topk=3)
+    s1, i1 = M.matching_templates(banks[:1].to(DEV).expand(4, -1, -1, -1, -1), tar_d, None, mask, topk=3)
+    bank = M.TemplateBank.from_features(banks[:1].to(DEV))
+    s2, i2 = M.matching_templates(bank, tar_d, None, mask, topk=3, bank_index=torch.zeros(4, dtype=torch.int32, device=DEV))
+    monkeypatch.setattr(M, "_WORKSPACE_LIMIT", 1)                    # no one-call path: prepare + chunked scores + topk
+    s3, i3 = M.matching_templates(dense, tar_d, None, mask, topk=3)
+    for s, i in ((s1, i1), (s2, i2), (s3, i3)):
+        assert torch.equal(i0, i) and torch.equal(s0, s)
+    assert i0[:, 0].cpu().tolist() == top1.tolist()
+    _lib.check_device_faults()
