@@ -181,7 +181,7 @@ def _match_one_call(bank, tar_feat, tar_mask, bank_index, k, cluster, want_sim):
     return score, idx, sim
 
 
-def _match_dense_call(src_feats, tar_feat, tar_mask, mode, k, cluster, want_sim):
+def _match_dense_call(src_feats, tar_feat, tar_mask, mode, k, cluster, want_sim, bank_index=None):
     """matching_templates on dense fp32 template features in ONE library call (bank prologue and query prologue run
     concurrently inside it).  None if the shapes need the chunked path."""
     lib = _lib.load()
@@ -202,7 +202,12 @@ def _match_dense_call(src_feats, tar_feat, tar_mask, mode, k, cluster, want_sim)
     score = torch.empty(B, k, dtype=torch.float32, device=dev) if k else None
     idx = torch.empty(B, k, dtype=torch.int64, device=dev) if k else None
     sim = torch.empty(B, N, dtype=torch.float32, device=dev) if want_sim else None
-    bank_of_det = torch.zeros(B, dtype=torch.int32, device=dev) if (G == 1 and B > 1) else None
+    if bank_index is not None:
+        if bank_index.numel() != B:
+            raise ValueError(f"bank_index names {bank_index.numel()} banks for {B} detections")
+        bank_of_det = bank_index.to(device=dev, dtype=torch.int32).contiguous()
+    else:
+        bank_of_det = torch.zeros(B, dtype=torch.int32, device=dev) if (G == 1 and B > 1) else None
     cl = default_cluster() if cluster is None else cluster
     with _on_device(dev):
         _lib.check(lib.pp_match_templates_dense(
@@ -212,15 +217,18 @@ def _match_dense_call(src_feats, tar_feat, tar_mask, mode, k, cluster, want_sim)
     return score, idx, sim
 
 
-def _dense_features(src_feats, tar_feat):
-    """The reference's own call shape: a plain (B | 1-expanded, N, C, H, W) tensor on the query's device -> the tensor
-    to prepare ((1, ...) for a stride-0 batch view), else None (banks, handles and odd shapes take the general path)."""
+def _dense_features(src_feats, tar_feat, bank_index=None):
+    """The reference's own call shape: a plain (B | 1-expanded, N, C, H, W) tensor on the query's device (any number of
+    banks when `bank_index` maps detections to them) -> the tensor to prepare ((1, ...) for a stride-0 batch view),
+    else None (banks, handles and odd shapes take the general path)."""
     from .serving import BankHandle
     if not isinstance(src_feats, torch.Tensor) or isinstance(src_feats, BankHandle) or src_feats.dim() != 5:
         return None
     B, Cc, H, W = tar_feat.shape
     if src_feats.device != tar_feat.device or tuple(src_feats.shape[2:]) != (Cc, H, W) or H != W:
         return None
+    if bank_index is not None:
+        return src_feats if src_feats.stride(0) != 0 else None
     if src_feats.shape[0] > 1 and src_feats.stride(0) == 0:
         return src_feats[:1]
     return src_feats if src_feats.shape[0] == B else None
@@ -240,6 +248,12 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
     _lib.require_cuda(tar_feat, tar_mask)
     lib = _lib.load()
     B, Cc, H, W = tar_feat.shape
+    if not want_indices and not want_mutual:
+        dense = _dense_features(src_feats, tar_feat, bank_index)
+        if dense is not None:
+            out = _match_dense_call(dense, tar_feat, tar_mask, mode, 0, cluster, True, bank_index)
+            if out is not None:
+                return out[2]
     bank, auto_index = _resolve_bank(src_feats, mode, B)
     bank_index = _check_bank(bank, auto_index if bank_index is None else bank_index, tar_feat)
     if not want_indices and not want_mutual:
@@ -321,11 +335,11 @@ def matching_templates(src_feats, tar_feat, src_masks, tar_mask, topk=5, *, mode
     be a TemplateBank (pre-normalised once per object) with `bank_index` mapping detections to banks.
     """
     _lib.require_cuda(tar_feat, tar_mask)
-    dense = _dense_features(src_feats, tar_feat) if bank_index is None else None
+    dense = _dense_features(src_feats, tar_feat, bank_index)
     if dense is not None:
         if topk > dense.shape[1]:
             raise RuntimeError(f"selected index k out of range (k={topk}, N={dense.shape[1]})")
-        out = _match_dense_call(dense, tar_feat, tar_mask, mode, topk, None, False)
+        out = _match_dense_call(dense, tar_feat, tar_mask, mode, topk, None, False, bank_index)
         if out is not None:
             return out[0], out[1]
     bank, auto_index = _resolve_bank(src_feats, mode, tar_feat.shape[0])
