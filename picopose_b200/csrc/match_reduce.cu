@@ -450,7 +450,7 @@ struct ForkJoin {
     cudaStream_t side = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-static ForkJoin g_fj[64];
+static thread_local ForkJoin g_fj[64];  // per host thread: concurrent callers never share the side stream or its events
 static int fork_join_for_current_device(ForkJoin** out) {
     int dev = 0;
     PP_CUDA(cudaGetDevice(&dev));
