@@ -6,8 +6,8 @@ set -x
 cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 600 python bench.py > gpurun_out/bench_r1q.json 2> gpurun_out/bench_r1q.err; tail -c 3000 gpurun_out/bench_r1q.json
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r1q.json 2> gpurun_out/bench_ref_r1q.err; tail -c 1500 gpurun_out/bench_ref_r1q.json
-timeout 300 python tools/bench_lookup.py --json gpurun_out/lookup_sweep_r1q.json 2>&1 | tail -6
-timeout 300 python bench.py --steps 2 --warmup 3 > /dev/null 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1q.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -s 28 -c 7 -o gpurun_out/prof_step_r1q -f python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
+timeout 600 python bench.py > gpurun_out/bench_${TAG:-final}.json 2> gpurun_out/bench_${TAG:-final}.err; tail -c 3000 gpurun_out/bench_${TAG:-final}.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${TAG:-final}.json 2> gpurun_out/bench_ref_${TAG:-final}.err; tail -c 1500 gpurun_out/bench_ref_${TAG:-final}.json
+timeout 300 python tools/bench_lookup.py --json gpurun_out/lookup_sweep_${TAG:-final}.json 2>&1 | tail -6
+timeout 300 python bench.py --steps 2 --warmup 3 > /dev/null 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG:-final}.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -s 28 -c 7 -o gpurun_out/prof_step_${TAG:-final} -f python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
