@@ -180,7 +180,8 @@ def run_ours(args):
     tar_d, mask_d = tar_h.to(dev), mask_h.to(dev)
     look_d = [([p.to(dev) for p in pyr], flow.to(dev)) for pyr, flow in lookups]
     lookup_mod = CorrLookup(radius=CFG["radius"])
-    matcher = ShardedMatcher(CFG["N"], None)
+    # second communicator for the query exchange of the end-to-end loop (overlaps the previous step's kernels)
+    matcher = ShardedMatcher(CFG["N"], None, query_group=dist.new_group() if world > 1 else None)
     bank_index = torch.arange(world, dtype=torch.int32, device=dev)
     k = CFG["topk"]
 

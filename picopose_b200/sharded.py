@@ -82,8 +82,11 @@ def merge_topk(local_pairs: torch.Tensor, k: int, group=None, merge: Optional[Ca
 class ShardedMatcher:
     """Template-sharded `matching_templates` over a process group."""
 
-    def __init__(self, n_views: int, group=None, merge: Optional[Callable] = None):
+    def __init__(self, n_views: int, group=None, merge: Optional[Callable] = None, query_group=None):
         self.group = group
+        # gather_queries on its own communicator: collectives of one NCCL communicator run in issue order on one
+        # internal stream, so a query gather for step i+1 would otherwise queue behind step i's top-k exchange
+        self.query_group = query_group if query_group is not None else group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.n_views = n_views
@@ -109,8 +112,8 @@ class ShardedMatcher:
         if out is None:
             out = (tar_local.new_empty((self.world * tar_local.shape[0],) + tuple(tar_local.shape[1:])),
                    mask_local.new_empty((self.world * mask_local.shape[0],) + tuple(mask_local.shape[1:])))
-        dist.all_gather_into_tensor(out[0], tar_local, group=self.group)
-        dist.all_gather_into_tensor(out[1], mask_local, group=self.group)
+        dist.all_gather_into_tensor(out[0], tar_local, group=self.query_group)
+        dist.all_gather_into_tensor(out[1], mask_local, group=self.query_group)
         return out
 
     def match(self, src, tar_feat, tar_mask, topk=5, bank_index=None, mode=None):
