@@ -1,5 +1,5 @@
 """Stage-by-stage bring-up of the CUDA kernels on a GPU box, each stage in its own process so that a
-trapped kernel cannot poison the next stage.   python tools/gpu_debug.py [stage ...]"""
+trapped kernel cannot poison the next stage (test infrastructure: uses the oracle as checker).   python tests/gpu_debug.py [stage ...]"""
 import os
 import subprocess
 import sys
