@@ -136,10 +136,13 @@ def make_inputs(world, rank, seed=0):
 
 
 def executed_rows(mask, H):
-    """Query rows the contraction really processes: unmasked patches, rounded up to the 256-row CTA-pair tile."""
+    """Query rows the contraction really processes: the unmasked patches of a detection are cut into ceil(tv/256)
+    column tiles of round_up(tv / tiles, 32) accumulator columns (match_gemm.cu, EPI_MATCH)."""
     m = torch.nn.functional.interpolate(mask.unsqueeze(1).float(), size=(H, H))       # nearest, as the reference
     tv = (m.reshape(mask.shape[0], -1) != 0).sum(dim=1)
-    return int(((tv + 255) // 256 * 256).sum()), int(tv.sum())
+    tiles = (tv + 255) // 256
+    per_tile = torch.where(tiles > 0, ((tv + tiles.clamp(min=1) - 1) // tiles.clamp(min=1) + 31) // 32 * 32, tiles)
+    return int((tiles * per_tile).sum()), int(tv.sum())
 
 
 def algorithmic_counts(world, lo, hi):
@@ -369,8 +372,10 @@ def run_ours(args):
                                    "clocks) and the sustained figure (%s TFLOP/s, frac_vs_sustained_peak) is the fair one"
                                    % (args.steps, ms_total, "%.1f" % sustained_tf if sustained_tf else "n/a"),
                          "note": "achieved = MMA FLOPs issued / kernel time: 2*N*S*C per unmasked query row, rows padded to "
-                                 "the 256-row CTA-pair tile (%d of %d query rows unmasked; masked patches are rows of "
-                                 "zeros in the reference and never reach the tensor cores). algorithmic_* uses the dense "
+                                 "ceil(tv/256) column tiles of a multiple of 32 (%d of %d query rows unmasked; masked "
+                                 "patches are rows of zeros in the reference and never reach the tensor cores; the "
+                                 "template-patch side S is padded to the 256-row CTA-pair tile, exact at 32x32). "
+                                 "algorithmic_* uses the dense "
                                  "SURVEY 8(d) formula 2*B*N*T*S*C and may exceed the peak for that reason"
                                  % (rows_unmasked, world * CFG["H"] ** 2)},
             "warm_bank": {"value": world * 1e3 / (warm_ms_total / args.steps), "unit": "detections/s",

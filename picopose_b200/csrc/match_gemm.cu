@@ -12,10 +12,16 @@
 //   warp 1     MMA issuer  : tcgen05.mma kind::f16, M = 128*CL, N = 256, K = 16 per instruction,
 //                            accumulators double-buffered in TMEM (2 x 256 columns)
 //   warp 2     TMEM allocator
-//   warps 4-19 epilogue    : tcgen05.ld 32x32b -> registers; warp w reads lane quarter w%4,
-//                            64-column slice (w-4)/4 of the 128 x 256 accumulator
+//   warps 4-19 epilogue    : tcgen05.ld 32x32b -> registers; warp w reads lane quarter w%4 and the
+//                            32-column chunks (w-4)/4, (w-4)/4 + 4 of the accumulator
 // CL = 2 pairs two SMs (cta_group::2): each CTA loads its own 128 A rows and half of the B tile, the
 // leader issues M=256 MMAs, commits are multicast to both CTAs.
+//
+// Operand roles.  EPI_MATCH puts the TEMPLATE patches on the M side (A operand, TMEM lanes) and the compact
+// query rows on the N side (B operand, TMEM columns): UMMA M is fixed at 128 per CTA but N may be any multiple
+// of 16, so a detection with tv unmasked patches is cut into ceil(tv/256) column tiles of
+// round_up(tv / tiles, 32) columns and (almost) no padding rows are multiplied -- 655 live patches cost
+// 3 x 224 columns instead of 3 x 256 rows.  EPI_EMIT keeps the query on the M side (its rows are not compacted).
 #include "pp_common.cuh"
 #include "pp_ptx.cuh"
 
@@ -65,7 +71,7 @@ struct GemmCfg {
     static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int RB_BYTES = NUM_EPI_WARPS * EPI_COLS * 4;  // per epilogue warp: inverse norms of its columns
+    static constexpr int RB_BYTES = NUM_EPI_WARPS * EPI_COLS * 8;  // per epilogue warp: factor + patch index of its columns
     static constexpr int PREFIX_BYTES = (MAX_DETS_PER_LAUNCH + 1) * 4;  // per-detection tile prefix (compacted rows)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + PREFIX_BYTES + 1024;  // + alignment slack
 };
@@ -93,6 +99,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fa
 
 struct TileCoord {
     int b, n, nt, mt;
+    int ncols;  // EPI_MATCH: accumulator columns of this tile (UMMA N), a multiple of 32
+    int rows;   // EPI_MATCH: live compact query rows of detection b
 };
 __device__ __forceinline__ TileCoord decode_tile(uint32_t tile, const GemmParams& p) {
     TileCoord c;
@@ -103,11 +111,17 @@ __device__ __forceinline__ TileCoord decode_tile(uint32_t tile, const GemmParams
     const uint32_t b = r2 / (uint32_t)p.N;
     c.n = (int)(r2 - b * (uint32_t)p.N);
     c.b = (int)b;
+    c.ncols = BLOCK_N;
+    c.rows = p.T;
     return c;
 }
 
-// Compacted query rows: detection b owns N * num_nt * ceil(tv[b] / rows_per_tile) tiles; prefix[] (shared memory)
-// holds the running tile count, a binary search maps a flat tile index back to its detection.
+// EPI_MATCH: detection b owns N * num_mt * ceil(tv[b] / 256) tiles (template-patch tiles x query-column tiles);
+// prefix[] (shared memory) holds the running tile count, a binary search maps a flat tile index back to its
+// detection.  Column tiles of one (view, patch tile) are neighbours in the flat order, so the clusters that run
+// them at the same time read the same template rows (L2 hits).
+__device__ __forceinline__ int live_rows(const GemmParams& p, int b) { return p.tv ? __ldg(p.tv + b) : p.T; }
+__device__ __forceinline__ uint32_t col_tiles(int rows) { return (uint32_t)((rows + BLOCK_N - 1) / BLOCK_N); }
 __device__ __forceinline__ TileCoord decode_tile_prefix(uint32_t tile, const GemmParams& p, const uint32_t* prefix) {
     int lo = 0, hi = p.B;
     while (hi - lo > 1) {
@@ -116,12 +130,14 @@ __device__ __forceinline__ TileCoord decode_tile_prefix(uint32_t tile, const Gem
     }
     TileCoord c;
     c.b = lo;
+    c.rows = live_rows(p, lo);
+    const uint32_t nct = col_tiles(c.rows);
+    c.ncols = (int)((((uint32_t)c.rows + nct - 1) / nct + 31u) & ~31u);
     const uint32_t local = tile - prefix[lo];
-    const uint32_t nmt = (prefix[lo + 1] - prefix[lo]) / (uint32_t)(p.N * p.num_nt);
-    const uint32_t r = local / nmt;
-    c.mt = (int)(local - r * nmt);
-    const uint32_t n = r / (uint32_t)p.num_nt;
-    c.nt = (int)(r - n * (uint32_t)p.num_nt);
+    const uint32_t r = local / nct;
+    c.nt = (int)(local - r * nct);
+    const uint32_t n = r / (uint32_t)p.num_mt;
+    c.mt = (int)(r - n * (uint32_t)p.num_mt);
     c.n = (int)n;
     return c;
 }
@@ -146,7 +162,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
     float* rb_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
     uint32_t* tile_prefix = reinterpret_cast<uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::RB_BYTES);
-    const bool compact = EPI == EPI_MATCH && p.tv != nullptr;
+    constexpr bool MATCH = EPI == EPI_MATCH;  // template patches on the M side, compact query rows on the N side
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -173,14 +189,14 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::fence_barrier_init();
     } else if (warp == 2) {
         ptx::tmem_alloc<CL>(ptx::smem_u32((const void*)tmem_slot), 512);
-    } else if (warp == 3 && compact) {
+    } else if (warp == 3 && MATCH) {
         // inclusive scan of the per-detection tile counts (B <= MAX_DETS_PER_LAUNCH), 32 detections per step
         uint32_t run = 0;
         if (lane == 0) tile_prefix[0] = 0;
         for (int b0 = 0; b0 < p.B; b0 += 32) {
             const int b = b0 + lane;
             uint32_t cnt = 0;
-            if (b < p.B) cnt = (uint32_t)((__ldg(p.tv + b) + BLOCK_M * CL - 1) / (BLOCK_M * CL)) * (uint32_t)(p.N * p.num_nt);
+            if (b < p.B) cnt = col_tiles(live_rows(p, b)) * (uint32_t)(p.N * p.num_mt);
             uint32_t inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -195,8 +211,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (CL > 1) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t total_tiles = compact ? tile_prefix[p.B] : p.total_tiles;
-    auto decode = [&](uint32_t tile) { return compact ? decode_tile_prefix(tile, p, tile_prefix) : decode_tile(tile, p); };
+    const uint32_t total_tiles = MATCH ? tile_prefix[p.B] : p.total_tiles;
+    auto decode = [&](uint32_t tile) { return MATCH ? decode_tile_prefix(tile, p, tile_prefix) : decode_tile(tile, p); };
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA) =====================
@@ -207,9 +223,13 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters) {
             const TileCoord tc = decode(tile);
             const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
-            const int a_row = tc.b * p.T + tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M;
-            const long long b_row_ll = ((long long)bank * p.N + tc.n) * p.T + tc.nt * BLOCK_N + (int)cta_rank * Cfg::B_ROWS;
-            const int b_row = (int)b_row_ll;
+            const int q_row0 = tc.b * p.T;                                       // query operand: rows of detection b
+            const int t_row0 = (int)(((long long)bank * p.N + tc.n) * p.T);      // bank operand: rows of view n
+            // A = M-side operand (128 rows per CTA), B = N-side operand (each CTA of a pair holds half of the columns;
+            // the box is always B_ROWS rows, the MMA reads the first ncols / CL of them)
+            const int a_row = (MATCH ? t_row0 : q_row0) + tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M;
+            const int b_row = MATCH ? q_row0 + tc.nt * tc.ncols + (int)cta_rank * (tc.ncols / CL)
+                                    : t_row0 + tc.nt * BLOCK_N + (int)cta_rank * Cfg::B_ROWS;
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u, p.fault, 1, stage);
                 const uint32_t da = smem_a + stage * A_STAGE_BYTES;
@@ -232,11 +252,11 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else if (warp == 1 && leader) {
         // ===================== MMA issuer (leader CTA; converged warp, one elected lane issues) =====================
-        constexpr uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, BLOCK_N);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t iter = 0;
         for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
+            const uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, MATCH ? decode(tile).ncols : BLOCK_N);
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             mbar_wait(tempty_bar(as), aphase ^ 1u, p.fault, 2, as);
@@ -265,118 +285,139 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ===================== epilogue (every CTA) =====================
         const int e = warp - FIRST_EPI_WARP;
         const int q = warp & 3;   // TMEM lane quarter this warp may read
-        const int hh = e >> 2;    // which EPI_COLS-wide column slice of the tile
+        const int hh = e >> 2;    // first 32-column chunk of the tile this warp reads (then hh + 4)
         uint32_t iter = 0;
         for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
             const TileCoord tc = decode(tile);
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             const int T = p.T;
-            // rows of this tile are compact query rows r (masked patches were dropped by the prologue);
-            // t is the patch index the row stands for
-            const int rows_b = compact ? __ldg(p.tv + tc.b) : T;
-            const int warp_row0 = tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M + q * 32;
-            const int r_row = warp_row0 + lane;
-            const bool row_ok = r_row < rows_b;
-            const int t = (compact && row_ok) ? __ldg(p.rowmap + (size_t)tc.b * T + r_row) : r_row;
-            // column reduction: value = acc * (query mask x inverse query norm) + 0.0 (-0.0 is canonicalised);
-            // rows past the last one get a huge negative value and lose against everything
-            const float m_t = (EPI == EPI_MATCH && row_ok)
-                                  ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + r_row) : 0.f;
-            const float c_add = row_ok ? 0.0f : -3.0e38f;
             const size_t bn = (size_t)tc.b * p.N + tc.n;
-            const int sbase = tc.nt * BLOCK_N + hh * EPI_COLS;
-            float* rb_s = rb_stage + e * EPI_COLS;  // this warp's inverse template norms
-            if (EPI == EPI_MATCH) {
-                // stage them before waiting for the accumulator so the global latency hides behind the MMAs
+            const int warp_row0 = tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M + q * 32;  // M-side row of lane 0
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+            auto release_tmem = [&]() {
+                // this warp has drained its part of the accumulator: hand the TMEM stage back
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CL == 1) ptx::mbar_arrive(tempty_bar(as));
+                    else ptx::mbar_arrive_cluster(tempty_bar(as), 0);
+                }
+            };
+
+            if (MATCH) {
+                // lane = template patch s (TMEM lane), columns = compact query rows r of detection b; t = rowmap[r]
+                const int s_row = warp_row0 + lane;
+                const bool s_ok = s_row < T;
                 const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
-                const float* rb_n = p.rb + ((size_t)bank * p.N + tc.n) * T;
-                __syncwarp();  // previous tile's readers of rb_s are done
+                // row maxima (over s, across lanes): value = acc * rb[s] + 0.0 (-0.0 is canonicalised); lanes past the
+                // last template patch get a huge negative value and lose against everything
+                const float rb_l = s_ok ? __ldg(p.rb + ((size_t)bank * p.N + tc.n) * T + s_row) : 0.f;
+                const float c_add = s_ok ? 0.0f : -3.0e38f;
+                const int col0 = tc.nt * tc.ncols;  // first compact query row of the tile
+                // per-column factor (query mask x inverse query norm) and patch index of this warp's <= 2 chunks,
+                // staged before waiting for the accumulator so the global latency hides behind the MMAs
+                float* fa_s = rb_stage + e * (2 * EPI_COLS);
+                int* tp_s = reinterpret_cast<int*>(fa_s + EPI_COLS);
+                __syncwarp();  // previous tile's readers are done
 #pragma unroll
                 for (int i = 0; i < EPI_CHUNKS; ++i) {
-                    const int s = sbase + i * 32 + lane;
-                    rb_s[i * 32 + lane] = s < T ? __ldg(rb_n + s) : 0.f;
+                    const int r = col0 + (hh + 4 * i) * 32 + lane;
+                    const bool r_ok = (hh + 4 * i) * 32 < tc.ncols && r < tc.rows;
+                    const int t = r_ok ? (p.rowmap ? __ldg(p.rowmap + (size_t)tc.b * T + r) : r) : 0;
+                    fa_s[i * 32 + lane] = r_ok ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + r) : 0.f;
+                    tp_s[i * 32 + lane] = t;
                 }
                 __syncwarp();
-            }
 
-            mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + hh * EPI_COLS);
+                mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
+                ptx::tc_fence_after();
+                if (hh * 32 >= tc.ncols) release_tmem();  // narrow tile: nothing for this warp to read
 
-            float best = -INFINITY;
-            int best_s = 0;
+                float best = -INFINITY;
+                int best_t = 0;
 #pragma unroll 1
-            for (int c = 0; c < EPI_CHUNKS; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                ptx::tmem_ld_wait();
-                if (c == EPI_CHUNKS - 1) {
-                    // this warp has drained its part of the accumulator: hand the TMEM stage back
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CL == 1) ptx::mbar_arrive(tempty_bar(as));
-                        else ptx::mbar_arrive_cluster(tempty_bar(as), 0);
-                    }
-                }
-                const int s0 = sbase + c * 32;
-                if (s0 >= T) continue;  // warp-uniform: chunk entirely past the last template patch
-                const int ncols = min(32, T - s0);
-                if (EPI == EPI_MATCH) {
-                    // ---- rows: first-argmax over s of acc * rb[s] (strict > keeps the first index on ties); the
-                    // row's own positive factor ra[t] commutes with the max and is applied when finalising.
-                    // ---- columns: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max).
-                    // Each value becomes a float key whose 5 low mantissa bits hold (31 - lane): a float max then
-                    // means "largest value, then lowest row"; values closer than 2^-18 relative count as ties.
+                for (int i = 0; i < EPI_CHUNKS; ++i) {
+                    const int c = hh + 4 * i;
+                    if (c * 32 >= tc.ncols) break;  // warp-uniform
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    ptx::tmem_ld_wait();
+                    if ((c + 4) * 32 >= tc.ncols) release_tmem();
+                    const int r0 = col0 + c * 32;
+                    const int ncols = min(32, tc.rows - r0);
+                    if (ncols <= 0) continue;  // warp-uniform: chunk entirely past the last live query row
+                    // ---- lane-local: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max;
+                    // strict > keeps the first index on ties, columns are in increasing t).
+                    // ---- across lanes: first-argmax over s of acc * rb[s] (the row's own positive factor ra[t]
+                    // commutes with the max and is applied when finalising).  Each value becomes a float key whose
+                    // 5 low mantissa bits hold (31 - lane), the value rounded to nearest at that position: a float max
+                    // then means "largest value, then lowest lane"; values closer than 2^-19 relative count as ties.
                     float k[32];
                     float cbest = -INFINITY;
                     int cj = 0;
                     const uint32_t lane_bits = (uint32_t)(31 - lane);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(rb_s + c * 32 + j);  // broadcast read
-                        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                        const float4 f4 = *reinterpret_cast<const float4*>(fa_s + i * 32 + j);  // broadcast read
+                        const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const float x = __uint_as_float(v[j + u]);
-                            const float xr = x * rr[u];
-                            if (xr > cbest) { cbest = xr; cj = j + u; }
-                            const float xc = fmaf(x, m_t, c_add);
-                            k[j + u] = __uint_as_float((__float_as_uint(xc) & 0xFFFFFFE0u) | lane_bits);
+                            const float xt = x * ff[u];
+                            if (xt > cbest) { cbest = xt; cj = j + u; }
+                            const float xs = fmaf(x, rb_l, c_add);
+                            k[j + u] = __uint_as_float(((__float_as_uint(xs) + 0x10u) & 0xFFFFFFE0u) | lane_bits);
                         }
                     }
                     if (ncols < 32) {
-                        // ragged last chunk: redo the row scan over the valid columns only (rare, tiny shapes)
+                        // ragged last chunk: redo the lane-local scan over the live columns only
                         cbest = -INFINITY;
                         cj = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float xr = __uint_as_float(v[j]) * rb_s[c * 32 + j];
-                            if (j < ncols && xr > cbest) { cbest = xr; cj = j; }
+                            const float xt = __uint_as_float(v[j]) * fa_s[i * 32 + j];
+                            if (j < ncols && xt > cbest) { cbest = xt; cj = j; }
                         }
                     }
-                    if (cbest > best) { best = cbest; best_s = s0 + cj; }
+                    if (cbest > best) { best = cbest; best_t = tp_s[i * 32 + cj]; }
                     // butterfly transpose-reduce: after the 5 exchanges lane j holds the warp's winner of column j
 #pragma unroll
                     for (int half = 16; half >= 1; half >>= 1) {
                         const bool up = (lane & half) != 0;
 #pragma unroll
-                        for (int i = 0; i < half; ++i) {
-                            const float send = up ? k[i] : k[i + half];
-                            const float keep = up ? k[i + half] : k[i];
+                        for (int ii = 0; ii < half; ++ii) {
+                            const float send = up ? k[ii] : k[ii + half];
+                            const float keep = up ? k[ii + half] : k[ii];
                             const float recv = __shfl_xor_sync(0xffffffffu, send, half);
-                            k[i] = fmaxf(keep, recv);
+                            k[ii] = fmaxf(keep, recv);
                         }
                     }
                     {
                         const uint32_t kb = __float_as_uint(k[0]);
-                        // patch index of the winning row: held by the lane that owns that row
-                        const int win_t = __shfl_sync(0xffffffffu, t, 31 - (int)(kb & 31u));
-                        if (lane < ncols && warp_row0 < rows_b)
-                            atomicMax(p.colkey + bn * T + s0 + lane, pack_key(__uint_as_float(kb & 0xFFFFFFE0u), (uint32_t)win_t));
+                        const int win_s = warp_row0 + 31 - (int)(kb & 31u);
+                        if (lane < ncols && warp_row0 < T)
+                            atomicMax(p.rowkey + bn * T + tp_s[i * 32 + lane],
+                                      pack_key(__uint_as_float(kb & 0xFFFFFFE0u), (uint32_t)win_s));
                     }
-                } else {
+                }
+                if (s_ok && best > -INFINITY) atomicMax(p.colkey + bn * T + s_row, pack_key(best + 0.0f, (uint32_t)best_t));
+            } else {
+                // EPI_EMIT: lane = query patch t, columns = template patches s; the scaled products go to HBM
+                const int t = warp_row0 + lane;
+                const bool row_ok = t < T;
+                mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int i = 0; i < EPI_CHUNKS; ++i) {
+                    const int c = hh + 4 * i;
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    ptx::tmem_ld_wait();
+                    if (i == EPI_CHUNKS - 1) release_tmem();
+                    const int s0 = tc.nt * BLOCK_N + c * 32;
+                    if (s0 >= T) continue;  // warp-uniform: chunk entirely past the last template patch
+                    const int ncols = min(32, T - s0);
                     if (row_ok) {
                         float* dst = p.emit + (bn * T + t) * (size_t)T + s0;
                         if (ncols == 32 && (T & 3) == 0) {
@@ -392,9 +433,6 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         }
                     }
                 }
-            }
-            if (EPI == EPI_MATCH && row_ok && best > -INFINITY) {
-                atomicMax(p.rowkey + bn * T + t, pack_key(best + 0.0f, (uint32_t)best_s));
             }
         }
     }
@@ -482,7 +520,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                  "prepared operands must be 128-byte aligned");
     PP_CHECK_ARG((long long)n_banks * N * T < (1LL << 31) && (long long)B * T < (1LL << 31),
                  "operand row count exceeds the 2^31 TMA coordinate range; split the call");
-    PP_CHECK_ARG(tv == nullptr || B <= MAX_DETS_PER_LAUNCH, "at most %d detections per launch (got %d)", MAX_DETS_PER_LAUNCH, B);
+    PP_CHECK_ARG(epi != EPI_MATCH || B <= MAX_DETS_PER_LAUNCH, "at most %d detections per launch (got %d)", MAX_DETS_PER_LAUNCH, B);
     if (cluster == 0) cluster = 2;
     PP_CHECK_ARG(cluster == 1 || cluster == 2, "cluster must be 0, 1 or 2 (got %d)", cluster);
     if (int rc = ensure_fault_buffer()) return rc;
@@ -508,9 +546,15 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.emit_scale = emit_scale;
     p.fault = g_fault_dev;
     if (p.total_tiles == 0) return PP_OK;
+    // A = M-side operand (box of 128 rows), B = N-side operand (box of 256 / cluster rows); EPI_MATCH puts the template
+    // bank on the M side and the compact query rows on the N side, EPI_EMIT the other way round
     CUtensorMap ta, tb;
-    if (int rc = make_tmap(&ta, q_prep, (uint64_t)B * T, (uint64_t)Kp, BLOCK_M)) return rc;
-    if (int rc = make_tmap(&tb, bank_prep, (uint64_t)n_banks * N * T, (uint64_t)Kp, BLOCK_N / cluster)) return rc;
+    const void* m_op = epi == EPI_MATCH ? bank_prep : q_prep;
+    const void* n_op = epi == EPI_MATCH ? q_prep : bank_prep;
+    const uint64_t m_rows = epi == EPI_MATCH ? (uint64_t)n_banks * N * T : (uint64_t)B * T;
+    const uint64_t n_rows = epi == EPI_MATCH ? (uint64_t)B * T : (uint64_t)n_banks * N * T;
+    if (int rc = make_tmap(&ta, m_op, m_rows, (uint64_t)Kp, BLOCK_M)) return rc;
+    if (int rc = make_tmap(&tb, n_op, n_rows, (uint64_t)Kp, BLOCK_N / cluster)) return rc;
     if (cluster == 1) {
         return epi == EPI_MATCH ? launch_gemm<1, EPI_MATCH>(ta, tb, p, st) : launch_gemm<1, EPI_EMIT>(ta, tb, p, st);
     }
