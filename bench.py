@@ -159,6 +159,42 @@ def algorithmic_counts(world, lo, hi):
     return flops, lookup_bytes
 
 
+def lookup_roofline(dev, batch=64, size=64, radius=4, iters=20):
+    """corr_lookup_banded_kernel at the configs[3] shape (64x64 maps, r=4, fp32 volume of batch*4096 slices -- 4.3 GB at
+    batch 64, far larger than L2): algorithmic bytes (8 + D^2*4 + (2r+2)^2*4 per query) / CUDA-event time
+    on the launching stream, against the measured HBM copy peak."""
+    from picopose_b200.corr_lookup import corr_lookup
+    _, peak_gbs, _, _ = measured_peaks()
+    Q = batch * size * size
+    g = torch.Generator(device=dev).manual_seed(0)
+    pyr = [torch.randn(Q, 1, size, size, device=dev, generator=g)]
+    flow = 4.0 * torch.randn(batch, 2, size, size, device=dev, generator=g)
+    D = 2 * radius + 1
+    per_q = 8 + D * D * 4 + min((2 * radius + 2) ** 2, size * size) * 4
+    for _ in range(3):
+        corr_lookup(pyr, flow, radius)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record()
+        corr_lookup(pyr, flow, radius)
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    ms = sum(ts) / len(ts)
+    achieved = Q * per_q / (ms * 1e-3) / 1e9
+    del pyr, flow
+    return {"bound": "hbm", "kernel": "corr_lookup_banded_kernel<4,5>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "frac": achieved / peak_gbs, "traffic": 1369 * Q + 254 * Q, "kernel_ms": ms, "kernel_ms_min": ts[0],
+            "queries": Q, "algorithmic_bytes_per_query": per_q,
+            "workload": "configs[3] shape: %d x %dx%d queries, L=1 fp32 volume (%.1f GB), r=%d, flow~N(0,16); not part of "
+                        "the timed step" % (batch, size, size, Q * size * size * 4 / 1e9, radius),
+            "note": "traffic = ncu dram bytes of this kernel at this shape (1369 B read + 254 B written per query, "
+                    "profiles/r1c_prof_lookup4_r1c.*): every L2 miss moves a whole 128-byte line on this GPU whatever the "
+                    "load instruction (profiles/r1w_dram_granularity.md), so a 10x10 fp32 window costs ~11.7 lines and the "
+                    "algorithmic fraction of this op is capped at ~0.43 at r=4; frac / 0.43 is the share of that cap"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from picopose_b200 import _lib
@@ -308,6 +344,11 @@ def run_ours(args):
     warm_ms_total = w0.elapsed_time(w1)
     _lib.check_device_faults()
 
+    # ---- extra (N=1): the stage-3 lookup at the BASELINE configs[3] shape against the HBM roofline ----
+    lookup_roof = None
+    if world == 1 and not args.no_lookup_roofline:
+        lookup_roof = lookup_roofline(dev)
+
     # ---- max over ranks ----
     times = torch.tensor([ms_total, e2e_ms_total, warm_ms_total, gemm_avg_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -383,6 +424,8 @@ def run_ours(args):
             "matches_per_sec": world * CFG["N"] * CFG["H"] ** 2 * 1e3 / ms_step,
             "lookup_algorithmic_bytes_per_step": lookup_bytes,
         }
+        if lookup_roof is not None:
+            line["roofline_lookup"] = lookup_roof
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
@@ -481,6 +524,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-lookup-roofline", action="store_true", help="skip the configs[3]-shape lookup roofline block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
