@@ -544,6 +544,27 @@ def test_matching_fuzz(case):
     _check_match(src, tar, mask, min(5, N), case["mode"], case["cluster"])
 
 
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("tv", [1, 33, 255, 256, 257, 480, 513, 700, 1023])
+def test_matching_column_tiles(tv, cluster):
+    """The contraction cuts a detection's tv unmasked patches into ceil(tv/256) column tiles of round_up(tv/tiles, 32)
+    columns (match_gemm.cu): one case on each side of every tile-count boundary, narrow tiles that leave epilogue warps
+    without a chunk (tv = 1, 33), ragged last chunks, and a different tv per detection in one launch; 32x32 patches,
+    fp32 mode so the 1e-5 tolerance also covers the rounded row keys."""
+    B, N, C, H = 2, 3, 64, 32
+    src, tar, _ = synth.planted_match_inputs(B, N, C, H, seed=300 + tv)
+    step = 224 // H
+    mask = torch.zeros(B, 224, 224)
+    for b, n_on in enumerate((tv, max(1, 1024 - tv))):
+        on = torch.arange(H * H) < n_on                              # the first n_on patches in (h w) order ...
+        if b == 1:
+            on = on.flip(0)                                          # ... or the last ones (patch 0 masked)
+        grid = on.view(H, H)
+        mask[b, ::step, ::step][:H, :H] = grid.float()
+    assert int((OM.nearest_mask(mask, H, H)[0] != 0).sum()) == tv
+    _check_match(src, tar, mask, 2, "fp32", cluster)
+
+
 def test_lookup_and_windowed_fuzz():
     """Seeded sweep of the stage-3 kernels over rectangular-free square maps of odd and even sizes, 1-3 levels, every
     radius the native path uses, flows from sub-pixel to far outside the map."""
