@@ -154,6 +154,24 @@ PP_API int pp_topk_pairs(const float* scores, int B, int N, int k, int64_t idx_o
 PP_API int pp_topk_merge(const double* pairs, int R, int B, int k_in, int k, float* out_score, int64_t* out_idx,
                   void* stream);
 
+/* The same exchange over NVLink peer memory in ONE kernel (one node, one process per GPU): block b ranks detection b's
+ * local scores, stores its k (score, global index) pairs into every peer's exchange buffer through the peer mapping,
+ * releases a per-(rank, detection) flag on every peer, waits for the peers' flags of that detection and merges.
+ *   pp_xchg_bytes(world, max_b, k_max)   size of one rank's exchange buffer
+ *   pp_xchg_create                        cudaMalloc + zero + cudaIpcGetMemHandle (64-byte handle for the peers)
+ *   pp_xchg_open / pp_xchg_close          cudaIpcOpenMemHandle / cudaIpcCloseMemHandle on a peer's handle
+ *   pp_topk_exchange                      peers_dev: device array of `world` buffer pointers (entry `rank` = own buffer);
+ *                                         epoch: non-zero, incremented by 1 per call, the same on every rank; every rank
+ *                                         must make the call (it is a collective); a missing peer traps after ~4 s. */
+PP_API size_t pp_xchg_bytes(int world, int max_b, int k_max);
+PP_API int pp_xchg_create(size_t bytes, void** buf, void* handle64);
+PP_API int pp_xchg_open(const void* handle64, void** peer_buf);
+PP_API int pp_xchg_close(void* peer_buf);
+PP_API int pp_xchg_destroy(void* buf);
+PP_API int pp_topk_exchange(const float* scores, int B, int N, int k, int64_t idx_offset, const void* const* peers_dev,
+                     int rank, int world, int max_b, int k_max, uint32_t epoch, float* out_score, int64_t* out_idx,
+                     void* stream);
+
 /* Stage-2 input volume.  Replaces matching_features_similarity, utils/matching.py:6-26.
  *   q_prep/q_rnorm, s_prep/s_rnorm : (B, T, Kp) / (B, T) prepared query / template features; src_mask (B,Hm,Wm) fp32
  *   out : (B, S, H, W) fp32 with out[b,s,h,w] = max(0, sim[b, t = w*H+h, s] * mask_s)

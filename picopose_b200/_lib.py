@@ -41,6 +41,12 @@ SIGNATURES = {
                                       _vp, _sz, _i, _vp]),
     "pp_topk_pairs": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp]),
     "pp_topk_merge": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pp_xchg_bytes": (_sz, [_i, _i, _i]),
+    "pp_xchg_create": (_i, [_sz, C.POINTER(_vp), _vp]),
+    "pp_xchg_open": (_i, [_vp, C.POINTER(_vp)]),
+    "pp_xchg_close": (_i, [_vp]),
+    "pp_xchg_destroy": (_i, [_vp]),
+    "pp_topk_exchange": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp]),
     "pp_match_similarity_workspace": (_sz, [_i, _i]),
     "pp_match_similarity": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pp_correlation_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), _i, _vp]),

@@ -1,0 +1,204 @@
+// Multi-GPU top-k exchange over NVLink peer memory (one node, one process per GPU).
+//
+// The template bank is sharded by views, so torch.topk over all views (utils/matching.py:68) becomes: local top-k per
+// rank, exchange of the (B, k) candidate pairs, identical merge on every rank.  This file does all three in ONE kernel:
+// block b ranks detection b's local scores, stores its k (score, global index) pairs straight into every peer's
+// exchange buffer (plain stores through the NVLink peer mapping), releases a per-(rank, detection) flag on every peer,
+// waits for the peers' flags of the same detection and merges the world*k candidates.  Nothing but detection b's own
+// flags is waited for, so there is no grid-wide or host-side synchronisation and a call costs one launch instead of
+// local top-k kernel + NCCL all-gather + merge kernel.
+//
+// Exchange buffer of a rank (allocated here with cudaMalloc so that it can be exported with cudaIpcGetMemHandle):
+//   flags [2][world][max_b] u32        flag value = epoch of the call that wrote the slot (never 0)
+//   pairs [2][world][max_b][k_max]     {float score, int64 index}, 16 bytes each
+// The leading [2] is the epoch parity: a rank may run at most one call ahead of a peer (its merge of call e needs the
+// peer's flags of call e, which the peer writes only after finishing call e-1 in stream order), so two slot sets
+// never collide.
+#include "pp_common.cuh"
+
+#include <cstring>
+
+namespace pp {
+
+struct XPair {
+    float score;
+    int pad;
+    long long index;
+};
+
+struct XchgLayout {
+    size_t flags_bytes, pairs_off, total;
+};
+static XchgLayout xchg_layout(int world, int max_b, int k_max) {
+    XchgLayout l;
+    l.flags_bytes = ((size_t)2 * world * max_b * sizeof(unsigned) + 255) / 256 * 256;
+    l.pairs_off = l.flags_bytes;
+    l.total = l.pairs_off + (size_t)2 * world * max_b * k_max * sizeof(XPair);
+    return l;
+}
+
+constexpr long long XCHG_TIMEOUT_CYCLES = 8000000000LL;  // ~4 s: a missing peer traps instead of hanging
+
+__global__ void __launch_bounds__(256)
+topk_exchange_kernel(const float* __restrict__ scores, int N, int k, long long idx_offset, char* const* __restrict__ peers,
+                     int rank, int world, int max_b, int k_max, size_t pairs_off, unsigned epoch,
+                     float* __restrict__ out_score, long long* __restrict__ out_idx) {
+    extern __shared__ unsigned long long s_keys[];  // N packed keys + 8 partials
+    unsigned long long* s_red = s_keys + N;
+    __shared__ XPair s_loc[256];
+    __shared__ unsigned long long s_merge[1024];
+    const int b = blockIdx.x;
+    const int par = (int)(epoch & 1u);
+    // ---- local top-k (torch.topk on this rank's views; ties resolve to the lowest index) ----
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_keys[i] = pack_key(scores[(size_t)b * N + i] + 0.0f, (uint32_t)i);
+    __syncthreads();
+    const int kl = k < N ? k : N;
+    for (int r = 0; r < k; ++r) {
+        if (r >= kl) {  // the shard holds fewer than k views: padding that loses every comparison
+            if (threadIdx.x == 0) s_loc[r] = XPair{-INFINITY, 0, -1};
+            continue;
+        }
+        unsigned long long best = 0ull;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) best = s_keys[i] > best ? s_keys[i] : best;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = s_red[w] > best ? s_red[w] : best;
+            const uint32_t idx = key_index(best);
+            s_loc[r] = XPair{key_value(best), 0, (long long)idx + idx_offset};
+            s_keys[idx] = 0ull;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- push: pair j of this rank's slot in every peer's buffer (its own included) ----
+    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+        const int p = i / k, j = i - p * k;
+        XPair* dst = reinterpret_cast<XPair*>(peers[p] + pairs_off) + (((size_t)par * world + rank) * max_b + b) * k_max + j;
+        const XPair v = s_loc[j];
+        *reinterpret_cast<volatile float*>(&dst->score) = v.score;
+        *reinterpret_cast<volatile long long*>(&dst->index) = v.index;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        // release: the pairs above are visible system-wide before the flag is
+        __threadfence_system();
+        volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(peers[threadIdx.x]) + ((size_t)par * world + rank) * max_b + b;
+        *flag = epoch;
+        // acquire: wait for peer `threadIdx.x`'s pairs of this detection in this rank's own buffer
+        volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(peers[rank]) + ((size_t)par * world + threadIdx.x) * max_b + b;
+        const long long t0 = clock64();
+        while (*mine != epoch) {
+            __nanosleep(200);
+            if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) __trap();
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    // ---- merge: world * k candidates, ties go to the lowest rank / slot (= lowest view index for contiguous shards) ----
+    const int n = world * k;
+    const XPair* own = reinterpret_cast<const XPair*>(peers[rank] + pairs_off);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = i / k, j = i - r * k;
+        const float sc = __ldcg(&own[(((size_t)par * world + r) * max_b + b) * k_max + j].score);
+        s_merge[i] = pack_key(sc + 0.0f, (uint32_t)i);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int o = 0; o < k; ++o) {
+            unsigned long long best = 0ull;
+            for (int i = lane; i < n; i += 32) best = s_merge[i] > best ? s_merge[i] : best;
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, sft);
+                best = other > best ? other : best;
+            }
+            if (lane == 0) {
+                const uint32_t pos = key_index(best);
+                const int r = pos / k, j = pos - r * k;
+                out_score[(size_t)b * k + o] = key_value(best);
+                out_idx[(size_t)b * k + o] = __ldcg(&own[(((size_t)par * world + r) * max_b + b) * k_max + j].index);
+                s_merge[pos] = 0ull;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace pp
+
+extern "C" size_t pp_xchg_bytes(int world, int max_b, int k_max) {
+    if (world <= 0 || max_b <= 0 || k_max <= 0) return 0;
+    return pp::xchg_layout(world, max_b, k_max).total;
+}
+
+extern "C" int pp_xchg_create(size_t bytes, void** buf, void* handle64) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    PP_CHECK_ARG(bytes > 0 && buf && handle64, "pp_xchg_create: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    PP_CUDA(cudaMalloc(&p, bytes));
+    PP_CUDA(cudaMemset(p, 0, bytes));
+    PP_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(PP_ERR_DEVICE, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *buf = p;
+    return PP_OK;
+}
+
+extern "C" int pp_xchg_open(const void* handle64, void** peer_buf) {
+    using namespace pp;
+    PP_CHECK_ARG(handle64 && peer_buf, "pp_xchg_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(PP_ERR_DEVICE, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    *peer_buf = p;
+    return PP_OK;
+}
+
+extern "C" int pp_xchg_close(void* peer_buf) {
+    using namespace pp;
+    if (peer_buf) PP_CUDA(cudaIpcCloseMemHandle(peer_buf));
+    return PP_OK;
+}
+
+extern "C" int pp_xchg_destroy(void* buf) {
+    using namespace pp;
+    if (buf) PP_CUDA(cudaFree(buf));
+    return PP_OK;
+}
+
+extern "C" int pp_topk_exchange(const float* scores, int B, int N, int k, int64_t idx_offset, const void* const* peers_dev,
+                                int rank, int world, int max_b, int k_max, uint32_t epoch, float* out_score,
+                                int64_t* out_idx, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (B == 0 || k == 0) return PP_OK;
+    PP_CHECK_ARG(peers_dev && out_score && out_idx && (scores || N == 0), "pp_topk_exchange: null pointer");
+    PP_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && world <= 256, "pp_topk_exchange: bad rank %d / world %d", rank, world);
+    PP_CHECK_ARG(B <= max_b && k <= k_max && k > 0 && k <= 256 && world * k <= 1024 && N >= 0 && N <= 24000,
+                 "pp_topk_exchange: bad sizes (B=%d of %d, k=%d of %d, N=%d)", B, max_b, k, k_max, N);
+    PP_CHECK_ARG(epoch != 0, "pp_topk_exchange: epoch 0 is reserved for 'never written'");
+    const XchgLayout l = xchg_layout(world, max_b, k_max);
+    const size_t smem = ((size_t)N + 8) * sizeof(unsigned long long);
+    if (smem > 48 * 1024)
+        PP_CUDA(cudaFuncSetAttribute(topk_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_exchange_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        scores, N, k, (long long)idx_offset, reinterpret_cast<char* const*>(const_cast<void* const*>(peers_dev)), rank, world,
+        max_b, k_max, l.pairs_off, epoch, out_score, reinterpret_cast<long long*>(out_idx));
+    PP_LAUNCHED();
+    return PP_OK;
+}

@@ -1,11 +1,16 @@
-"""Multi-GPU stage-1 matching: template-axis sharding + one all-gather top-k merge.
+"""Multi-GPU stage-1 matching: template-axis sharding + one top-k exchange.
 
 One process per GPU (torchrun).  Rank g keeps views [lo_g, hi_g) of every object's template bank
 (prepared bf16, resident), all ranks see the whole detection batch (a rank's own detections come from its
 host, the others' over NVLink: `ShardedMatcher.gather_queries`), each computes its local
-sim_avg[:, lo_g:hi_g] and a local top-k with GLOBAL view indices packed as one (B, k, 2) tensor, and a single
-NCCL all-gather of those pairs over NVLink is merged identically on every rank by one small kernel.  Every (detection, view)
-score is independent (utils/matching.py:47-67); only topk (:68) couples views, hence one exchange.
+sim_avg[:, lo_g:hi_g] and a local top-k with GLOBAL view indices, and the (B, k) candidate pairs are exchanged and merged
+identically on every rank.  Every (detection, view) score is independent (utils/matching.py:47-67); only topk (:68)
+couples views, hence one exchange.  Two forms of it:
+
+* `PeerExchange` (default on CUDA): ONE kernel does local top-k, stores the pairs into every peer's buffer through the
+  NVLink peer mapping (CUDA IPC), flags them, waits for the peers' flags and merges (csrc/exchange.cu);
+* `merge_topk`: local top-k kernel, one NCCL (or gloo) all-gather of a (B, k, 2) tensor, merge kernel -- the portable
+  form, used when peer mappings are not available and by the CPU tests of the plumbing.
 """
 from __future__ import annotations
 
@@ -79,10 +84,83 @@ def merge_topk(local_pairs: torch.Tensor, k: int, group=None, merge: Optional[Ca
     return merge(gathered, k)
 
 
+class PeerExchange:
+    """Per-rank exchange buffer + peer mappings for `pp_topk_exchange` (one node, one process per GPU).
+
+    Collective constructor: every rank allocates its buffer in the library (cudaMalloc + cudaIpcGetMemHandle), the
+    64-byte handles travel through one `all_gather_object`, every rank maps its peers' buffers.  `exchange` is a
+    collective too (every rank must call it, with the same B and k); the epoch counter advances identically everywhere.
+    """
+
+    def __init__(self, group=None, max_b: int = 64, k_max: int = 8, device=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.max_b, self.k_max = int(max_b), int(k_max)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.epoch = 0
+        self._own = None
+        self._opened = []
+        with torch.cuda.device(self.device):
+            nbytes = lib.pp_xchg_bytes(self.world, self.max_b, self.k_max)
+            buf, handle = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
+            self._own = buf.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            ptrs = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(self._own)
+                else:
+                    p = C.c_void_p()
+                    _lib.check(lib.pp_xchg_open(C.create_string_buffer(h, 64), C.byref(p)), "pp_xchg_open")
+                    self._opened.append(p.value)
+                    ptrs.append(p.value)
+            self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        dist.barrier(group)   # nobody pushes before everybody has mapped everybody
+
+    def exchange(self, sim: torch.Tensor, k: int, idx_offset: int = 0):
+        """sim (B, N_local) local scores -> global (score (B,k) f32, idx (B,k) i64), identical on every rank."""
+        from . import _lib
+        lib = _lib.load()
+        sim = sim.float().contiguous()
+        B, N = sim.shape
+        if B > self.max_b or k > self.k_max:
+            raise ValueError(f"PeerExchange sized for B <= {self.max_b}, k <= {self.k_max} (got B={B}, k={k})")
+        self.epoch = 1 if self.epoch >= 0xFFFFFFFE else self.epoch + 1      # never 0, parity alternates across the wrap
+        score = torch.empty(B, k, dtype=torch.float32, device=sim.device)
+        idx = torch.empty(B, k, dtype=torch.int64, device=sim.device)
+        with torch.cuda.device(sim.device):
+            _lib.check(lib.pp_topk_exchange(_lib.ptr(sim), B, N, k, idx_offset, _lib.ptr(self.peers), self.rank, self.world,
+                                            self.max_b, self.k_max, self.epoch, _lib.ptr(score), _lib.ptr(idx),
+                                            _lib.stream_of(sim)), "pp_topk_exchange")
+        return score, idx
+
+    def close(self):
+        """Collective: unmap the peers' buffers, then free the own one."""
+        from . import _lib
+        lib = _lib.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                lib.pp_xchg_close(p)
+            self._opened = []
+            dist.barrier(self.group)
+            if self._own is not None:
+                lib.pp_xchg_destroy(self._own)
+                self._own = None
+
+
 class ShardedMatcher:
     """Template-sharded `matching_templates` over a process group."""
 
-    def __init__(self, n_views: int, group=None, merge: Optional[Callable] = None, query_group=None):
+    def __init__(self, n_views: int, group=None, merge: Optional[Callable] = None, query_group=None,
+                 peer_exchange: Optional[bool] = None):
         self.group = group
         # gather_queries on its own communicator: collectives of one NCCL communicator run in issue order on one
         # internal stream, so a query gather for step i+1 would otherwise queue behind step i's top-k exchange
@@ -93,6 +171,12 @@ class ShardedMatcher:
         self.lo, self.hi = shard_range(n_views, self.rank, self.world)
         self.merge = merge
         self.bank = None
+        # top-k exchange through NVLink peer memory unless a custom merge was injected or it is switched off
+        if peer_exchange is None:
+            import os
+            peer_exchange = merge is None and os.environ.get("PICOPOSE_PEER_EXCHANGE", "1") != "0"
+        self._want_peer = bool(peer_exchange) and self.world > 1
+        self._xchg = None
 
     def load_bank(self, src_feats_shard: torch.Tensor, mode: Optional[str] = None):
         """src_feats_shard: this rank's views (n_banks, hi-lo, C, H, W) fp32 -> resident prepared bank."""
@@ -124,4 +208,25 @@ class ShardedMatcher:
             # single rank: nothing to exchange, one library call ranks the whole bank
             return matching_templates(src, tar_feat, None, tar_mask, topk, mode=mode, bank_index=bank_index)
         sim = template_scores(src, tar_feat, tar_mask, mode=mode, bank_index=bank_index)     # (B, hi-lo)
+        xchg = self._peer_exchange_for(sim, topk)
+        if xchg is not None:
+            return xchg.exchange(sim, topk, idx_offset=self.lo)
         return merge_topk(topk_pairs(sim, topk, idx_offset=self.lo), topk, self.group, self.merge)
+
+    def _peer_exchange_for(self, sim: torch.Tensor, k: int):
+        """The PeerExchange to use for this call, created (collectively) on first use; None = all-gather form."""
+        if not self._want_peer or not sim.is_cuda:
+            return None
+        B = sim.shape[0]
+        if self._xchg is not None and (B > self._xchg.max_b or k > self._xchg.k_max):
+            self._xchg.close()
+            self._xchg = None
+        if self._xchg is None:
+            try:
+                self._xchg = PeerExchange(self.group, max_b=max(64, B), k_max=max(8, k), device=sim.device)
+            except RuntimeError as exc:   # no peer mappings in this environment: every rank fails alike
+                import warnings
+                warnings.warn(f"picopose_b200: peer-memory top-k exchange unavailable ({exc}); using the all-gather form")
+                self._want_peer = False
+                return None
+        return self._xchg

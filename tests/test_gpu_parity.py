@@ -615,3 +615,48 @@ def test_matching_templates_dense_call_paths(monkeypatch):
         assert torch.equal(i0, i) and torch.equal(s0, s)
     assert i0[:, 0].cpu().tolist() == top1.tolist()
     _lib.check_device_faults()
+
+
+def test_topk_exchange_three_ranks_on_one_gpu():
+    """pp_topk_exchange's protocol with three 'ranks' simulated on one GPU: three exchange buffers in one process (their
+    pointers are shared directly instead of through CUDA IPC) and the three rank kernels on three streams, so that they
+    push into, flag and wait for each other exactly as three processes would; uneven shards, one of them smaller than k;
+    two consecutive calls exercise both epoch parities.  Kept last in the file: the kernels need to run concurrently."""
+    import ctypes as C
+    lib = _lib.load()
+    world, B, k, max_b, k_max = 3, 5, 4, 8, 6
+    shard = [70, 3, 57]                                              # views per rank (rank 1 holds fewer than k)
+    offs = [0, 70, 73]
+    nbytes = lib.pp_xchg_bytes(world, max_b, k_max)
+    bufs = []
+    for _ in range(world):
+        buf, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
+        bufs.append(buf.value)
+    peers = torch.tensor(bufs, dtype=torch.int64, device=DEV)
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    try:
+        for epoch in (1, 2):
+            g = torch.Generator().manual_seed(40 + epoch)
+            full = torch.randn(B, sum(shard), generator=g)
+            full[:, 71] = full[:, 5]                                 # a tie across ranks: the lower view index wins
+            parts = [full[:, o:o + n].contiguous().to(DEV) for o, n in zip(offs, shard)]
+            outs = []
+            torch.cuda.synchronize()
+            for r in range(world):
+                sc = torch.empty(B, k, dtype=torch.float32, device=DEV)
+                ix = torch.empty(B, k, dtype=torch.int64, device=DEV)
+                outs.append((sc, ix))
+                _lib.check(lib.pp_topk_exchange(_lib.ptr(parts[r]), B, shard[r], k, offs[r], _lib.ptr(peers), r, world, max_b,
+                                                k_max, epoch, _lib.ptr(sc), _lib.ptr(ix), streams[r].cuda_stream),
+                           "pp_topk_exchange")
+            torch.cuda.synchronize()
+            _lib.check_device_faults()
+            ref_s, ref_i = torch.sort(full, dim=1, descending=True, stable=True)
+            for sc, ix in outs:
+                assert torch.equal(ix.cpu(), ref_i[:, :k])
+                assert torch.equal(sc.cpu(), ref_s[:, :k])
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            lib.pp_xchg_destroy(b)
