@@ -159,9 +159,9 @@ def algorithmic_counts(world, lo, hi):
     return flops, lookup_bytes
 
 
-def lookup_roofline(dev, batch=64, size=64, radius=4, iters=20):
-    """corr_lookup_banded_kernel at the configs[3] shape (64x64 maps, r=4, fp32 volume of batch*4096 slices -- 4.3 GB at
-    batch 64, far larger than L2): algorithmic bytes (8 + D^2*4 + (2r+2)^2*4 per query) / CUDA-event time
+def lookup_roofline(dev, batch=256, size=64, radius=4, iters=20):
+    """corr_lookup_banded_kernel at the configs[3] shape (batch 256, 64x64 maps, r=4, fp32 volume of 2^20 slices = 17.2 GB,
+    far larger than L2): algorithmic bytes (8 + D^2*4 + (2r+2)^2*4 per query) / CUDA-event time
     on the launching stream, against the measured HBM copy peak."""
     from picopose_b200.corr_lookup import corr_lookup
     _, peak_gbs, _, _ = measured_peaks()
