@@ -229,7 +229,7 @@ static int match_scores_impl(const void* q_prep, const float* q_rnorm, const voi
                              const float* bank_rnorm, int64_t n_banks, const int32_t* bank_of_det, int B, int N, int H,
                              int W, int Kp, float* sim_avg, float* score_t2s, int32_t* idx_t2s, int32_t* idx_s2t,
                              uint8_t* mutual_nn, int k, float* topk_score, int64_t* topk_idx, void* workspace,
-                             size_t workspace_bytes, int cluster, void* stream) {
+                             size_t workspace_bytes, int cluster, void* stream, bool keys_cleared = false) {
     if (int rc = require_sm100()) return rc;
     if (B == 0 || N == 0) return PP_OK;
     PP_CHECK_ARG(q_prep && q_rnorm && q_meta && bank_prep && bank_rnorm && sim_avg, "pp_match_scores: null pointer");
@@ -247,7 +247,9 @@ static int match_scores_impl(const void* q_prep, const float* q_rnorm, const voi
     unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(workspace);
     unsigned long long* colkey = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + keys);
     int* done = reinterpret_cast<int*>(static_cast<char*>(workspace) + 2 * keys);  // per-detection finished-view counters
-    PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys + align_up((size_t)B * sizeof(int), 256), st));
+    // the key arrays and the per-detection counters start at zero (a caller that has already cleared the scratch,
+    // e.g. on a forked stream beside the bank prologue, says so)
+    if (!keys_cleared) PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys + align_up((size_t)B * sizeof(int), 256), st));
     if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, qm.mrow, qm.tv, qm.rowmap, q_rnorm,
                                 bank_rnorm, rowkey, colkey, nullptr, 1.0f, cluster, st))
         return rc;
@@ -494,17 +496,20 @@ extern "C" int pp_match_templates_dense(const float* src_feats, int64_t G, const
     PP_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
     const int rc = pp_match_prepare_query(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
                                           reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, fj->side);
+    // ... and so does the clearing of the key scratch
+    const cudaError_t e0 = cudaMemsetAsync(ws + w.keys, 0, pp_match_scores_workspace(B, N, T), fj->side);
     const int rc2 = pp_match_prepare(src_feats, G * N, C, T, mode, 0, bank_prep, bank_rnorm, stream);
     // join unconditionally so that the side stream never outlives the call's ordering on `stream`
     const cudaError_t e1 = cudaEventRecord(fj->join, fj->side);
     const cudaError_t e2 = cudaStreamWaitEvent(st, fj->join, 0);
     if (rc) return rc;
     if (rc2) return rc2;
+    PP_CUDA(e0);
     PP_CUDA(e1);
     PP_CUDA(e2);
     const bool rank_it = k > 0 && out_score && out_idx;
     return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
                              G, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
                              rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
-                             stream);
+                             stream, /*keys_cleared=*/true);
 }
