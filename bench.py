@@ -300,13 +300,14 @@ def run_ours(args):
                 if world == 1:
                     bufs[sl][0].copy_(tar_h, non_blocking=True)
                     bufs[sl][1].copy_(mask_h, non_blocking=True)
+                    cur = bufs[sl]
                 else:
                     own[sl][0].copy_(own_tar_h, non_blocking=True)
                     own[sl][1].copy_(own_mask_h, non_blocking=True)
-                    matcher.gather_queries(own[sl][0], own[sl][1], out=bufs[sl])   # ordered after the uploads, off the main stream
+                    cur = matcher.gather_queries(own[sl][0], own[sl][1], out=bufs[sl])   # ordered after the uploads, off the main stream
                 up_done[sl].record(copy_stream)
             main_stream.wait_event(up_done[sl])
-            s, i, _ = step(bufs[sl][0], bufs[sl][1], src_d)
+            s, i, _ = step(cur[0], cur[1], src_d)
             used[sl].record(main_stream)
             with torch.cuda.stream(down_stream):            # device->host read of the step's result (pinned, async) on
                 down_stream.wait_event(used[sl])            # its own stream: the next step does not queue behind it

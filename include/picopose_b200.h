@@ -168,6 +168,15 @@ PP_API int pp_xchg_create(size_t bytes, void** buf, void* handle64);
 PP_API int pp_xchg_open(const void* handle64, void** peer_buf);
 PP_API int pp_xchg_close(void* peer_buf);
 PP_API int pp_xchg_destroy(void* buf);
+/* Bulk pushes through the same kind of buffer (used for the query gather): pp_xchg_push copies `bytes` from `src` to
+ * offset `dst_offset` of EVERY peer's buffer with copy-engine peer copies (peers_host: HOST array of `world` buffer
+ * pointers), pp_xchg_signal then writes `epoch` into flag [rank] (u32 array at `flag_offset`) of every peer's buffer and
+ * pp_xchg_wait spins on the `world` flags of the own buffer; all three are stream-ordered. */
+PP_API int pp_xchg_push(const void* src, size_t bytes, const void* const* peers_host, int world, size_t dst_offset,
+                 void* stream);
+PP_API int pp_xchg_signal(const void* const* peers_dev, size_t flag_offset, int rank, int world, uint32_t epoch,
+                   void* stream);
+PP_API int pp_xchg_wait(const void* own_buf, size_t flag_offset, int world, uint32_t epoch, void* stream);
 PP_API int pp_topk_exchange(const float* scores, int B, int N, int k, int64_t idx_offset, const void* const* peers_dev,
                      int rank, int world, int max_b, int k_max, uint32_t epoch, float* out_score, int64_t* out_idx,
                      void* stream);

@@ -15,8 +15,6 @@
 // inverse, utils/corr_lookup.py:61-65 + ATen grid_sampler_unnormalize), so floor/weights agree.
 #include "pp_common.cuh"
 
-#include <cstdlib>
-
 namespace pp {
 
 constexpr int LOOKUP_MAX_LEVELS = 8;
@@ -429,17 +427,6 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
     p.total_groups = B * p.groups_per_b;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (all_vec) {
-        // tuning aid: PICOPOSE_LOOKUP_JB overrides the band height for the radii of the BASELINE sweep
-        static const int jb_override = [] { const char* e = getenv("PICOPOSE_LOOKUP_JB"); return e ? atoi(e) : 0; }();
-        if (jb_override) {
-#define PP_JB_CASE(R, JB) if (radius == R && jb_override == JB) return launch_banded<R, JB>(p, st);
-            PP_JB_CASE(4, 2) PP_JB_CASE(4, 3) PP_JB_CASE(4, 4) PP_JB_CASE(4, 9)
-            PP_JB_CASE(5, 2) PP_JB_CASE(5, 3) PP_JB_CASE(5, 6)
-            PP_JB_CASE(6, 2) PP_JB_CASE(6, 3) PP_JB_CASE(6, 4) PP_JB_CASE(6, 7)
-            PP_JB_CASE(7, 2) PP_JB_CASE(7, 3) PP_JB_CASE(7, 4) PP_JB_CASE(7, 8)
-            PP_JB_CASE(8, 2) PP_JB_CASE(8, 3) PP_JB_CASE(8, 4) PP_JB_CASE(8, 5) PP_JB_CASE(8, 9)
-#undef PP_JB_CASE
-        }
         // band height per radius: keeps ~12-25 KB of staging per warp so 8-16 warps share an SM
         switch (radius) {
             case 1: return launch_banded<1, 3>(p, st);

@@ -130,7 +130,56 @@ topk_exchange_kernel(const float* __restrict__ scores, int N, int k, long long i
     }
 }
 
+// ---- flags for bulk pushes (PeerGather): one u32 per (parity, source rank) at the head of a buffer ----
+__global__ void xchg_signal_kernel(char* const* __restrict__ peers, size_t flag_off, int rank, int world, unsigned epoch) {
+    // runs after the pushes of this rank in stream order: the copies have landed before the flag is written
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(peers[threadIdx.x] + flag_off) + rank;
+        *flag = epoch;
+    }
+}
+__global__ void xchg_wait_kernel(const char* __restrict__ own, size_t flag_off, int world, unsigned epoch) {
+    if ((int)threadIdx.x < world) {
+        const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(own + flag_off) + threadIdx.x;
+        const long long t0 = clock64();
+        while (*flag != epoch) {
+            __nanosleep(500);
+            if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) __trap();
+        }
+        __threadfence_system();
+    }
+}
+
 }  // namespace pp
+
+extern "C" int pp_xchg_push(const void* src, size_t bytes, const void* const* peers_host, int world, size_t dst_offset,
+                            void* stream) {
+    using namespace pp;
+    PP_CHECK_ARG(src && peers_host && world > 0, "pp_xchg_push: bad arguments");
+    for (int p = 0; p < world; ++p)
+        PP_CUDA(cudaMemcpyAsync(static_cast<char*>(const_cast<void*>(peers_host[p])) + dst_offset, src, bytes,
+                                cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return PP_OK;
+}
+
+extern "C" int pp_xchg_signal(const void* const* peers_dev, size_t flag_offset, int rank, int world, uint32_t epoch,
+                              void* stream) {
+    using namespace pp;
+    PP_CHECK_ARG(peers_dev && world > 0 && world <= 256 && rank >= 0 && rank < world && epoch != 0, "pp_xchg_signal: bad arguments");
+    xchg_signal_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<char* const*>(const_cast<void* const*>(peers_dev)), flag_offset, rank, world, epoch);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_xchg_wait(const void* own_buf, size_t flag_offset, int world, uint32_t epoch, void* stream) {
+    using namespace pp;
+    PP_CHECK_ARG(own_buf && world > 0 && world <= 256 && epoch != 0, "pp_xchg_wait: bad arguments");
+    xchg_wait_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const char*>(own_buf), flag_offset, world, epoch);
+    PP_LAUNCHED();
+    return PP_OK;
+}
 
 extern "C" size_t pp_xchg_bytes(int world, int max_b, int k_max) {
     if (world <= 0 || max_b <= 0 || k_max <= 0) return 0;

@@ -43,6 +43,8 @@ struct QueryMaskArgs {
     int* rowmap;
     int* tv;
     int* fm;
+    uint4* clear;                   // optional scratch to zero in the same launch (the contraction's key arrays)
+    unsigned long long clear_n16;   // its size in 16-byte units
 };
 
 template <int NPARTS, bool QM>
@@ -64,6 +66,13 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int tv_total = 0;
     if (QM) {
+        if (qm.clear) {
+            // zero the caller's scratch while we are here: saves a memset node in front of the contraction
+            const unsigned long long nth = (unsigned long long)gridDim.x * gridDim.y * PREP_THREADS;
+            for (unsigned long long i = ((unsigned long long)blockIdx.y * gridDim.x + blockIdx.x) * PREP_THREADS + threadIdx.x;
+                 i < qm.clear_n16; i += nth)
+                qm.clear[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         auto mask_at = [&](int t) {
             const int y = t / qm.W, xx = t - y * qm.W;
             return __ldg(qm.mask + ((size_t)g * qm.Hm + nearest_src(y, qm.Hm, qm.H)) * qm.Wm + nearest_src(xx, qm.Wm, qm.W));
@@ -277,8 +286,19 @@ extern "C" size_t pp_match_query_meta_bytes(int B, int T) {
     return ((size_t)3 * B * T + 2 * (size_t)B) * 4;
 }
 
+namespace pp {
+int prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm, int Wm, int mode,
+                       void* q_prep, float* q_rnorm, void* q_meta, void* clear, size_t clear_bytes, void* stream);
+}
+
 extern "C" int pp_match_prepare_query(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm,
                                       int Wm, int mode, void* q_prep, float* q_rnorm, void* q_meta, void* stream) {
+    return pp::prepare_query_impl(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, q_prep, q_rnorm, q_meta, nullptr, 0, stream);
+}
+
+// `clear` (16-byte aligned, clear_bytes a multiple of 16) is zeroed by the same launch when given
+int pp::prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm, int Wm, int mode,
+                           void* q_prep, float* q_rnorm, void* q_meta, void* clear, size_t clear_bytes, void* stream) {
     using namespace pp;
     if (int rc = require_sm100()) return rc;
     if (B == 0) return PP_OK;
@@ -293,7 +313,10 @@ extern "C" int pp_match_prepare_query(const float* tar_feat, const float* tar_ma
     const int Kp = pp_match_kp(C, mode);
     const QueryMeta m = split_query_meta(q_meta, B, T);
     // one launch: mask resize + compaction bookkeeping + cast/transposition of the unmasked patches + inverse norms
-    const QueryMaskArgs qa{tar_mask, Hm, Wm, H, W, m.mrow, m.rank, m.rowmap, m.tv, m.fm};
+    PP_CHECK_ARG(!clear || ((reinterpret_cast<uintptr_t>(clear) & 15) == 0 && clear_bytes % 16 == 0),
+                 "pp_match_prepare_query: scratch to clear must be 16-byte aligned and sized");
+    const QueryMaskArgs qa{tar_mask, Hm, Wm, H, W, m.mrow, m.rank, m.rowmap, m.tv, m.fm, static_cast<uint4*>(clear),
+                           (unsigned long long)(clear ? clear_bytes / 16 : 0)};
     const int nseg = mode_segments(mode), nparts = mode_parts(mode);
     dim3 grid((T + PREP_PT - 1) / PREP_PT, B);
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(q_prep);

@@ -12,6 +12,9 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
                    cudaStream_t st);
 
+int prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm, int Wm, int mode,
+                       void* q_prep, float* q_rnorm, void* q_meta, void* clear, size_t clear_bytes, void* stream);
+
 // F.interpolate(mask[:,None], size=(H,W)) (nearest) flattened to (B, H*W): utils/matching.py:38-39 / :16-17
 __global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm, int Wm, int H, int W,
                                    float* __restrict__ out) {
@@ -436,14 +439,16 @@ extern "C" int pp_match_templates(const float* tar_feat, const float* tar_mask, 
     PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_templates: workspace must be 256-byte aligned");
     char* ws = static_cast<char*>(workspace);
     float* sim_avg = sim_avg_out ? sim_avg_out : reinterpret_cast<float*>(ws + w.sim_avg);
-    if (int rc = pp_match_prepare_query(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
-                                        reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, stream))
+    // the query prologue also zeroes the contraction's key scratch: one launch instead of a kernel and a memset node
+    if (int rc = prepare_query_impl(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
+                                    reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, ws + w.keys,
+                                    pp_match_scores_workspace(B, N, T), stream))
         return rc;
     const bool rank_it = k > 0 && out_score && out_idx;
     return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
                              n_banks, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
                              rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
-                             stream);
+                             stream, /*keys_cleared=*/true);
 }
 
 namespace pp {
@@ -494,10 +499,11 @@ extern "C" int pp_match_templates_dense(const float* src_feats, int64_t G, const
     // fork: the (small, latency-bound) query prologue runs beside the (large, bandwidth-bound) bank prologue
     PP_CUDA(cudaEventRecord(fj->fork, st));
     PP_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
-    const int rc = pp_match_prepare_query(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
-                                          reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, fj->side);
-    // ... and so does the clearing of the key scratch
-    const cudaError_t e0 = cudaMemsetAsync(ws + w.keys, 0, pp_match_scores_workspace(B, N, T), fj->side);
+    // (it also clears the contraction's key scratch)
+    const int rc = prepare_query_impl(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
+                                      reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, ws + w.keys,
+                                      pp_match_scores_workspace(B, N, T), fj->side);
+    const cudaError_t e0 = cudaSuccess;
     const int rc2 = pp_match_prepare(src_feats, G * N, C, T, mode, 0, bank_prep, bank_rnorm, stream);
     // join unconditionally so that the side stream never outlives the call's ordering on `stream`
     const cudaError_t e1 = cudaEventRecord(fj->join, fj->side);

@@ -104,23 +104,9 @@ class PeerExchange:
         self.epoch = 0
         self._own = None
         self._opened = []
-        with torch.cuda.device(self.device):
-            nbytes = lib.pp_xchg_bytes(self.world, self.max_b, self.k_max)
-            buf, handle = C.c_void_p(), C.create_string_buffer(64)
-            _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
-            self._own = buf.value
-            handles = [None] * self.world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            ptrs = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    ptrs.append(self._own)
-                else:
-                    p = C.c_void_p()
-                    _lib.check(lib.pp_xchg_open(C.create_string_buffer(h, 64), C.byref(p)), "pp_xchg_open")
-                    self._opened.append(p.value)
-                    ptrs.append(p.value)
-            self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        nbytes = lib.pp_xchg_bytes(self.world, self.max_b, self.k_max)
+        self._own, ptrs, self._opened = _open_peers(lib, group, nbytes, self.device)
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
         dist.barrier(group)   # nobody pushes before everybody has mapped everybody
 
     def exchange(self, sim: torch.Tensor, k: int, idx_offset: int = 0):
@@ -156,6 +142,101 @@ class PeerExchange:
                 self._own = None
 
 
+class _DeviceView:
+    """Zero-copy torch view of library-owned device memory (through __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _open_peers(lib, group, nbytes: int, device):
+    """Collective: allocate this rank's exchange buffer, swap the IPC handles, map every peer's buffer.
+    -> (own pointer, [pointer of rank 0 .. world-1] with the own one in place, [opened peer pointers])."""
+    import ctypes as C
+    from . import _lib
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    with torch.cuda.device(device):
+        buf, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        ptrs, opened = [], []
+        for r, h in enumerate(handles):
+            if r == rank:
+                ptrs.append(buf.value)
+            else:
+                p = C.c_void_p()
+                _lib.check(lib.pp_xchg_open(C.create_string_buffer(h, 64), C.byref(p)), "pp_xchg_open")
+                opened.append(p.value)
+                ptrs.append(p.value)
+    return buf.value, ptrs, opened
+
+
+class PeerGather:
+    """All-gather of every rank's query slice (features + mask) through NVLink peer memory with the COPY ENGINES.
+
+    An NCCL all-gather needs SMs, and the contraction kernel holds all of them, so a gather issued for step i+1 while
+    step i computes only runs in the gaps between kernels.  Here rank r copies its slice into slot r of every peer's
+    buffer with `cudaMemcpyAsync` peer copies (no SM), a one-block kernel then writes the call's epoch into flag [r]
+    of every peer, and a one-block kernel spins on the `world` flags of the own buffer; all on the caller's stream.
+    Slots are double-buffered by epoch parity.  Contract (same as for any double-buffered upload): a `gather` may run
+    at most one step ahead of the compute it feeds -- the stream it is issued on must be ordered after the `match`
+    (top-k exchange) that consumed the gather before the previous one; the exchange guarantees that every peer has
+    finished reading that parity.
+    """
+
+    def __init__(self, tar_slice_shape, mask_slice_shape, group=None, device=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.tar_shape, self.mask_shape = tuple(tar_slice_shape), tuple(mask_slice_shape)
+        self.tar_bytes = 4 * int(torch.Size(self.tar_shape).numel())
+        self.mask_bytes = 4 * int(torch.Size(self.mask_shape).numel())
+        assert self.tar_bytes % 16 == 0 and self.mask_bytes % 16 == 0
+        self.flag_bytes = 256 * ((2 * self.world * 4 + 255) // 256)
+        self.tar_region = self.world * self.tar_bytes
+        self.mask_region = 256 * ((self.world * self.mask_bytes + 255) // 256)
+        self.parity_bytes = 256 * ((self.tar_region + 255) // 256) + self.mask_region
+        nbytes = self.flag_bytes + 2 * self.parity_bytes
+        self._own, ptrs, self._opened = _open_peers(lib, group, nbytes, self.device)
+        self._peers_host = (C.c_void_p * self.world)(*ptrs)
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self.epoch = 0
+        dist.barrier(group)
+
+    def _offsets(self, par: int):
+        base = self.flag_bytes + par * self.parity_bytes
+        return base, base + 256 * ((self.tar_region + 255) // 256)
+
+    def gather(self, tar_local: torch.Tensor, mask_local: torch.Tensor):
+        """-> (tar (world*b, ...), mask (world*b, ...)) views of this rank's buffer, valid in stream order on the
+        current stream (and on any stream that waits for it) until the gather after next."""
+        from . import _lib
+        lib = _lib.load()
+        assert tuple(tar_local.shape) == self.tar_shape and tuple(mask_local.shape) == self.mask_shape
+        tar_local, mask_local = tar_local.float().contiguous(), mask_local.float().contiguous()
+        self.epoch = 1 if self.epoch >= 0xFFFFFFFE else self.epoch + 1
+        par = self.epoch & 1
+        t_off, m_off = self._offsets(par)
+        st = _lib.stream_of(tar_local)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.pp_xchg_push(_lib.ptr(tar_local), self.tar_bytes, self._peers_host, self.world,
+                                        t_off + self.rank * self.tar_bytes, st), "pp_xchg_push")
+            _lib.check(lib.pp_xchg_push(_lib.ptr(mask_local), self.mask_bytes, self._peers_host, self.world,
+                                        m_off + self.rank * self.mask_bytes, st), "pp_xchg_push")
+            _lib.check(lib.pp_xchg_signal(_lib.ptr(self.peers), par * self.world * 4, self.rank, self.world, self.epoch, st),
+                       "pp_xchg_signal")
+            _lib.check(lib.pp_xchg_wait(self._own, par * self.world * 4, self.world, self.epoch, st), "pp_xchg_wait")
+        b = self.tar_shape[0]
+        tar = torch.as_tensor(_DeviceView(self._own + t_off, (self.world * b,) + self.tar_shape[1:]), device=self.device)
+        mask = torch.as_tensor(_DeviceView(self._own + m_off, (self.world * b,) + self.mask_shape[1:]), device=self.device)
+        return tar, mask
+
+
 class ShardedMatcher:
     """Template-sharded `matching_templates` over a process group."""
 
@@ -174,9 +255,10 @@ class ShardedMatcher:
         # top-k exchange through NVLink peer memory unless a custom merge was injected or it is switched off
         if peer_exchange is None:
             import os
-            peer_exchange = merge is None and os.environ.get("PICOPOSE_PEER_EXCHANGE", "1") != "0"
+            peer_exchange = merge is None and os.environ.get("PICOPOSE_B200_PEER_EXCHANGE", "1") != "0"
         self._want_peer = bool(peer_exchange) and self.world > 1
         self._xchg = None
+        self._gather = None
 
     def load_bank(self, src_feats_shard: torch.Tensor, mode: Optional[str] = None):
         """src_feats_shard: this rank's views (n_banks, hi-lo, C, H, W) fp32 -> resident prepared bank."""
@@ -187,12 +269,27 @@ class ShardedMatcher:
 
     def gather_queries(self, tar_local: torch.Tensor, mask_local: torch.Tensor, out=None):
         """Each rank received its own detections' query features (b, C, H, W) and masks (b, Hm, Wm) from its host;
-        every rank needs the whole batch (template-axis sharding), so the queries travel GPU-to-GPU: two
-        all-gathers over NVLink instead of every rank uploading world x the data over PCIe.
-        -> (tar (world*b, C, H, W), mask (world*b, Hm, Wm)), rank-major; `out` = optional preallocated pair."""
+        every rank needs the whole batch (template-axis sharding), so the queries travel GPU-to-GPU over NVLink
+        instead of every rank uploading world x the data over PCIe: copy-engine peer pushes (`PeerGather`, see its
+        one-step-ahead contract) or, as fallback, two NCCL all-gathers.
+        -> (tar (world*b, C, H, W), mask (world*b, Hm, Wm)), rank-major; `out` = optional preallocated pair for the
+        NCCL form.  Use the RETURNED tensors.""" 
         if self.world == 1:
             return tar_local, mask_local
         tar_local, mask_local = tar_local.contiguous(), mask_local.contiguous()
+        if self._want_peer and tar_local.is_cuda and tar_local.dtype == torch.float32 and mask_local.dtype == torch.float32:
+            # copy-engine pushes through peer memory (PeerGather): no SMs, so it overlaps the contraction of the step
+            # before; the result is a view of this rank's exchange buffer (`out` is not used)
+            if self._gather is None or self._gather.tar_shape != tuple(tar_local.shape) \
+                    or self._gather.mask_shape != tuple(mask_local.shape):
+                try:
+                    self._gather = PeerGather(tar_local.shape, mask_local.shape, self.group, tar_local.device)
+                except RuntimeError as exc:
+                    import warnings
+                    warnings.warn(f"picopose_b200: peer-memory query gather unavailable ({exc}); using NCCL all-gathers")
+                    self._want_peer = False
+            if self._gather is not None:
+                return self._gather.gather(tar_local, mask_local)
         if out is None:
             out = (tar_local.new_empty((self.world * tar_local.shape[0],) + tuple(tar_local.shape[1:])),
                    mask_local.new_empty((self.world * mask_local.shape[0],) + tuple(mask_local.shape[1:])))

@@ -660,3 +660,42 @@ def test_topk_exchange_three_ranks_on_one_gpu():
         torch.cuda.synchronize()
         for b in bufs:
             lib.pp_xchg_destroy(b)
+
+
+def test_peer_gather_primitives_two_ranks_on_one_gpu():
+    """pp_xchg_push / pp_xchg_signal / pp_xchg_wait with two 'ranks' on one GPU (two buffers, two streams): every rank
+    copies its slice into slot [rank] of both buffers, flags it, and waits for both flags of its own buffer; afterwards
+    both buffers hold both slices.  Two epochs, flags at different offsets (the two parities)."""
+    import ctypes as C
+    lib = _lib.load()
+    world, n = 2, 4096
+    flag_bytes, slot = 256, n * 4
+    nbytes = flag_bytes + world * slot
+    bufs = []
+    for _ in range(world):
+        buf, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
+        bufs.append(buf.value)
+    peers_host = (C.c_void_p * world)(*bufs)
+    peers_dev = torch.tensor(bufs, dtype=torch.int64, device=DEV)
+    streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
+    try:
+        for epoch in (1, 2):
+            par = epoch & 1
+            slices = [torch.full((n,), float(10 * epoch + r), device=DEV) for r in range(world)]
+            torch.cuda.synchronize()
+            for r in range(world):
+                st = streams[r].cuda_stream
+                _lib.check(lib.pp_xchg_push(_lib.ptr(slices[r]), slot, peers_host, world, flag_bytes + r * slot, st), "pp_xchg_push")
+                _lib.check(lib.pp_xchg_signal(_lib.ptr(peers_dev), par * world * 4, r, world, epoch, st), "pp_xchg_signal")
+                _lib.check(lib.pp_xchg_wait(bufs[r], par * world * 4, world, epoch, st), "pp_xchg_wait")
+            torch.cuda.synchronize()
+            _lib.check_device_faults()
+            from picopose_b200.sharded import _DeviceView
+            for r in range(world):
+                got = torch.as_tensor(_DeviceView(bufs[r] + flag_bytes, (world, n)), device=DEV)
+                assert got[0].eq(10 * epoch + 0).all() and got[1].eq(10 * epoch + 1).all()
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            lib.pp_xchg_destroy(b)
