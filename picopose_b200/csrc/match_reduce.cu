@@ -503,14 +503,12 @@ extern "C" int pp_match_templates_dense(const float* src_feats, int64_t G, const
     const int rc = prepare_query_impl(tar_feat, tar_mask, B, C, H, W, Hm, Wm, mode, ws + w.q_prep,
                                       reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, ws + w.keys,
                                       pp_match_scores_workspace(B, N, T), fj->side);
-    const cudaError_t e0 = cudaSuccess;
     const int rc2 = pp_match_prepare(src_feats, G * N, C, T, mode, 0, bank_prep, bank_rnorm, stream);
     // join unconditionally so that the side stream never outlives the call's ordering on `stream`
     const cudaError_t e1 = cudaEventRecord(fj->join, fj->side);
     const cudaError_t e2 = cudaStreamWaitEvent(st, fj->join, 0);
     if (rc) return rc;
     if (rc2) return rc2;
-    PP_CUDA(e0);
     PP_CUDA(e1);
     PP_CUDA(e2);
     const bool rank_it = k > 0 && out_score && out_idx;
