@@ -129,17 +129,8 @@ class PeerExchange:
     def close(self):
         """Collective: unmap the peers' buffers, then free the own one."""
         from . import _lib
-        lib = _lib.load()
-        torch.cuda.synchronize(self.device)
-        dist.barrier(self.group)
-        with torch.cuda.device(self.device):
-            for p in self._opened:
-                lib.pp_xchg_close(p)
-            self._opened = []
-            dist.barrier(self.group)
-            if self._own is not None:
-                lib.pp_xchg_destroy(self._own)
-                self._own = None
+        _close_peers(_lib.load(), self.group, self.device, self._own, self._opened)
+        self._own, self._opened = None, []
 
 
 class _DeviceView:
@@ -171,6 +162,18 @@ def _open_peers(lib, group, nbytes: int, device):
                 opened.append(p.value)
                 ptrs.append(p.value)
     return buf.value, ptrs, opened
+
+
+def _close_peers(lib, group, device, own, opened):
+    """Collective: unmap the peers' buffers, then free the own one (nobody frees what a peer still has mapped)."""
+    torch.cuda.synchronize(device)
+    dist.barrier(group)
+    with torch.cuda.device(device):
+        for p in opened:
+            lib.pp_xchg_close(p)
+        dist.barrier(group)
+        if own is not None:
+            lib.pp_xchg_destroy(own)
 
 
 class PeerGather:
@@ -235,6 +238,12 @@ class PeerGather:
         tar = torch.as_tensor(_DeviceView(self._own + t_off, (self.world * b,) + self.tar_shape[1:]), device=self.device)
         mask = torch.as_tensor(_DeviceView(self._own + m_off, (self.world * b,) + self.mask_shape[1:]), device=self.device)
         return tar, mask
+
+    def close(self):
+        """Collective; tensors returned by `gather` must not be used afterwards."""
+        from . import _lib
+        _close_peers(_lib.load(), self.group, self.device, self._own, self._opened)
+        self._own, self._opened = None, []
 
 
 class ShardedMatcher:
@@ -309,6 +318,13 @@ class ShardedMatcher:
         if xchg is not None:
             return xchg.exchange(sim, topk, idx_offset=self.lo)
         return merge_topk(topk_pairs(sim, topk, idx_offset=self.lo), topk, self.group, self.merge)
+
+    def close(self):
+        """Collective: releases the peer-memory buffers (exchange + gather) if any were created."""
+        for obj in (self._xchg, self._gather):
+            if obj is not None:
+                obj.close()
+        self._xchg = self._gather = None
 
     def _peer_exchange_for(self, sim: torch.Tensor, k: int):
         """The PeerExchange to use for this call, created (collectively) on first use; None = all-gather form."""
