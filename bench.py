@@ -12,7 +12,13 @@ bf16 tensor-core contraction -- through the reference-facing signature
 resident in HBM (so the normalise/cast prologue is INSIDE every step), followed by the stage-3
 `CorrLookup` of that detection on the FlowDecoder ladder (16^2/L1, 32^2/L2, 64^2/L3, r=2).
 N>1: N detections of N objects per step, every object's bank sharded over the N ranks along the view
-axis (per-rank work constant = weak scaling), local top-k, one NCCL all-gather, merge.
+axis (per-rank work constant = weak scaling); local top-k, exchange and merge are one kernel over NVLink
+peer memory, and in the end-to-end loop every rank uploads its own detection and the batch is assembled
+with copy-engine peer pushes (picopose_b200/sharded.py; NCCL all-gathers when peer mappings are unavailable).
+
+Extra keys beside the contract's: `roofline` (the tensor-core contraction, timed by its own CUDA events),
+`roofline_lookup` (N=1: the stage-3 lookup at the configs[3] shape against the HBM copy peak, outside the
+timed step), `warm_bank` (template bank prepared once), `cpu_baseline` (oracle port on the host cores).
 """
 from __future__ import annotations
 
@@ -386,13 +392,13 @@ def run_ours(args):
                                 "/".join("%d^2xL%d" % (h, L) for h, L in CFG["ladder"]), CFG["radius"])),
                 "detections_per_step": world, "views": CFG["N"], "views_per_rank": hi - lo, "C": CFG["C"],
                 "patches": CFG["H"] ** 2, "topk": k, "mode": M.default_mode(),
-                "parallelism": "1 GPU" if world == 1 else "template bank sharded x%d + NCCL all-gather top-k merge" % world,
+                "parallelism": "1 GPU" if world == 1 else "template bank sharded x%d + top-k exchange over NVLink peer memory" % world,
                 "l2": "per-step inputs (%.0f MB fp32 template features) exceed the 126 MB L2; no explicit flush"
                       % (src_d.numel() * 4 / 1e6),
                 "e2e_inputs": ("query features + mask copied from pinned host memory every step; template features are "
                                "device-resident fp32 (as in run_test.py:121-134) and re-prepared every step"
                                + ("" if world == 1 else "; each rank uploads its own detection (h2d_bytes_per_step is the "
-                                  "whole job's) and the batch is all-gathered over NVLink inside the timed region")),
+                                  "whole job's) and the batch is gathered over NVLink (copy-engine peer pushes) inside the timed region")),
             },
             "clocks": clocks,
             "e2e": {"value": world * 1e3 / (e2e_ms_total / args.steps), "unit": "detections/s",
