@@ -684,11 +684,12 @@ def test_peer_gather_primitives_two_ranks_on_one_gpu():
             par = epoch & 1
             slices = [torch.full((n,), float(10 * epoch + r), device=DEV) for r in range(world)]
             torch.cuda.synchronize()
-            for r in range(world):
-                st = streams[r].cuda_stream
+            for r in range(world):                       # every rank's pushes and flags first, then the waits: no
+                st = streams[r].cuda_stream              # ordering of the streams can make a wait starve a push
                 _lib.check(lib.pp_xchg_push(_lib.ptr(slices[r]), slot, peers_host, world, flag_bytes + r * slot, st), "pp_xchg_push")
                 _lib.check(lib.pp_xchg_signal(_lib.ptr(peers_dev), par * world * 4, r, world, epoch, st), "pp_xchg_signal")
-                _lib.check(lib.pp_xchg_wait(bufs[r], par * world * 4, world, epoch, st), "pp_xchg_wait")
+            for r in range(world):
+                _lib.check(lib.pp_xchg_wait(bufs[r], par * world * 4, world, epoch, streams[r].cuda_stream), "pp_xchg_wait")
             torch.cuda.synchronize()
             _lib.check_device_faults()
             from picopose_b200.sharded import _DeviceView
