@@ -310,7 +310,9 @@ def run_ours(args):
                 else:
                     own[sl][0].copy_(own_tar_h, non_blocking=True)
                     own[sl][1].copy_(own_mask_h, non_blocking=True)
-                    cur = matcher.gather_queries(own[sl][0], own[sl][1], out=bufs[sl])   # ordered after the uploads, off the main stream
+                    # ordered after the uploads, off the main stream; the peer-memory form returns views of the exchange
+                    # buffer, the NCCL form fills the preallocated double buffer
+                    cur = matcher.gather_queries(own[sl][0], own[sl][1], out=None if matcher.uses_peer_memory else bufs[sl])
                 up_done[sl].record(copy_stream)
             main_stream.wait_event(up_done[sl])
             s, i, _ = step(cur[0], cur[1], src_d)

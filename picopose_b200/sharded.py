@@ -281,14 +281,14 @@ class ShardedMatcher:
         every rank needs the whole batch (template-axis sharding), so the queries travel GPU-to-GPU over NVLink
         instead of every rank uploading world x the data over PCIe: copy-engine peer pushes (`PeerGather`, see its
         one-step-ahead contract) or, as fallback, two NCCL all-gathers.
-        -> (tar (world*b, C, H, W), mask (world*b, Hm, Wm)), rank-major; `out` = optional preallocated pair for the
-        NCCL form.  Use the RETURNED tensors.""" 
+        -> (tar (world*b, C, H, W), mask (world*b, Hm, Wm)), rank-major; `out` = optional preallocated pair (filled
+        and returned; leave it out to get zero-copy views of the exchange buffer, valid until the gather after next)."""
         if self.world == 1:
             return tar_local, mask_local
         tar_local, mask_local = tar_local.contiguous(), mask_local.contiguous()
         if self._want_peer and tar_local.is_cuda and tar_local.dtype == torch.float32 and mask_local.dtype == torch.float32:
             # copy-engine pushes through peer memory (PeerGather): no SMs, so it overlaps the contraction of the step
-            # before; the result is a view of this rank's exchange buffer (`out` is not used)
+            # before; without `out` the result is a view of this rank's exchange buffer
             if self._gather is None or self._gather.tar_shape != tuple(tar_local.shape) \
                     or self._gather.mask_shape != tuple(mask_local.shape):
                 try:
@@ -298,7 +298,12 @@ class ShardedMatcher:
                     warnings.warn(f"picopose_b200: peer-memory query gather unavailable ({exc}); using NCCL all-gathers")
                     self._want_peer = False
             if self._gather is not None:
-                return self._gather.gather(tar_local, mask_local)
+                tar_all, mask_all = self._gather.gather(tar_local, mask_local)
+                if out is None:
+                    return tar_all, mask_all                       # zero-copy views of this rank's exchange buffer
+                out[0].copy_(tar_all)                              # a caller-provided pair is still filled
+                out[1].copy_(mask_all)
+                return out
         if out is None:
             out = (tar_local.new_empty((self.world * tar_local.shape[0],) + tuple(tar_local.shape[1:])),
                    mask_local.new_empty((self.world * mask_local.shape[0],) + tuple(mask_local.shape[1:])))
@@ -318,6 +323,11 @@ class ShardedMatcher:
         if xchg is not None:
             return xchg.exchange(sim, topk, idx_offset=self.lo)
         return merge_topk(topk_pairs(sim, topk, idx_offset=self.lo), topk, self.group, self.merge)
+
+    @property
+    def uses_peer_memory(self) -> bool:
+        """True while the exchange / gather go through NVLink peer memory (False: NCCL all-gather forms)."""
+        return self._want_peer
 
     def close(self):
         """Collective: releases the peer-memory buffers (exchange + gather) if any were created."""
