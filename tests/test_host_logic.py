@@ -205,3 +205,27 @@ def test_bank_handle_passes_the_reference_loop_operations_through():
                 lambda: picked[0], lambda: torch.cat([picked, picked])):
         with pytest.raises(NotImplementedError):
             bad()
+
+
+def test_column_tiling_rule_and_bench_accounting():
+    """The contraction cuts tv unmasked query patches into ceil(tv/256) column tiles of round_up(tv/tiles, 32) columns
+    (csrc/match_gemm.cu, decode_tile_prefix).  The rule must cover every patch, never exceed the UMMA N limit, never
+    produce an empty tile -- and bench.py's issued-FLOP accounting (executed_rows) must follow the same rule."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for tv in range(1, 1025):
+        tiles = (tv + 255) // 256
+        ncols = (-(-tv // tiles) + 31) // 32 * 32
+        assert 32 <= ncols <= 256 and ncols % 32 == 0
+        assert tiles * ncols >= tv > (tiles - 1) * ncols
+    H, step = 32, 224 // 32
+    masks = []
+    for tv in (1, 256, 257, 655, 1024):
+        m = torch.zeros(224, 224)
+        m[::step, ::step][:H, :H] = (torch.arange(H * H) < tv).view(H, H).float()
+        masks.append(m)
+    rows_exec, rows_unmasked = bench.executed_rows(torch.stack(masks), H)
+    assert rows_unmasked == 1 + 256 + 257 + 655 + 1024
+    assert rows_exec == 32 + 256 + 2 * 160 + 3 * 224 + 4 * 256
