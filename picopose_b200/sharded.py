@@ -183,10 +183,12 @@ class PeerGather:
     step i computes only runs in the gaps between kernels.  Here rank r copies its slice into slot r of every peer's
     buffer with `cudaMemcpyAsync` peer copies (no SM), a one-block kernel then writes the call's epoch into flag [r]
     of every peer, and a one-block kernel spins on the `world` flags of the own buffer; all on the caller's stream.
-    Slots are double-buffered by epoch parity.  Contract (same as for any double-buffered upload): a `gather` may run
-    at most one step ahead of the compute it feeds -- the stream it is issued on must be ordered after the `match`
-    (top-k exchange) that consumed the gather before the previous one; the exchange guarantees that every peer has
-    finished reading that parity.
+    Slots are double-buffered by epoch parity.  Contract: (1) a `gather` may run at most one step ahead of the compute it
+    feeds -- the stream it is issued on must be ordered after the `match` (top-k exchange) that consumed the gather before
+    the previous one, as any double-buffered upload loop is; that exchange proves every peer has passed the query
+    prologue of that step.  (2) The gathered tensors are views of this rank's buffer and only the query prologue of the
+    step's `match` may read them: a faster peer is free to overwrite that parity as soon as the exchange of the same
+    step has completed.  Pass `out=` to `ShardedMatcher.gather_queries` for a private copy.
     """
 
     def __init__(self, tar_slice_shape, mask_slice_shape, group=None, device=None):
@@ -216,8 +218,8 @@ class PeerGather:
         return base, base + 256 * ((self.tar_region + 255) // 256)
 
     def gather(self, tar_local: torch.Tensor, mask_local: torch.Tensor):
-        """-> (tar (world*b, ...), mask (world*b, ...)) views of this rank's buffer, valid in stream order on the
-        current stream (and on any stream that waits for it) until the gather after next."""
+        """-> (tar (world*b, ...), mask (world*b, ...)) views of this rank's buffer, complete in stream order on the
+        current stream (and on any stream that waits for it); see the class contract for how long they stay valid."""
         from . import _lib
         lib = _lib.load()
         assert tuple(tar_local.shape) == self.tar_shape and tuple(mask_local.shape) == self.mask_shape
@@ -282,7 +284,8 @@ class ShardedMatcher:
         instead of every rank uploading world x the data over PCIe: copy-engine peer pushes (`PeerGather`, see its
         one-step-ahead contract) or, as fallback, two NCCL all-gathers.
         -> (tar (world*b, C, H, W), mask (world*b, Hm, Wm)), rank-major; `out` = optional preallocated pair (filled
-        and returned; leave it out to get zero-copy views of the exchange buffer, valid until the gather after next)."""
+        and returned; leave it out to get zero-copy views of the exchange buffer, which only the following `match` may
+        read -- see `PeerGather`)."""
         if self.world == 1:
             return tar_local, mask_local
         tar_local, mask_local = tar_local.contiguous(), mask_local.contiguous()
