@@ -2,6 +2,11 @@
 # One gpurun call that re-validates and re-measures everything on a single B200: GPU tests, smoke, both bench arms,
 # the lookup sweep, the ncu launch list and an `ncu --set full` capture of one whole timed step (outputs in gpurun_out/).
 #   gpurun --timeout 1800 -- 'bash tools/gpu_final_pass.sh'
+# Multi-GPU lines (N = 2, 4, 8; one JSON line on stdout, NCCL's banner goes to stderr):
+#   gpurun --gpus N -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+#       --master-port 29500 bench.py --gpus N > gpurun_out/bench_${TAG}_${N}gpu.json'
+#   ... tools/bench_configs.py --detections 512 --json gpurun_out/config5_8gpu_${TAG}.json        (configs[4], 8 GPUs)
+# Microbenchmarks behind DESIGN 3.1 / 3.4: tools/microbench/{dram_gran,partition,subset_stream}.cu (+ run.sh).
 set -x
 cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
