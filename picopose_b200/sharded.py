@@ -202,16 +202,26 @@ class PeerGather:
         self.tar_bytes = 4 * int(torch.Size(self.tar_shape).numel())
         self.mask_bytes = 4 * int(torch.Size(self.mask_shape).numel())
         assert self.tar_bytes % 16 == 0 and self.mask_bytes % 16 == 0
-        self.flag_bytes = 256 * ((2 * self.world * 4 + 255) // 256)
-        self.tar_region = self.world * self.tar_bytes
-        self.mask_region = 256 * ((self.world * self.mask_bytes + 255) // 256)
-        self.parity_bytes = 256 * ((self.tar_region + 255) // 256) + self.mask_region
-        nbytes = self.flag_bytes + 2 * self.parity_bytes
+        lay = self.layout(self.world, self.tar_bytes, self.mask_bytes)
+        self.flag_bytes, self.tar_region, self.parity_bytes = lay["flag_bytes"], lay["tar_region"], lay["parity_bytes"]
+        nbytes = lay["total"]
         self._own, ptrs, self._opened = _open_peers(lib, group, nbytes, self.device)
         self._peers_host = (C.c_void_p * self.world)(*ptrs)
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
         self.epoch = 0
         dist.barrier(group)
+
+    @staticmethod
+    def layout(world: int, tar_bytes: int, mask_bytes: int) -> dict:
+        """Byte layout of one rank's buffer: flags [2][world] u32 | parity 0: tar slots, mask slots | parity 1: ...;
+        every region starts on a 256-byte boundary."""
+        up = lambda x: 256 * ((x + 255) // 256)                                    # noqa: E731
+        flag_bytes = up(2 * world * 4)
+        tar_region = world * tar_bytes
+        mask_off = up(tar_region)
+        parity_bytes = mask_off + up(world * mask_bytes)
+        return {"flag_bytes": flag_bytes, "tar_region": tar_region, "mask_off": mask_off, "parity_bytes": parity_bytes,
+                "total": flag_bytes + 2 * parity_bytes}
 
     def _offsets(self, par: int):
         base = self.flag_bytes + par * self.parity_bytes

@@ -229,3 +229,19 @@ def test_column_tiling_rule_and_bench_accounting():
     rows_exec, rows_unmasked = bench.executed_rows(torch.stack(masks), H)
     assert rows_unmasked == 1 + 256 + 257 + 655 + 1024
     assert rows_exec == 32 + 256 + 2 * 160 + 3 * 224 + 4 * 256
+
+
+def test_peer_gather_buffer_layout():
+    """PeerGather.layout: flag array, then two parities of (tar slots, mask slots); regions are 256-byte aligned, do
+    not overlap and the slot offsets used by `gather` stay inside their regions."""
+    from picopose_b200.sharded import PeerGather
+    for world, tar_b, mask_b in [(2, 4 * 1024 * 32 * 32, 4 * 224 * 224), (8, 4 * 1024 * 32 * 32, 4 * 224 * 224), (3, 4 * 48, 4 * 20)]:
+        lay = PeerGather.layout(world, tar_b, mask_b)
+        assert lay["flag_bytes"] % 256 == 0 and lay["flag_bytes"] >= 2 * world * 4
+        assert lay["mask_off"] % 256 == 0 and lay["mask_off"] >= world * tar_b
+        assert lay["parity_bytes"] % 256 == 0 and lay["parity_bytes"] >= lay["mask_off"] + world * mask_b
+        assert lay["total"] == lay["flag_bytes"] + 2 * lay["parity_bytes"]
+        for par in (0, 1):
+            base = lay["flag_bytes"] + par * lay["parity_bytes"]
+            assert base + (world - 1) * tar_b + tar_b <= base + lay["mask_off"]
+            assert base + lay["mask_off"] + world * mask_b <= lay["flag_bytes"] + (par + 1) * lay["parity_bytes"]
