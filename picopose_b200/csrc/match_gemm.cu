@@ -26,6 +26,7 @@
 #include "pp_ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <mutex>
 
 namespace pp {
 
@@ -473,11 +474,21 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 
 static int* g_fault_host = nullptr;  // pinned, host-mapped: survives a trapped kernel
 static int* g_fault_dev = nullptr;
+static std::mutex g_fault_mutex;  // first use may come from several host threads at once
 static int ensure_fault_buffer() {
-    if (g_fault_host) return PP_OK;
-    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_fault_host), 64 * sizeof(int), cudaHostAllocMapped));
-    for (int i = 0; i < 64; ++i) g_fault_host[i] = 0;
-    PP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_fault_dev), g_fault_host, 0));
+    std::lock_guard<std::mutex> lock(g_fault_mutex);
+    if (g_fault_dev) return PP_OK;
+    int* host = nullptr;
+    int* dev = nullptr;
+    PP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&host), 64 * sizeof(int), cudaHostAllocMapped));
+    for (int i = 0; i < 64; ++i) host[i] = 0;
+    const cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), host, 0);
+    if (e != cudaSuccess) {
+        cudaFreeHost(host);
+        return fail(PP_ERR_LAUNCH, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e));
+    }
+    g_fault_host = host;
+    g_fault_dev = dev;
     return PP_OK;
 }
 
