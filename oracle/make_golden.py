@@ -76,6 +76,16 @@ def main():
             m = torch.ones(B, 224, 224)
         elif mask == "zeros":
             m = torch.zeros(B, 224, 224)
+        elif mask == "prefix":
+            # detection 0: the first 257 patches unmasked, detection 1: the last 700 (patch 0 masked) -- unmasked counts
+            # on both sides of the 256-column tile boundaries of the CUDA contraction (match_gemm.cu)
+            m = torch.zeros(B, 224, 224)
+            step = 224 // H
+            for b, n_on in enumerate((257, 700)):
+                on = torch.arange(H * H) < n_on
+                if b == 1:
+                    on = on.flip(0)
+                m[b, ::step, ::step][:H, :H] = on.view(H, H).float()
         if special == "identical":          # query == template 0 exactly
             tar = src[:, 0].clone()
         src_masks = torch.ones(B, N, 224, 224)[:, :, :1, :1]  # unused by the reference
@@ -95,6 +105,7 @@ def main():
     match_case("ones", 1, 6, 16, 4, 5, seed=3, mask="ones")
     match_case("allmasked", 1, 6, 16, 4, 2, seed=4, mask="zeros")
     match_case("identical", 1, 6, 16, 4, 2, seed=5, mask="ones", special="identical")
+    match_case("tiles", 2, 2, 16, 32, 2, seed=6, mask="prefix")
 
     # ---------------- stage-2 similarity volume ----------------
     for name, B, C, H, seed in (("small", 2, 16, 4, 10), ("medium", 1, 32, 8, 11)):

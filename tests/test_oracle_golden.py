@@ -17,7 +17,7 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
-MATCH = ["small", "medium", "bern", "ones", "allmasked", "identical"]
+MATCH = ["small", "medium", "bern", "ones", "allmasked", "identical", "tiles"]   # tiles: 32x32 patches, prefix masks
 
 
 @pytest.mark.parametrize("name", MATCH)
