@@ -117,19 +117,45 @@ def visible_nvml_index(local_rank):
     return local_rank
 
 
-def make_inputs(world, rank, seed=0):
+def workload_config(world):
+    """The `config` object of the JSON line -- built by this one function for BOTH arms (ours and --impl reference), so the
+    driver sees the same workload on both sides."""
+    from picopose_b200 import matching as M
+    from picopose_b200.sharded import shard_range
+    lo, hi = shard_range(CFG["N"], 0, world)
+    return {
+        "workload": ("configs[1]: %d detection(s) x %d template views, %dx%d patches, C=%d; stage-1 "
+                     "matching_templates through the frozen signature on fp32 template features (normalise/cast "
+                     "prologue inside the step, top-%d included) + stage-3 CorrLookup ladder %s r=%d"
+                     % (world, CFG["N"], CFG["H"], CFG["H"], CFG["C"], CFG["topk"],
+                        "/".join("%d^2xL%d" % (h, L) for h, L in CFG["ladder"]), CFG["radius"])),
+        "detections_per_step": world, "views": CFG["N"], "views_per_rank": hi - lo, "C": CFG["C"],
+        "patches": CFG["H"] ** 2, "topk": CFG["topk"], "mode": M.default_mode(),
+        "parallelism": "1 GPU" if world == 1 else "template bank sharded x%d + top-k exchange over NVLink peer memory" % world,
+        "l2": "per-step inputs (%.0f MB fp32 template features per GPU) exceed the 126 MB L2; no explicit flush"
+              % (world * (hi - lo) * CFG["C"] * CFG["H"] ** 2 * 4 / 1e6),
+        "e2e_inputs": ("query features + mask copied from pinned host memory every step; template features are "
+                       "device-resident fp32 (as in run_test.py:121-134) and re-prepared every step"
+                       + ("" if world == 1 else "; each rank uploads its own detection (h2d_bytes_per_step is the "
+                          "whole job's) and the batch is gathered over NVLink (copy-engine peer pushes) inside the timed region")),
+    }
+
+
+def make_inputs(world, rank, seed=0, keep_full=False):
     """Synthetic step inputs on the CPU (pinned): world detections of world objects, this rank's view shard."""
     from picopose_b200 import synth
     from picopose_b200.sharded import shard_range
     N, C, H = CFG["N"], CFG["C"], CFG["H"]
     lo, hi = shard_range(N, rank, world)
     # one planted bank per object; detection d looks at object d.  Every rank draws the same tensors and keeps its slice.
-    shards, tars, planted = [], [], []
+    shards, tars, planted, full0 = [], [], [], None
     for obj in range(world):
         src, tar, pl = synth.planted_match_inputs(1, N, C, H, seed=seed + obj)
         shards.append(src[0, lo:hi].clone())
         tars.append(tar[0])
         planted.append(pl[0])
+        if keep_full and obj == 0:
+            full0 = src                                  # (1, N, C, H, H): object 0's whole bank, for the sharded == single check
         del src
     src_shard = torch.stack(shards)                       # (world, hi-lo, C, H, H)
     tar = torch.stack(tars)                               # (world, C, H, H)
@@ -138,7 +164,7 @@ def make_inputs(world, rank, seed=0):
     for (h, L) in CFG["ladder"]:                           # this rank's own detection (detection-axis sharding)
         pyr, flow = synth.lookup_inputs(1, h, L, seed=seed + 100 + rank, flow_sigma=2.0)
         lookups.append((pyr, flow))
-    return src_shard, tar, mask, lookups, torch.stack(planted), (lo, hi)
+    return src_shard, tar, mask, lookups, torch.stack(planted), (lo, hi), full0
 
 
 def executed_rows(mask, H):
@@ -219,7 +245,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    src_shard, tar, mask, lookups, planted, (lo, hi) = make_inputs(world, rank)
+    src_shard, tar, mask, lookups, planted, (lo, hi), full0 = make_inputs(world, rank, keep_full=(rank == 0))
     tar_h, mask_h = tar.pin_memory(), mask.pin_memory()
     src_d = src_shard.to(dev)                               # fp32 template features, resident (like run_test.py:121-134)
     tar_d, mask_d = tar_h.to(dev), mask_h.to(dev)
@@ -245,6 +271,21 @@ def run_ours(args):
     _lib.check_device_faults()
     if not SMALL:
         assert idx.cpu().tolist() == planted[:, :k].tolist(), (idx.cpu().tolist(), planted[:, :k].tolist())
+    sharded_check = None
+    if rank == 0 and full0 is not None:
+        # sharded == single GPU: detection 0 against its WHOLE bank in one unsharded call on this GPU must give the
+        # ranking and scores the N-rank exchange produced (every (detection, view) score is computed by the same kernel
+        # on the same operands, so the agreement is exact, not approximate)
+        full_d = full0.to(dev)
+        s1, i1 = M.matching_templates(full_d, tar_d[0:1], None, mask_d[0:1], topk=k)
+        dense1 = M.template_scores(full_d, tar_d[0:1], mask_d[0:1])
+        torch.cuda.synchronize()
+        assert torch.equal(i1[0].cpu(), idx[0].cpu()), ("sharded top-k != single-GPU top-k", i1.tolist(), idx[0].tolist())
+        assert torch.equal(s1[0].cpu(), score[0].cpu()), ("sharded scores != single-GPU scores", s1.tolist(), score[0].tolist())
+        assert torch.equal(torch.topk(dense1, k, dim=1).indices[0].cpu(), idx[0].cpu())
+        sharded_check = "detection 0: %d-rank sharded top-%d (indices and scores) == unsharded single-GPU result, bit for bit" % (world, k)
+        del full_d, dense1
+    del full0
 
     for _ in range(args.warmup):
         step(tar_d, mask_d, src_d)
@@ -386,22 +427,7 @@ def run_ours(args):
             "metric": "detections/sec", "value": world * 1e3 / ms_step, "unit": "detections/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": ("configs[1]: %d detection(s) x %d template views, %dx%d patches, C=%d; stage-1 "
-                             "matching_templates through the frozen signature on fp32 template features resident in "
-                             "HBM (normalise/cast prologue inside the step) + stage-3 CorrLookup ladder %s r=%d"
-                             % (world, CFG["N"], CFG["H"], CFG["H"], CFG["C"],
-                                "/".join("%d^2xL%d" % (h, L) for h, L in CFG["ladder"]), CFG["radius"])),
-                "detections_per_step": world, "views": CFG["N"], "views_per_rank": hi - lo, "C": CFG["C"],
-                "patches": CFG["H"] ** 2, "topk": k, "mode": M.default_mode(),
-                "parallelism": "1 GPU" if world == 1 else "template bank sharded x%d + top-k exchange over NVLink peer memory" % world,
-                "l2": "per-step inputs (%.0f MB fp32 template features) exceed the 126 MB L2; no explicit flush"
-                      % (src_d.numel() * 4 / 1e6),
-                "e2e_inputs": ("query features + mask copied from pinned host memory every step; template features are "
-                               "device-resident fp32 (as in run_test.py:121-134) and re-prepared every step"
-                               + ("" if world == 1 else "; each rank uploads its own detection (h2d_bytes_per_step is the "
-                                  "whole job's) and the batch is gathered over NVLink (copy-engine peer pushes) inside the timed region")),
-            },
+            "config": workload_config(world),
             "clocks": clocks,
             "e2e": {"value": world * 1e3 / (e2e_ms_total / args.steps), "unit": "detections/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_enqueue_ms_per_step": e2e_host[0]},
@@ -433,6 +459,8 @@ def run_ours(args):
             "matches_per_sec": world * CFG["N"] * CFG["H"] ** 2 * 1e3 / ms_step,
             "lookup_algorithmic_bytes_per_step": lookup_bytes,
         }
+        if sharded_check:
+            line["sharded_equals_single_gpu"] = sharded_check
         if lookup_roof is not None:
             line["roofline_lookup"] = lookup_roof
         if world == 1 and not args.no_cpu_baseline:
@@ -443,86 +471,131 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _cpu_inputs():
-    from picopose_b200 import synth
-    N, C, H = CFG["N"], CFG["C"], CFG["H"]
-    src, tar, _ = synth.planted_match_inputs(1, min(N, 24), C, H, seed=0)
-    mask = synth.disc_mask(1)
-    lookups = [synth.lookup_inputs(1, h, L, seed=100, flow_sigma=2.0) for (h, L) in CFG["ladder"]]
-    return src, tar, mask, lookups
+def _reference_impl():
+    """-> (matching_templates, corr_lookup(pyr, flow, r), kind).  `kind` is "reference" when PICOPOSE_REFERENCE names a
+    PicoPose tree on this box (its own utils/matching.py and utils/corr_lookup.py are imported and timed), else "port":
+    the torch-CPU restatement under oracle/ (the reference is a Python repository that does not travel to the GPU box)."""
+    ref = os.environ.get("PICOPOSE_REFERENCE")
+    if ref and os.path.isdir(os.path.join(ref, "utils")):
+        import importlib
+        import warnings
+        warnings.filterwarnings("ignore")
+        saved = list(sys.path)
+        sys.path.insert(0, ref)
+        try:
+            for name in ("utils", "utils.matching", "utils.corr_lookup"):
+                sys.modules.pop(name, None)
+            rm = importlib.import_module("utils.matching")
+            rl = importlib.import_module("utils.corr_lookup")
+            if os.path.abspath(rm.__file__).startswith(os.path.abspath(ref)):
+                lookups = {}
 
-
-def _cpu_pass(src, tar, mask, lookups, n_s):
-    """One bounded sample of the step on the CPU: n_s views of stage-1 + the full lookup ladder -> (t_match, t_lookup)."""
+                def ref_lookup(pyr, flow, r):
+                    mod = lookups.setdefault(r, rl.CorrLookup(radius=r))
+                    return mod(pyr, flow)
+                return rm.matching_templates, ref_lookup, "reference"
+        finally:
+            sys.path[:] = saved
     from oracle import corr_lookup_oracle as OL
     from oracle import matching_oracle as OM
+    return OM.matching_templates, OL.corr_lookup, "port"
+
+
+def _cpu_inputs(world=1):
+    """The GPU arm's step inputs on the host: `world` detections, each with its own full 162-view bank, mask, lookup ladder."""
+    from picopose_b200 import synth
+    N, C, H = CFG["N"], CFG["C"], CFG["H"]
+    dets = []
+    for d in range(world):
+        src, tar, planted = synth.planted_match_inputs(1, N, C, H, seed=d)
+        lookups = [synth.lookup_inputs(1, h, L, seed=100 + d, flow_sigma=2.0) for (h, L) in CFG["ladder"]]
+        dets.append((src, tar, synth.disc_mask(1), lookups, planted))
+    return dets
+
+
+def _cpu_step(dets, match_fn, lookup_fn):
+    """One FULL step of the GPU arm's workload on the host cores: for every detection the complete
+    matching_templates (all views, top-k included) and its lookup ladder -> (t_match, t_lookup, last top-k indices)."""
+    tm = tl = 0.0
+    idx = None
     with torch.no_grad():
-        t = time.perf_counter()
-        OM.template_scores(src[:, :n_s], tar, mask)
-        t_match = time.perf_counter() - t
-        t = time.perf_counter()
-        for pyr, flow in lookups:
-            OL.corr_lookup(pyr, flow, CFG["radius"])
-        t_look = time.perf_counter() - t
-    return t_match, t_look
+        for src, tar, mask, lookups, _ in dets:
+            t = time.perf_counter()
+            _, idx = match_fn(src, tar, None, mask, CFG["topk"])
+            tm += time.perf_counter() - t
+            t = time.perf_counter()
+            for pyr, flow in lookups:
+                lookup_fn(pyr, flow, CFG["radius"])
+            tl += time.perf_counter() - t
+    return tm, tl, idx
 
 
-def _cpu_describe(n_s, t_match, t_look, cores):
-    N = CFG["N"]
-    t_step = t_match * N / n_s + t_look
-    return {"value": 1.0 / t_step, "unit": "detections/s", "cores": cores, "kind": "port",
-            "sample": "%d of %d views timed (%.3f s, scaled linearly; per-view cost is constant) + full lookup ladder "
-                      "(%.4f s); torch-CPU fp32 restatement (oracle/) of utils/matching.py + utils/corr_lookup.py, "
-                      "%d threads" % (n_s, N, t_match, t_look, cores),
-            "seconds_per_detection": t_step}
+def _cpu_describe(world, reps, t_match, t_look, cores, kind):
+    t_step = t_match + t_look
+    what = ("the reference's own utils/matching.py + utils/corr_lookup.py (PICOPOSE_REFERENCE)" if kind == "reference"
+            else "torch-CPU fp32 restatement (oracle/) of utils/matching.py + utils/corr_lookup.py")
+    return {"value": world / t_step, "unit": "detections/s", "cores": cores, "kind": kind,
+            "sample": "%d full step(s) timed, mean: %d detection(s) x all %d views through matching_templates incl. top-%d "
+                      "(%.3f s) + full lookup ladder (%.4f s); nothing extrapolated; %s, %d threads"
+                      % (reps, world, CFG["N"], CFG["topk"], t_match, t_look, what, cores),
+            "seconds_per_detection": t_step / world}
 
 
 def cpu_baseline(budget_s=15.0):
-    """Times the CPU restatement of the reference path (oracle/, torch-CPU, all host threads) on a bounded
-    sample of the step: n_s of the 162 views (per-view cost is constant) + the full lookup ladder."""
+    """N=1 leg of our own line: the CPU path of the same step on the host cores, whole step (all 162 views), a few
+    repetitions inside `budget_s`."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    src, tar, mask, lookups = _cpu_inputs()
-    _cpu_pass(src, tar, mask, lookups, 2)                                   # warm-up
-    per_view = _cpu_pass(src, tar, mask, lookups, 2)[0] / 2
-    n_s = int(max(2, min(src.shape[1], budget_s / max(per_view, 1e-6) / 2)))
-    best = min((_cpu_pass(src, tar, mask, lookups, n_s) for _ in range(2)), key=lambda x: x[0])
-    return _cpu_describe(n_s, best[0], best[1], cores)
+    match_fn, lookup_fn, kind = _reference_impl()
+    dets = _cpu_inputs(1)
+    t0 = time.perf_counter()
+    _cpu_step(dets, match_fn, lookup_fn)                                     # warm-up
+    per = max(time.perf_counter() - t0, 1e-3)
+    reps = int(max(1, min(20, budget_s / per - 1)))
+    tm = tl = 0.0
+    for _ in range(reps):
+        a, b, idx = _cpu_step(dets, match_fn, lookup_fn)
+        tm += a
+        tl += b
+    if not SMALL:
+        assert idx[0].tolist() == dets[-1][4][0, :CFG["topk"]].tolist()
+    return _cpu_describe(1, reps, tm / reps, tl / reps, cores, kind)
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU path (oracle port; the reference is Python and cannot
-    travel to the GPU box) on the host cores, same config/metric.  Rank 0 only; other ranks exit."""
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores, same config and
+    metric as our arm: every step is the FULL workload (all views of every detection, top-k included, lookup ladder).
+    The reference's own modules are timed when PICOPOSE_REFERENCE points at a PicoPose tree (kind "reference"); on the
+    GPU box that tree does not exist and the oracle port runs (kind "port").  Rank 0 only; other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    src, tar, mask, lookups = _cpu_inputs()
-    _cpu_pass(src, tar, mask, lookups, 2)
-    per_view = _cpu_pass(src, tar, mask, lookups, 2)[0] / 2
-    total = max(1, args.warmup + args.steps)
-    n_s = int(max(2, min(src.shape[1], (150.0 / total) / max(per_view, 1e-6))))   # whole run within a few minutes
+    match_fn, lookup_fn, kind = _reference_impl()
+    dets = _cpu_inputs(world)
     for _ in range(args.warmup):
-        _cpu_pass(src, tar, mask, lookups, n_s)
+        _cpu_step(dets, match_fn, lookup_fn)
     tm = tl = 0.0
     for _ in range(args.steps):
-        a, b = _cpu_pass(src, tar, mask, lookups, n_s)
+        a, b, idx = _cpu_step(dets, match_fn, lookup_fn)
         tm += a
         tl += b
-    desc = _cpu_describe(n_s, tm / args.steps, tl / args.steps, cores)
+    if not SMALL:
+        assert idx[0].tolist() == dets[-1][4][0, :CFG["topk"]].tolist()      # the planted ranking comes out here too
+    desc = _cpu_describe(world, args.steps, tm / args.steps, tl / args.steps, cores, kind)
     v = desc["value"]
     line = {
         "impl": "reference", "metric": "detections/sec", "value": v, "unit": "detections/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": world * 1e3 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1 detection x %d template views, %dx%d patches, C=%d; stage-1 match + "
-                               "stage-3 lookup ladder on the host CPU (bounded sample per step, see cpu_baseline.sample)"
-                               % (CFG["N"], CFG["H"], CFG["H"], CFG["C"])},
+        "config": workload_config(world),
         "cpu_baseline": desc,
         "e2e": {"value": v, "unit": "detections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "arm_note": "`config` is the GPU arm's (same function builds it); this arm runs that workload on %d host threads "
+                    "in fp32, kind=%s" % (cores, kind),
     }
     emit(line)
 

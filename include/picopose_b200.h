@@ -49,7 +49,8 @@ typedef enum pp_mode {
 
 PP_API int pp_version(void);
 PP_API const char* pp_last_error(void);
-/* Reads and clears the device-side fault flag (synchronises the device). 0 = no fault. */
+/* Reads and clears the device-side fault record (synchronises the device). 0 = no fault; PP_ERR_KERNEL with a message
+ * for a pipeline timeout (kernel trapped), a peer that never arrived at an exchange, or a bank index out of range. */
 PP_API int pp_check_device_faults(void);
 /* Number of kernels this library has launched in this process (measurement aid). */
 PP_API long long pp_launch_count(void);
@@ -162,7 +163,11 @@ PP_API int pp_topk_merge(const double* pairs, int R, int B, int k_in, int k, flo
  *   pp_xchg_open / pp_xchg_close          cudaIpcOpenMemHandle / cudaIpcCloseMemHandle on a peer's handle
  *   pp_topk_exchange                      peers_dev: device array of `world` buffer pointers (entry `rank` = own buffer);
  *                                         epoch: non-zero, incremented by 1 per call, the same on every rank; every rank
- *                                         must make the call (it is a collective); a missing peer traps after ~4 s. */
+ *                                         must make the call (it is a collective).  Waiting for a peer is bounded by
+ *                                         PICOPOSE_B200_XCHG_TIMEOUT_S (default 120 s, 0 = for ever): a rank that gives up
+ *                                         records a fault (pp_check_device_faults -> PP_ERR_KERNEL), writes NaN / -1 into
+ *                                         its outputs and returns -- no trap, the context survives.  B may exceed the
+ *                                         number of co-resident blocks: the call is cut into launches that fit. */
 PP_API size_t pp_xchg_bytes(int world, int max_b, int k_max);
 PP_API int pp_xchg_create(size_t bytes, void** buf, void* handle64);
 PP_API int pp_xchg_open(const void* handle64, void** peer_buf);
@@ -225,6 +230,19 @@ PP_API int pp_init_correspondences(const float* Ms, const float* tem_mask, int B
                             int h, int w, float* flow, float* certainty, void* stream);
 PP_API int pp_stage3_correspondences(const float* flow, const float* certainty, int B, int H, int W,
                               float threshold, int64_t* tar_pts, int64_t* src_pts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hypothesis selection between stage 1 and stages 2/3.
+ * Replaces Net.select_template_data, model/picopose.py:52-70 (six torch.gather + repeat per hypothesis) and, with
+ * hyp_sel < 0, the per-hypothesis loop around it (:107-110): ONE launch gathers the selected template view of every
+ * detection out of every per-view tensor.
+ *   tensor i: src_ptrs[i] (B, N, view_bytes[i]) -> dst_ptrs[i] (rows, view_bytes[i])   (HOST arrays, DEVICE pointers, <= 16)
+ *   pred_id (B, K) int64 (pp_match_templates' out_idx)
+ *   hyp_sel = k >= 0 : rows = B,   row b       <- view pred_id[b, k]
+ *   hyp_sel < 0      : rows = B*K, row k*B + b <- view pred_id[b, k]   (hypothesis-major: chunk k is one stage-2/3 batch)
+ * ------------------------------------------------------------------------------------------ */
+PP_API int pp_select_templates(const void* const* src_ptrs, void* const* dst_ptrs, const int64_t* view_bytes, int n_tensors,
+                        int B, int N, const int64_t* pred_id, int K, int hyp_sel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -126,6 +126,17 @@ def correlation_pyramid(feat1, feat2, num_levels):
     return pyr
 
 
+def conv1x1_relu(x, weight, bias=None, relu=True):
+    """First layer of MotionEncoder.corr_net (model/stage3/raft_decoder.py:113-116,127-129,157): a 1x1 convolution
+    corr_inch -> Cout (+ ReLU) over the lookup output x (B, Cin, H, W), written as the per-pixel matrix product it is.
+    weight (Cout, Cin) or (Cout, Cin, 1, 1)."""
+    w = weight.reshape(weight.shape[0], -1).float()
+    y = torch.einsum("oc,bchw->bohw", w, x.float())
+    if bias is not None:
+        y = y + bias.float().view(1, -1, 1, 1)
+    return torch.clamp(y, min=0.0) if relu else y
+
+
 # ----------------------------------------------------------------------------
 # explicit-loop second opinion (tiny shapes only)
 # ----------------------------------------------------------------------------

@@ -9,6 +9,8 @@ copied) and records inputs + outputs of
     utils.corr_lookup.CorrLookup / bilinear_sample / coords_grid
     utils.correspondence.compute_init_correspondences / compute_stage3_correspondences
     model.stage3.raft_decoder.CorrelationPyramid   (through a stub mmcv.cnn.ConvModule)
+    model.picopose.Net.select_template_data, model.stage3.raft_decoder.MotionEncoder.corr_net[0],
+    model.stage3.flow_decoder.FlowDecoder.forward   (`python oracle/make_golden.py r2` mints only these)
 
 on seeded synthetic inputs (picopose_b200/synth.py).  /root/reference does not
 exist on the GPU box, so tests only ever read the committed .npz files.
@@ -38,9 +40,16 @@ def _import_reference():
     mmcv = types.ModuleType("mmcv")
     cnn = types.ModuleType("mmcv.cnn")
 
-    class ConvModule(torch.nn.Module):  # pragma: no cover - never instantiated here
-        def __init__(self, *a, **k):
+    class ConvModule(torch.nn.Module):
+        """Conv2d -> ReLU (act_cfg None: no activation); child named `conv` like mmcv's."""
+
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, act_cfg=dict(type="ReLU"), **kw):
             super().__init__()
+            self.conv = torch.nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding)
+            self.act = torch.nn.ReLU() if act_cfg is not None else torch.nn.Identity()
+
+        def forward(self, x):
+            return self.act(self.conv(x))
 
     cnn.ConvModule = ConvModule
     mmcv.cnn = cnn
@@ -58,9 +67,79 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+def main_round2():
+    """Fixtures added in round 2: hypothesis selection (model/picopose.py:52-70), lookup + first MotionEncoder conv
+    (model/stage3/raft_decoder.py:113-116,157) and the whole FlowDecoder loop (model/stage3/flow_decoder.py:74-94)."""
+    _import_reference()
+    import json
+    from model.picopose import Net
+    from model.stage3.flow_decoder import FlowDecoder
+    from model.stage3.raft_decoder import CorrelationPyramid, MotionEncoder
+    from utils.corr_lookup import CorrLookup
+    from oracle import flow_decoder_oracle as OF
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- Net.select_template_data: the method does not touch `self` ----
+    g = torch.Generator().manual_seed(60)
+    B, N, hm, hp = 3, 6, 8, 4
+    ep = {"tem_pose": torch.randn(B, N, 4, 4, generator=g), "tem_K": torch.randn(B, N, 3, 3, generator=g),
+          "tem_M": torch.randn(B, N, 3, 3, generator=g), "tem_mask": (torch.rand(B, N, hm, hm, generator=g) > 0.5).float(),
+          "tem_rgb": torch.rand(B, N, 3, hm, hm, generator=g), "tem_pts3d": torch.randn(B, N, hp, hp, 3, generator=g),
+          "real_pts2d": torch.randn(B, hp, hp, 2, generator=g), "real_K": torch.randn(B, 3, 3, generator=g),
+          "real_M": torch.randn(B, 3, 3, generator=g), "real_mask": (torch.rand(B, hm, hm, generator=g) > 0.5).float(),
+          "real_pose": torch.randn(B, 4, 4, generator=g)}
+    pred_id = torch.stack([torch.randperm(N, generator=g)[:3] for _ in range(B)])
+    d = {"in_" + k: _np(v) for k, v in ep.items()}
+    d["pred_id"] = _np(pred_id)
+    for k in range(3):
+        sel = Net.select_template_data(None, ep, pred_id, k)
+        for key, v in sel.items():
+            d[f"out{k}_{key}"] = _np(v)
+    np.savez_compressed(os.path.join(OUT, "hyp_select.npz"), **d)
+    print("hyp_select: keys", sorted(sel))
+
+    # ---- lookup followed by the motion encoder's first (1x1) convolution ----
+    torch.manual_seed(61)
+    enc = MotionEncoder(num_levels=2, radius=2, net_type="Basic", conv_cfg=None, norm_cfg=None, act_cfg=dict(type="ReLU")).eval()
+    g = torch.Generator().manual_seed(62)
+    f1 = torch.randn(2, 32, 16, 16, generator=g)
+    f2 = torch.randn(2, 32, 16, 16, generator=g)
+    flow = 2.0 * torch.randn(2, 2, 16, 16, generator=g)
+    with torch.no_grad():
+        corr = CorrLookup(radius=2)(CorrelationPyramid(num_levels=2)(f1, f2), flow.clone())
+        feat0 = enc.corr_net[0](corr)
+    np.savez_compressed(os.path.join(OUT, "motion_conv.npz"), f1=_np(f1), f2=_np(f2), flow=_np(flow), corr=_np(corr),
+                        weight=_np(enc.corr_net[0].conv.weight), bias=_np(enc.corr_net[0].conv.bias), out=_np(feat0))
+    print("motion_conv: corr", tuple(corr.shape), "->", tuple(feat0.shape))
+
+    # ---- the whole FlowDecoder (3 levels, radius 4 -> lookup radius 2), seeded weights, eval mode ----
+    seed = 1234
+    torch.manual_seed(seed)
+    ref = FlowDecoder(num_levels=3, radius=4).eval()
+    torch.manual_seed(seed)
+    mine = OF.FlowDecoder(3, 4).eval()
+    sd_ref, sd_mine = ref.state_dict(), mine.state_dict()
+    assert list(sd_ref) == list(sd_mine), "parameter names / order differ"
+    assert all(torch.equal(sd_ref[k], sd_mine[k]) for k in sd_ref), "seeded construction does not reproduce the reference's weights"
+    render, real, flow0, cert0 = OF.decoder_inputs(seed + 1)
+    with torch.no_grad():
+        fr, cr = ref([t.clone() for t in render], [t.clone() for t in real], flow0.clone(), cert0.clone())
+        fm, cm = mine(render, real, flow0, cert0)
+    err = max(float((a - b).abs().max()) for a, b in zip(fr + cr, fm + cm))
+    assert err < 1e-4, err
+    print("flow_decoder: restatement vs reference max |diff| = %.2e" % err)
+    sums = OF.weight_checksums(ref)
+    np.savez_compressed(os.path.join(OUT, "flow_decoder.npz"), seed=seed,
+                        checksums=json.dumps(sums), restatement_vs_reference=err,
+                        **{f"flow{i}": _np(t) for i, t in enumerate(fr)}, **{f"cert{i}": _np(t) for i, t in enumerate(cr)})
+    print("round-2 golden vectors written to", OUT)
+
+
 def main():
     from picopose_b200 import synth
 
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":
+        return main_round2()
     ref_matching, ref_lookup, ref_corresp, CorrelationPyramid = _import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -185,6 +264,7 @@ def main():
                         tar=_np(tar), src=_np(src), flow_r=_np(flow_r), cert_r=_np(cert_r),
                         tar_r=_np(tar_r), src_r=_np(src_r))
     print("golden vectors written to", OUT)
+    main_round2()
 
 
 if __name__ == "__main__":

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pp_windowed_correlation_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_windowed_correlation_prepare_all": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.POINTER(_vp), _vp]),
     "pp_windowed_correlation": (_i, [_vp, C.POINTER(_vp), _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pp_select_templates": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i, _i, _i, _vp, _i, _i, _vp]),
     "pp_init_correspondences": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_stage3_correspondences": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
 }
@@ -111,6 +112,18 @@ def require_cuda(*tensors) -> None:
             raise RuntimeError(
                 "picopose_b200 runs on a CUDA (sm_100) device only: got a tensor on "
                 f"'{t.device}'; there is no CPU fallback")
+
+
+def require_inference(what: str, *tensors) -> None:
+    """The kernels have no backward: fail loudly instead of silently cutting the autograd graph (the reference calls
+    these functions under autograd in forward_train, model/picopose.py:114-137 -- training keeps the reference modules)."""
+    import torch
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise RuntimeError(
+                    f"picopose_b200.{what} is inference-only (no autograd): an input requires grad and grad mode is on. "
+                    "Call it under torch.no_grad() (as run_test.py:165 does) or use the reference module for training.")
 
 
 def ptr(t) -> int:

@@ -34,6 +34,7 @@ def bilinear_sample(feat: Tensor, grid: Tensor, mode: str = 'bilinear', padding_
             f"picopose_b200.bilinear_sample implements mode='bilinear', padding_mode='zeros' "
             f"(the only combination PicoPose uses); got mode='{mode}', padding_mode='{padding_mode}'")
     _lib.require_cuda(feat, grid)
+    _lib.require_inference("bilinear_sample", feat, grid)
     lib = _lib.load()
     feat = feat.float().contiguous()
     grid = grid.float().contiguous()
@@ -51,6 +52,7 @@ def bilinear_sample(feat: Tensor, grid: Tensor, mode: str = 'bilinear', padding_
 def corr_lookup(corr_pyramid: Sequence[Tensor], flow: Tensor, radius: int) -> Tensor:
     """Functional form of CorrLookup.forward -> (B, L*(2r+1)^2, H, W) fp32."""
     _lib.require_cuda(flow, *corr_pyramid)
+    _lib.require_inference("CorrLookup", flow, *corr_pyramid)
     lib = _lib.load()
     flow = flow.float().contiguous()
     B, two, H, W = flow.shape

@@ -24,6 +24,7 @@ def correlation_pyramid(feat1: torch.Tensor, feat2: torch.Tensor, num_levels: in
                         mode: Optional[str] = None) -> Sequence[torch.Tensor]:
     """-> [ (N*H*W, 1, H>>l, W>>l) fp32 for l in range(num_levels) ], corr = <f1, f2> / sqrt(C), 2x2 average pools."""
     _lib.require_cuda(feat1, feat2)
+    _lib.require_inference("CorrelationPyramid", feat1, feat2)
     lib = _lib.load()
     N, Cc, H, W = feat1.shape
     if tuple(feat2.shape) != (N, Cc, H, W):
@@ -52,6 +53,7 @@ def windowed_correlation(feat1: torch.Tensor, feat2: torch.Tensor, flow: torch.T
     -> (N, L*(2r+1)^2, H, W) fp32, same channel order and values (to ~1e-6) as the two-step path.
     """
     _lib.require_cuda(feat1, feat2, flow)
+    _lib.require_inference("CorrLookup (fused correlation)", feat1, feat2, flow)
     lib = _lib.load()
     f1 = feat1.float().contiguous()
     f2 = feat2.float().contiguous()

@@ -10,6 +10,7 @@ from .corr_lookup import coords_grid  # re-exported like the reference module do
 def compute_init_correspondences(pred_Ms, tem_mask, size=(16, 16)):
     """Drop-in for utils/correspondence.py:10-26 -> (init_flow (B,2,h,w), init_certainty (B,1,h,w))."""
     _lib.require_cuda(pred_Ms, tem_mask)
+    _lib.require_inference("compute_init_correspondences", pred_Ms)
     lib = _lib.load()
     B, H, W = tem_mask.shape
     assert H == W

@@ -90,6 +90,13 @@ extern "C" int pp_check_device_faults(void) {
     cudaError_t e = cudaDeviceSynchronize();
     int rec[5] = {0, 0, 0, 0, 0};
     const int code = pp::read_fault_record(rec);
+    if (code == 5)
+        return pp::fail(PP_ERR_KERNEL, "exchange timeout: peer %d never published epoch %u (block %d); the outputs of that call "
+                                       "are poisoned (NaN / -1).  PICOPOSE_B200_XCHG_TIMEOUT_S sets the limit (%s)",
+                        rec[3], (unsigned)rec[4], rec[1], cudaGetErrorString(e));
+    if (code == 6)
+        return pp::fail(PP_ERR_KERNEL, "bank index out of range: detection %d names bank %d of %d (clamped; results of that "
+                                       "detection are meaningless)", rec[1], rec[2], rec[3]);
     if (code != 0) {
         // codes: 1 producer waits for a free smem stage, 2 MMA waits for a drained TMEM stage,
         //        3 MMA waits for TMA data, 4 epilogue waits for the accumulator

@@ -16,6 +16,7 @@
 // never collide.
 #include "pp_common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace pp {
@@ -37,17 +38,53 @@ static XchgLayout xchg_layout(int world, int max_b, int k_max) {
     return l;
 }
 
-constexpr long long XCHG_TIMEOUT_CYCLES = 8000000000LL;  // ~4 s: a missing peer traps instead of hanging
+// Waiting for a peer is bounded in wall time (PICOPOSE_B200_XCHG_TIMEOUT_S, default 120 s, 0 = wait for ever, like NCCL).
+// A rank that gives up does NOT trap -- the CUDA context and the healthy ranks survive: it records fault code 5 in the
+// host-mapped fault buffer (pp_check_device_faults reports it), poisons its outputs (NaN scores, index -1) and returns.
+// Flags are compared wrap-safe with >= , so a peer that (against the one-step-ahead contract) has already overwritten a
+// slot with a later epoch cannot dead-lock the waiter.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool epoch_reached(unsigned seen, unsigned epoch) { return (int)(seen - epoch) >= 0 && seen != 0u; }
+
+__device__ __noinline__ void record_xchg_fault(int* fault, int peer, unsigned epoch) {
+    if (fault) {
+        fault[1] = blockIdx.x;
+        fault[2] = threadIdx.x;
+        fault[3] = peer;
+        fault[4] = (int)epoch;
+        __threadfence_system();
+        fault[0] = 5;
+        __threadfence_system();
+    }
+}
+
+static unsigned long long xchg_timeout_ns() {
+    static long long cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("PICOPOSE_B200_XCHG_TIMEOUT_S");
+        double s = e ? atof(e) : 120.0;
+        if (!(s >= 0.0)) s = 120.0;
+        cached = (long long)(s * 1e9);
+    }
+    return (unsigned long long)cached;
+}
 
 __global__ void __launch_bounds__(256)
 topk_exchange_kernel(const float* __restrict__ scores, int N, int k, long long idx_offset, char* const* __restrict__ peers,
-                     int rank, int world, int max_b, int k_max, size_t pairs_off, unsigned epoch,
+                     int rank, int world, int max_b, int k_max, size_t pairs_off, unsigned epoch, int b0,
+                     unsigned long long timeout_ns, int* __restrict__ fault,
                      float* __restrict__ out_score, long long* __restrict__ out_idx) {
     extern __shared__ unsigned long long s_keys[];  // N packed keys + 8 partials
     unsigned long long* s_red = s_keys + N;
     __shared__ XPair s_loc[256];
     __shared__ unsigned long long s_merge[1024];
-    const int b = blockIdx.x;
+    __shared__ int s_gave_up;
+    const int b = b0 + blockIdx.x;
+    if (threadIdx.x == 0) s_gave_up = 0;
     const int par = (int)(epoch & 1u);
     // ---- local top-k (torch.topk on this rank's views; ties resolve to the lowest index) ----
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_keys[i] = pack_key(scores[(size_t)b * N + i] + 0.0f, (uint32_t)i);
@@ -92,14 +129,25 @@ topk_exchange_kernel(const float* __restrict__ scores, int N, int k, long long i
         *flag = epoch;
         // acquire: wait for peer `threadIdx.x`'s pairs of this detection in this rank's own buffer
         volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(peers[rank]) + ((size_t)par * world + threadIdx.x) * max_b + b;
-        const long long t0 = clock64();
-        while (*mine != epoch) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (!epoch_reached(*mine, epoch)) {
             __nanosleep(200);
-            if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) __trap();
+            if (timeout_ns && globaltimer_ns() - t0 > timeout_ns) {
+                record_xchg_fault(fault, (int)threadIdx.x, epoch);
+                s_gave_up = 1;
+                break;
+            }
         }
         __threadfence_system();
     }
     __syncthreads();
+    if (s_gave_up) {  // a peer never showed up: poison this detection's result instead of merging stale slots
+        if ((int)threadIdx.x < k) {
+            out_score[(size_t)b * k + threadIdx.x] = __int_as_float(0x7fc00000);
+            out_idx[(size_t)b * k + threadIdx.x] = -1;
+        }
+        return;
+    }
     // ---- merge: world * k candidates, ties go to the lowest rank / slot (= lowest view index for contiguous shards) ----
     const int n = world * k;
     const XPair* own = reinterpret_cast<const XPair*>(peers[rank] + pairs_off);
@@ -139,13 +187,17 @@ __global__ void xchg_signal_kernel(char* const* __restrict__ peers, size_t flag_
         *flag = epoch;
     }
 }
-__global__ void xchg_wait_kernel(const char* __restrict__ own, size_t flag_off, int world, unsigned epoch) {
+__global__ void xchg_wait_kernel(const char* __restrict__ own, size_t flag_off, int world, unsigned epoch,
+                                 unsigned long long timeout_ns, int* __restrict__ fault) {
     if ((int)threadIdx.x < world) {
         const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(own + flag_off) + threadIdx.x;
-        const long long t0 = clock64();
-        while (*flag != epoch) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (!epoch_reached(*flag, epoch)) {
             __nanosleep(500);
-            if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) __trap();
+            if (timeout_ns && globaltimer_ns() - t0 > timeout_ns) {
+                record_xchg_fault(fault, (int)threadIdx.x, epoch);  // reported by pp_check_device_faults; no trap
+                break;
+            }
         }
         __threadfence_system();
     }
@@ -176,7 +228,10 @@ extern "C" int pp_xchg_signal(const void* const* peers_dev, size_t flag_offset, 
 extern "C" int pp_xchg_wait(const void* own_buf, size_t flag_offset, int world, uint32_t epoch, void* stream) {
     using namespace pp;
     PP_CHECK_ARG(own_buf && world > 0 && world <= 256 && epoch != 0, "pp_xchg_wait: bad arguments");
-    xchg_wait_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const char*>(own_buf), flag_offset, world, epoch);
+    int* fault = nullptr;
+    if (int rc = fault_buffer(&fault)) return rc;
+    xchg_wait_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const char*>(own_buf), flag_offset, world, epoch,
+                                                                       xchg_timeout_ns(), fault);
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -245,9 +300,23 @@ extern "C" int pp_topk_exchange(const float* scores, int B, int N, int k, int64_
     const size_t smem = ((size_t)N + 8) * sizeof(unsigned long long);
     if (smem > 48 * 1024)
         PP_CUDA(cudaFuncSetAttribute(topk_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_exchange_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        scores, N, k, (long long)idx_offset, reinterpret_cast<char* const*>(const_cast<void* const*>(peers_dev)), rank, world,
-        max_b, k_max, l.pairs_off, epoch, out_score, reinterpret_cast<long long*>(out_idx));
-    PP_LAUNCHED();
+    int* fault = nullptr;
+    if (int rc = fault_buffer(&fault)) return rc;
+    // A block spins until the peers' blocks of the SAME detection have run, so every block of a launch must be
+    // co-resident with the ones it (transitively) waits for: launches are cut into chunks of at most the number of
+    // blocks the device holds at once.  Chunks of one call share the epoch (flags are per detection) and every rank
+    // issues them in the same order, so a chunk only ever waits for the same chunk of its peers.
+    int per_sm = 0;
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, topk_exchange_kernel, 256, smem));
+    PP_CHECK_ARG(per_sm >= 1, "pp_topk_exchange: kernel does not fit an SM with N=%d", N);
+    const int resident = per_sm * sm_count();
+    for (int b0 = 0; b0 < B; b0 += resident) {
+        const int nb = B - b0 < resident ? B - b0 : resident;
+        topk_exchange_kernel<<<nb, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+            scores, N, k, (long long)idx_offset, reinterpret_cast<char* const*>(const_cast<void* const*>(peers_dev)), rank,
+            world, max_b, k_max, l.pairs_off, epoch, b0, xchg_timeout_ns(), fault, out_score,
+            reinterpret_cast<long long*>(out_idx));
+        PP_LAUNCHED();
+    }
     return PP_OK;
 }

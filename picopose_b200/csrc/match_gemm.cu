@@ -52,7 +52,8 @@ struct GemmParams {
     int num_k_blocks;
     int num_mt, num_nt;  // tiles along T (per 128*CL rows) and S (per 256 columns)
     uint32_t total_tiles;
-    const int32_t* bank_of_det;    // (B,) or null = identity
+    int n_banks;
+    const int32_t* bank_of_det;    // (B,) or null = identity; entries outside [0, n_banks) are clamped and reported (fault 6)
     const float* mrow;             // (B, T) nearest-resized query mask, indexed by patch
     const int* tv;                 // (B) unmasked query patches per detection (EPI_MATCH: rows are compacted); null = T
     const int* rowmap;             // (B, T) patch index of compact query row r
@@ -122,6 +123,12 @@ __device__ __forceinline__ TileCoord decode_tile(uint32_t tile, const GemmParams
 // detection.  Column tiles of one (view, patch tile) are neighbours in the flat order, so the clusters that run
 // them at the same time read the same template rows (L2 hits).
 __device__ __forceinline__ int live_rows(const GemmParams& p, int b) { return p.tv ? __ldg(p.tv + b) : p.T; }
+// bank of detection b, forced into range: a bad index must not become an out-of-bounds TMA coordinate / rnorm read
+__device__ __forceinline__ int bank_of(const GemmParams& p, int b) {
+    if (!p.bank_of_det) return b;
+    const int v = __ldg(p.bank_of_det + b);
+    return v < 0 ? 0 : (v >= p.n_banks ? p.n_banks - 1 : v);
+}
 __device__ __forceinline__ uint32_t col_tiles(int rows) { return (uint32_t)((rows + BLOCK_N - 1) / BLOCK_N); }
 __device__ __forceinline__ TileCoord decode_tile_prefix(uint32_t tile, const GemmParams& p, const uint32_t* prefix) {
     int lo = 0, hi = p.B;
@@ -198,6 +205,18 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int b = b0 + lane;
             uint32_t cnt = 0;
             if (b < p.B) cnt = col_tiles(live_rows(p, b)) * (uint32_t)(p.N * p.num_mt);
+            if (b < p.B && p.bank_of_det && blockIdx.x == 0) {
+                // range check of the caller's bank indices (the loads above clamp): reported, not trapped
+                const int v = __ldg(p.bank_of_det + b);
+                if ((v < 0 || v >= p.n_banks) && p.fault) {
+                    p.fault[1] = b;
+                    p.fault[2] = v;
+                    p.fault[3] = p.n_banks;
+                    p.fault[4] = 0;
+                    __threadfence_system();
+                    p.fault[0] = 6;
+                }
+            }
             uint32_t inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -223,7 +242,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t phase = 0;
         for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters) {
             const TileCoord tc = decode(tile);
-            const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
+            const int bank = bank_of(p, tc.b);
             const int q_row0 = tc.b * p.T;                                       // query operand: rows of detection b
             const int t_row0 = (int)(((long long)bank * p.N + tc.n) * p.T);      // bank operand: rows of view n
             // A = M-side operand (128 rows per CTA), B = N-side operand (each CTA of a pair holds half of the columns;
@@ -310,7 +329,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 // lane = template patch s (TMEM lane), columns = compact query rows r of detection b; t = rowmap[r]
                 const int s_row = warp_row0 + lane;
                 const bool s_ok = s_row < T;
-                const int bank = p.bank_of_det ? __ldg(p.bank_of_det + tc.b) : tc.b;
+                const int bank = bank_of(p, tc.b);
                 // row maxima (over s, across lanes): value = acc * rb[s] + 0.0 (-0.0 is canonicalised); lanes past the
                 // last template patch get a huge negative value and lose against everything
                 const float rb_l = s_ok ? __ldg(p.rb + ((size_t)bank * p.N + tc.n) * T + s_row) : 0.f;
@@ -352,12 +371,15 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     // strict > keeps the first index on ties, columns are in increasing t).
                     // ---- across lanes: first-argmax over s of acc * rb[s] (the row's own positive factor ra[t]
                     // commutes with the max and is applied when finalising).  Each value becomes a float key whose
-                    // 5 low mantissa bits hold (31 - lane), the value rounded to nearest at that position: a float max
-                    // then means "largest value, then lowest lane"; values closer than 2^-19 relative count as ties.
+                    // 5 low mantissa bits hold the lane (31 - lane for x >= 0, lane for x < 0), the value rounded to nearest
+                    // at that position: a float max then means "largest value, then lowest lane" for either sign; values
+                    // closer than 2^-19 relative count as ties.
                     float k[32];
                     float cbest = -INFINITY;
                     int cj = 0;
-                    const uint32_t lane_bits = (uint32_t)(31 - lane);
+                    // payload: for x >= 0 a larger payload is a larger float, for x < 0 a smaller one, so the lane goes in
+                    // as 31 - lane resp. lane: in both cases the lowest lane (= first template patch) wins a tie
+                    const uint32_t lane_pos = (uint32_t)(31 - lane), lane_neg = (uint32_t)lane;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 f4 = *reinterpret_cast<const float4*>(fa_s + i * 32 + j);  // broadcast read
@@ -368,7 +390,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             const float xt = x * ff[u];
                             if (xt > cbest) { cbest = xt; cj = j + u; }
                             const float xs = fmaf(x, rb_l, c_add);
-                            k[j + u] = __uint_as_float(((__float_as_uint(xs) + 0x10u) & 0xFFFFFFE0u) | lane_bits);
+                            const uint32_t xb = __float_as_uint(xs);
+                            k[j + u] = __uint_as_float(((xb + 0x10u) & 0xFFFFFFE0u) | ((xb >> 31) ? lane_neg : lane_pos));
                         }
                     }
                     if (ncols < 32) {
@@ -396,7 +419,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     {
                         const uint32_t kb = __float_as_uint(k[0]);
-                        const int win_s = warp_row0 + 31 - (int)(kb & 31u);
+                        const int win_lane = (kb >> 31) ? (int)(kb & 31u) : 31 - (int)(kb & 31u);
+                        const int win_s = warp_row0 + win_lane;
                         if (lane < ncols && warp_row0 < T)
                             atomicMax(p.rowkey + bn * T + tp_s[i * 32 + lane],
                                       pack_key(__uint_as_float(kb & 0xFFFFFFE0u), (uint32_t)win_s));
@@ -545,6 +569,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     const long long tiles_ll = (long long)B * N * p.num_mt * p.num_nt;
     PP_CHECK_ARG(tiles_ll < (1LL << 31), "too many tiles in one launch (%lld); split the detection batch", tiles_ll);
     p.total_tiles = (uint32_t)tiles_ll;
+    p.n_banks = (int)n_banks;
     p.bank_of_det = bank_of_det;
     p.mrow = mrow;
     p.tv = tv;
@@ -570,6 +595,12 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
         return epi == EPI_MATCH ? launch_gemm<1, EPI_MATCH>(ta, tb, p, st) : launch_gemm<1, EPI_EMIT>(ta, tb, p, st);
     }
     return epi == EPI_MATCH ? launch_gemm<2, EPI_MATCH>(ta, tb, p, st) : launch_gemm<2, EPI_EMIT>(ta, tb, p, st);
+}
+
+int fault_buffer(int** dev_ptr) {
+    if (int rc = ensure_fault_buffer()) return rc;
+    *dev_ptr = g_fault_dev;
+    return PP_OK;
 }
 
 int read_fault_record(int* out5) {

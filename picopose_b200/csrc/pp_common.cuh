@@ -50,6 +50,10 @@ struct QueryMeta {
 };
 QueryMeta split_query_meta(void* q_meta, int B, int T);
 
+// Host-mapped fault record shared by all kernels (5 ints: code, block, thread, aux0, aux1); created on first use.
+// codes: 1-4 contraction pipeline time-outs (the kernel traps), 5 exchange peer missing, 6 bank index out of range.
+int fault_buffer(int** dev_ptr);
+
 // Verifies the current device is sm_100 (cached per device).
 int require_sm100();
 int sm_count();

@@ -140,6 +140,24 @@ class _on_device:
             self.ctx.__exit__(*a)
 
 
+def _checked_index(bank_index, src_feats):
+    """Range check of `bank_index` where it costs nothing: an index that lives on the host is validated here; one that
+    lives on the device is clamped and reported by the contraction kernel (fault record, `_lib.check_device_faults`)."""
+    if bank_index is None or bank_index.is_cuda or bank_index.numel() == 0:
+        return bank_index
+    from .serving import BankHandle
+    if isinstance(src_feats, BankHandle):
+        n_banks = src_feats.bank.n_banks
+    elif isinstance(src_feats, TemplateBank):
+        n_banks = src_feats.n_banks
+    else:
+        n_banks = src_feats.shape[0]
+    lo, hi = int(bank_index.min()), int(bank_index.max())
+    if lo < 0 or hi >= n_banks:
+        raise IndexError(f"bank_index out of range: values span [{lo}, {hi}] for {n_banks} banks")
+    return bank_index
+
+
 def _check_bank(bank, bank_index, tar_feat):
     B, Cc, H, W = tar_feat.shape
     if H != W:
@@ -246,8 +264,10 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
     TemplateBank.
     """
     _lib.require_cuda(tar_feat, tar_mask)
+    _lib.require_inference("template_scores", src_feats, tar_feat)
     lib = _lib.load()
     B, Cc, H, W = tar_feat.shape
+    bank_index = _checked_index(bank_index, src_feats)
     if not want_indices and not want_mutual:
         dense = _dense_features(src_feats, tar_feat, bank_index)
         if dense is not None:
@@ -335,6 +355,8 @@ def matching_templates(src_feats, tar_feat, src_masks, tar_mask, topk=5, *, mode
     be a TemplateBank (pre-normalised once per object) with `bank_index` mapping detections to banks.
     """
     _lib.require_cuda(tar_feat, tar_mask)
+    _lib.require_inference("matching_templates", src_feats, tar_feat)
+    bank_index = _checked_index(bank_index, src_feats)
     dense = _dense_features(src_feats, tar_feat, bank_index)
     if dense is not None:
         if topk > dense.shape[1]:
@@ -356,6 +378,7 @@ def matching_templates(src_feats, tar_feat, src_masks, tar_mask, topk=5, *, mode
 def matching_features_similarity(src_feat, tar_feat, src_mask, tar_mask, *, mode: Optional[str] = None):
     """Drop-in for utils/matching.py:6-26.  Returns the (B, H*W, H, W) stage-2 similarity volume."""
     _lib.require_cuda(src_feat, tar_feat, src_mask)
+    _lib.require_inference("matching_features_similarity", src_feat, tar_feat)
     lib = _lib.load()
     B, Cc, H, W = src_feat.shape
     if H != W:

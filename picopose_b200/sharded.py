@@ -143,25 +143,51 @@ class _DeviceView:
 
 def _open_peers(lib, group, nbytes: int, device):
     """Collective: allocate this rank's exchange buffer, swap the IPC handles, map every peer's buffer.
-    -> (own pointer, [pointer of rank 0 .. world-1] with the own one in place, [opened peer pointers])."""
+    -> (own pointer, [pointer of rank 0 .. world-1] with the own one in place, [opened peer pointers]).
+
+    Failure is collective too: a rank whose allocation or mapping fails (out of memory, no P2P path to one peer) still
+    takes part in both object all-gathers, every rank learns that somebody failed, releases what it had created and
+    raises the same RuntimeError -- so the callers' fallback to the all-gather forms is taken by all ranks or by none,
+    and nobody is left waiting inside a collective."""
     import ctypes as C
     from . import _lib
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    own, opened, ptrs, err = None, [], [], None
     with torch.cuda.device(device):
         buf, handle = C.c_void_p(), C.create_string_buffer(64)
-        _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
+        try:
+            _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
+            own = buf.value
+        except RuntimeError as exc:
+            err = str(exc)
         handles = [None] * world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        ptrs, opened = [], []
-        for r, h in enumerate(handles):
-            if r == rank:
-                ptrs.append(buf.value)
-            else:
-                p = C.c_void_p()
-                _lib.check(lib.pp_xchg_open(C.create_string_buffer(h, 64), C.byref(p)), "pp_xchg_open")
-                opened.append(p.value)
-                ptrs.append(p.value)
-    return buf.value, ptrs, opened
+        dist.all_gather_object(handles, handle.raw if own is not None else None, group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r, h in enumerate(handles):
+                    if r == rank:
+                        ptrs.append(own)
+                    else:
+                        p = C.c_void_p()
+                        _lib.check(lib.pp_xchg_open(C.create_string_buffer(h, 64), C.byref(p)), "pp_xchg_open")
+                        opened.append(p.value)
+                        ptrs.append(p.value)
+            except RuntimeError as exc:
+                err = str(exc)
+        elif err is None:
+            err = "a peer could not allocate its exchange buffer"
+        verdicts = [None] * world
+        dist.all_gather_object(verdicts, err, group=group)
+        failed = [(r, v) for r, v in enumerate(verdicts) if v is not None]
+        if failed:
+            for p in opened:
+                lib.pp_xchg_close(p)
+            dist.barrier(group)          # nobody frees a buffer a peer may still have mapped
+            if own is not None:
+                lib.pp_xchg_destroy(own)
+            raise RuntimeError("peer-memory buffers unavailable on rank(s) %s: %s"
+                               % ([r for r, _ in failed], failed[0][1]))
+    return own, ptrs, opened
 
 
 def _close_peers(lib, group, device, own, opened):
@@ -209,6 +235,8 @@ class PeerGather:
         self._peers_host = (C.c_void_p * self.world)(*ptrs)
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
         self.epoch = 0
+        self.consumed = 0      # gathers whose batch has been handed to a `match` (ShardedMatcher keeps it up to date)
+        self._issued = 0
         dist.barrier(group)
 
     @staticmethod
@@ -233,6 +261,12 @@ class PeerGather:
         from . import _lib
         lib = _lib.load()
         assert tuple(tar_local.shape) == self.tar_shape and tuple(mask_local.shape) == self.mask_shape
+        if self._issued - self.consumed >= 2:
+            # contract (1): gather e+2 overwrites the slots of gather e, which is only safe once the match that consumed
+            # gather e has run its exchange -- a third gather without a match in between would hand peers torn data
+            raise RuntimeError("PeerGather: two gathers are already waiting for their `match`; a gather may run at most "
+                               "one step ahead of the compute it feeds (double-buffered slots)")
+        self._issued += 1
         tar_local, mask_local = tar_local.float().contiguous(), mask_local.float().contiguous()
         self.epoch = 1 if self.epoch >= 0xFFFFFFFE else self.epoch + 1
         par = self.epoch & 1
@@ -304,7 +338,10 @@ class ShardedMatcher:
             # before; without `out` the result is a view of this rank's exchange buffer
             if self._gather is None or self._gather.tar_shape != tuple(tar_local.shape) \
                     or self._gather.mask_shape != tuple(mask_local.shape):
-                try:
+                if self._gather is not None:
+                    self._gather.close()
+                    self._gather = None
+                try:    # collective: fails on every rank or on none (_open_peers)
                     self._gather = PeerGather(tar_local.shape, mask_local.shape, self.group, tar_local.device)
                 except RuntimeError as exc:
                     import warnings
@@ -328,6 +365,8 @@ class ShardedMatcher:
         """src: this rank's shard, a TemplateBank or raw (B|n_banks, hi-lo, C, H, W) features."""
         from .matching import matching_templates, template_scores
         src = self.bank if src is None else src
+        if self._gather is not None and self._gather.consumed < self._gather._issued:
+            self._gather.consumed += 1       # this match consumes the oldest outstanding gather (see PeerGather contract)
         if self.world == 1:
             # single rank: nothing to exchange, one library call ranks the whole bank
             return matching_templates(src, tar_feat, None, tar_mask, topk, mode=mode, bank_index=bank_index)
@@ -360,7 +399,7 @@ class ShardedMatcher:
         if self._xchg is None:
             try:
                 self._xchg = PeerExchange(self.group, max_b=max(64, B), k_max=max(8, k), device=sim.device)
-            except RuntimeError as exc:   # no peer mappings in this environment: every rank fails alike
+            except RuntimeError as exc:   # collective failure (_open_peers): every rank lands here together
                 import warnings
                 warnings.warn(f"picopose_b200: peer-memory top-k exchange unavailable ({exc}); using the all-gather form")
                 self._want_peer = False

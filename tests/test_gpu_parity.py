@@ -172,67 +172,94 @@ def test_prepare_features_layout():
     ref_rn = 1.0 / torch.clamp(x.reshape(3, 2, 72, 25).norm(dim=2), min=1e-12)
     np.testing.assert_allclose(rn.numpy(), ref_rn.numpy(), rtol=2e-6)
     assert float(rn[0, 0, 0]) == pytest.approx(1e12, rel=1e-6)
-    # split modes reconstruct the fp32 value exactly: query segments [q1 q1 q2 | q1 q2 q3], bank [b1 b2 b1 | b3 b2 b1]
+    # split modes reconstruct the fp32 value exactly; segments are ordered smallest cross term first (the tensor core's
+    # accumulator truncates): query [q3 q2 q1 | q2 q1 q1], bank [b1 b2 b3 | b1 b2 b1]; bf16x3 = the last three
     o6 = prepare_features(x.to(DEV), "fp32", is_query=True)[0].float().cpu()
     assert o6.shape[-1] == 448
     s = [o6[..., i * 72:(i + 1) * 72] for i in range(6)]
-    assert torch.equal(s[0], s[1]) and torch.equal(s[0], s[3]) and torch.equal(s[2], s[4])
-    assert torch.equal(s[0] + s[2] + s[5], xt)
+    assert torch.equal(s[2], s[4]) and torch.equal(s[2], s[5]) and torch.equal(s[1], s[3])
+    assert torch.equal(s[5] + s[3] + s[0], xt) and torch.equal(s[5], xt.bfloat16().float())
     b6 = prepare_features(x.to(DEV), "fp32", is_query=False)[0].float().cpu()
     t = [b6[..., i * 72:(i + 1) * 72] for i in range(6)]
-    assert torch.equal(t[0], t[2]) and torch.equal(t[0], t[5]) and torch.equal(t[1], t[4])
-    assert torch.equal(t[0] + t[1] + t[3], xt)
+    assert torch.equal(t[0], t[3]) and torch.equal(t[0], t[5]) and torch.equal(t[1], t[4])
+    assert torch.equal(t[5] + t[4] + t[2], xt)
+    o3 = prepare_features(x.to(DEV), "bf16x3", is_query=True)[0].float().cpu()
+    b3 = prepare_features(x.to(DEV), "bf16x3", is_query=False)[0].float().cpu()
+    assert torch.equal(o3[..., :216], o6[..., 216:432]) and torch.equal(b3[..., :216], b6[..., 216:432])
 
 
 MODE_TOL = {"bf16": 4e-3, "bf16x3": 2e-5, "fp32": 1e-5}
 
 
-def _check_match(src, tar, mask, k, mode, cluster, ref=None):
+REL_BF16 = 1e-2          # north_star: similarity scores within 1e-2 relative in bf16 mode ...
+REL_FLOOR = 1e-4         # ... with an absolute floor for values near zero; asserted at the reference's widths C >= 384
+
+
+def _check_match(src, tar, mask, k, mode, cluster, ref=None, bank_index=None):
     """Runs the CUDA path and checks it against the oracle under the north_star tolerances.
 
     Integer outputs must be exact wherever the reference's own decision gap exceeds 1e-3.  The score of
     a (detection, view) pair may additionally move by score_j / H^2 for every patch j whose validity
     flag (argmax != 0, utils/matching.py:58-59) is decided by a gap narrower than the arithmetic error.
+    `bank_index` (B,): src holds shared banks (G, N, C, H, W) and detection b uses bank bank_index[b].
     """
     from picopose_b200.matching import matching_templates, template_scores
+    obj = list(range(tar.shape[0])) if bank_index is None else [int(v) for v in bank_index]
     if ref is None:
-        ref = OM.template_scores(src, tar, mask, want_indices=True)
+        if bank_index is None:
+            ref = OM.template_scores(src, tar, mask, want_indices=True)
+        else:
+            parts = [OM.template_scores(src[o:o + 1], tar[b:b + 1], mask[b:b + 1], want_indices=True) for b, o in enumerate(obj)]
+            ref = tuple(torch.cat([p[i] for p in parts]) for i in range(4))
     sim_ref, sc_ref, it_ref, is_ref = ref
     tol = MODE_TOL[mode]
     band = 2 * tol
-    sim, sc, it, is_ = template_scores(src.to(DEV), tar.to(DEV), mask.to(DEV), mode=mode, want_indices=True,
-                                       cluster=cluster)
+    bidx = None if bank_index is None else torch.as_tensor(obj, dtype=torch.int32, device=DEV)
+    src_d = src.to(DEV)
+    sim, sc, it, is_ = template_scores(src_d, tar.to(DEV), mask.to(DEV), mode=mode, want_indices=True,
+                                       cluster=cluster, bank_index=bidx)
     _lib.check_device_faults()
     B, N, T = sc_ref.shape
+    C = tar.shape[1]
     H = int(round(T ** 0.5))
     m = OM.nearest_mask(mask.float(), H, H)                            # (B,T)
     np.testing.assert_allclose(sc.cpu().numpy(), sc_ref.numpy(), rtol=0, atol=tol)
+    if mode == "bf16" and C >= 384:
+        # the north_star bound proper: per-patch similarity scores within 1e-2 RELATIVE at the reference's feature widths
+        np.testing.assert_allclose(sc.cpu().numpy(), sc_ref.numpy(), rtol=REL_BF16, atol=REL_FLOOR)
     a = OM._unit(tar.float(), 1).reshape(B, -1, T)
-    b_ = OM._unit(src.float(), 2).reshape(B, N, -1, T)
     it_c, is_c = it.cpu().long(), is_.cpu().long()
     allowed = torch.full((B, N), tol)
     n_checked = 0
+    NV = 48                                                            # views per step of the gap analysis (memory bound)
     for bi in range(B):
-        simm = torch.matmul(a[bi].t().unsqueeze(0), b_[bi]) * m[bi].view(1, T, 1)   # (N,T,S)
-        top2 = simm.topk(2, dim=2).values
-        gap_r = top2[..., 0] - top2[..., 1]
-        sure = gap_r > 1e-3
-        assert torch.equal(it_c[bi][sure], it_ref[bi][sure])
-        top2c = simm.topk(2, dim=1).values
-        gap_c = top2c[:, 0] - top2c[:, 1]
-        sure_c = gap_c > 1e-3
-        assert torch.equal(is_c[bi][sure_c], is_ref[bi][sure_c])
-        n_checked += int(sure.sum()) + int(sure_c.sum())
-        # patches whose "argmax != 0" flag hangs on a gap inside the arithmetic error band
-        amb_r = torch.where(it_ref[bi] == 0, gap_r < band, (top2[..., 0] - simm[:, :, 0]) < band)
-        amb_c = torch.where(is_ref[bi] == 0, gap_c < band, (top2c[:, 0] - simm[:, 0, :]) < band)
-        amb = (amb_r | amb_c) & (m[bi].view(1, T) != 0)
-        allowed[bi] += (amb * (sc_ref[bi].abs() + tol)).sum(dim=1) / float(H * H)
+        for n0 in range(0, N, NV):
+            n1 = min(N, n0 + NV)
+            b_ = OM._unit(src[obj[bi], n0:n1].float(), 1).reshape(n1 - n0, -1, T)
+            simm = torch.matmul(a[bi].t().unsqueeze(0), b_) * m[bi].view(1, T, 1)      # (n,T,S)
+            top2 = simm.topk(2, dim=2).values
+            gap_r = top2[..., 0] - top2[..., 1]
+            sure = gap_r > 1e-3
+            assert torch.equal(it_c[bi, n0:n1][sure], it_ref[bi, n0:n1][sure])
+            top2c = simm.topk(2, dim=1).values
+            gap_c = top2c[:, 0] - top2c[:, 1]
+            sure_c = gap_c > 1e-3
+            assert torch.equal(is_c[bi, n0:n1][sure_c], is_ref[bi, n0:n1][sure_c])
+            n_checked += int(sure.sum()) + int(sure_c.sum())
+            # patches whose "argmax != 0" flag hangs on a gap inside the arithmetic error band
+            amb_r = torch.where(it_ref[bi, n0:n1] == 0, gap_r < band, (top2[..., 0] - simm[:, :, 0]) < band)
+            amb_c = torch.where(is_ref[bi, n0:n1] == 0, gap_c < band, (top2c[:, 0] - simm[:, 0, :]) < band)
+            amb = (amb_r | amb_c) & (m[bi].view(1, T) != 0)
+            allowed[bi, n0:n1] += (amb * (sc_ref[bi, n0:n1].abs() + tol)).sum(dim=1) / float(H * H)
     assert n_checked > 0 or float(m.sum()) == 0
     diff = (sim.cpu() - sim_ref).abs()
     assert bool((diff <= allowed + 1e-2 * sim_ref.abs() * (mode == "bf16")).all()), (diff.max(), allowed.max())
+    if mode == "bf16" and C >= 384:
+        # sim_avg within 1e-2 relative wherever no validity flag of the pair is ambiguous
+        clean = allowed <= tol
+        assert bool((diff[clean] <= REL_BF16 * sim_ref[clean].abs() + REL_FLOOR).all())
     # top-k: exact wherever adjacent reference scores are more than 1e-3 apart
-    score, idx = matching_templates(src.to(DEV), tar.to(DEV), None, mask.to(DEV), topk=k, mode=mode)
+    score, idx = matching_templates(src_d, tar.to(DEV), None, mask.to(DEV), topk=k, mode=mode, bank_index=bidx)
     assert score.dtype == torch.float32 and idx.dtype == torch.int64
     sref, iref = torch.topk(sim_ref, k, dim=1)
     full = torch.sort(sim_ref, dim=1, descending=True).values
@@ -250,8 +277,12 @@ def _check_match(src, tar, mask, k, mode, cluster, ref=None):
 
 @pytest.mark.parametrize("cluster", [1, 2])
 @pytest.mark.parametrize("mode", ["bf16", "fp32", "bf16x3"])
-@pytest.mark.parametrize("name", ["small", "medium", "bern", "ones", "allmasked", "identical"])
+@pytest.mark.parametrize("name", ["small", "medium", "bern", "ones", "allmasked", "identical", "tiles"])
 def test_matching_golden(name, mode, cluster):
+    if name == "tiles" and mode == "bf16":
+        # 1024 x 1024 similarities of C = 16 features: single-pass bf16 (error ~4e-3 at this width) flips argmaxes outside
+        # the 1e-3 gap band; that mode is specified for the reference's widths (384 / 1024) and checked there at full size
+        pytest.skip("single-pass bf16 is not specified for 16-channel features")
     g = load(f"match_{name}.npz")
     src, tar = torch.from_numpy(g["src"]), torch.from_numpy(g["tar"])
     mask = torch.from_numpy(g["mask"]).float()
@@ -341,6 +372,94 @@ def test_matching_config1_vs_oracle():
     ref = OM.template_scores(src, tar, mask, want_indices=True)
     for mode in ("bf16", "fp32"):
         _check_match(src, tar, mask, 5, mode, 0, ref=ref)
+
+
+def test_matching_config2_vs_oracle():
+    """BASELINE configs[1] (1 detection x 162 views x 1024 ch x 32^2 patches, the benched configuration) at FULL size
+    against the CPU oracle, in the bf16 mode the bench runs (scores within 1e-2 relative, indices exact outside the
+    1e-3 gap band) and in the fp32 mode (1e-5)."""
+    src, tar, planted = synth.planted_match_inputs(1, 162, 1024, 32, seed=0)
+    mask = synth.disc_mask(1)
+    ref = OM.template_scores(src, tar, mask, want_indices=True)
+    assert torch.topk(ref[0], 5, dim=1).indices[0].tolist() == planted[0, :5].tolist()
+    for mode in ("bf16", "fp32"):
+        _check_match(src, tar, mask, 5, mode, 0, ref=ref)
+
+
+def test_matching_config3_shape_vs_oracle():
+    """BASELINE configs[2] shape at reduced batch: 2 detections x 642 views x 1024 ch x 32^2 patches against ONE bank
+    shared through bank_index (as 64 detections share 8 object banks), different masks per detection; sim_avg, both
+    argmax maps and the top-5 against the CPU oracle in bf16 mode."""
+    g = torch.Generator().manual_seed(77)
+    N, C, H = 642, 1024, 32
+    bank = torch.randn(1, N, C, H, H, generator=g)
+    picks = [17, 600]
+    tar = torch.stack([bank[0, p] + 0.5 * torch.randn(C, H, H, generator=g) for p in picks])
+    for j, rho in enumerate((0.8, 0.6, 0.45, 0.3)):                 # a planted runner-up ladder for detection 0
+        bank[0, 100 + j] = rho * bank[0, picks[0]] + (1 - rho * rho) ** 0.5 * bank[0, 100 + j]
+    mask = torch.cat([synth.disc_mask(1), synth.bernoulli_mask(1, 224, 0.7, 5)])
+    sim = _check_match(bank, tar, mask, 5, "bf16", 0, bank_index=[0, 0])
+    assert sim.argmax(dim=1).tolist() == picks
+
+
+def test_negative_tied_rows_resolve_to_the_first_index():
+    """Every similarity of a row is the same NEGATIVE value (query = -v, all template patches = v): torch.max returns
+    index 0 for every row, so the reference's (idx != 0) rule invalidates every patch and sim_avg is exactly 0.  The row
+    keys of the contraction carry the lane in the low mantissa bits; for negative values the payload is inverted so that
+    the first index still wins."""
+    from picopose_b200.matching import template_scores
+    g = torch.Generator().manual_seed(3)
+    B, N, C, H = 1, 3, 64, 16
+    v = torch.randn(C, generator=g)
+    src = v.view(1, 1, C, 1, 1).expand(B, N, C, H, H).contiguous()
+    tar = (-v).view(1, C, 1, 1).expand(B, C, H, H).contiguous()
+    mask = torch.ones(B, 224, 224)
+    ref = OM.template_scores(src, tar, mask, want_indices=True)
+    assert float(ref[0].abs().max()) == 0.0 and int(ref[2].max()) == 0
+    for mode in ("bf16", "fp32"):
+        for cluster in (1, 2):
+            sim, sc, it, is_ = template_scores(src.to(DEV), tar.to(DEV), mask.to(DEV), mode=mode, want_indices=True, cluster=cluster)
+            assert int(it.max()) == 0 and int(is_.max()) == 0, (mode, cluster, it.unique().tolist())
+            assert float(sim.abs().max()) == 0.0
+            np.testing.assert_allclose(sc.cpu().numpy(), ref[1].numpy(), rtol=0, atol=MODE_TOL[mode])
+
+
+def test_bank_index_out_of_range_is_reported():
+    from picopose_b200 import matching as M
+    banks, tar, obj, _ = synth.shared_bank_inputs(2, 4, 64, 8, B=3, seed=4)
+    mask = synth.disc_mask(3).to(DEV)
+    bank = M.TemplateBank.from_features(banks.to(DEV))
+    with pytest.raises(IndexError):                                   # host index: checked before anything is launched
+        M.template_scores(bank, tar.to(DEV), mask, bank_index=torch.tensor([0, 2, 1]))
+    bad = torch.tensor([0, 7, 1], dtype=torch.int32, device=DEV)      # device index: clamped by the kernel and reported
+    M.template_scores(bank, tar.to(DEV), mask, bank_index=bad)
+    with pytest.raises(RuntimeError, match="bank index out of range"):
+        _lib.check_device_faults()
+    _lib.check_device_faults()                                        # the record is cleared by the read
+    good = M.template_scores(bank, tar.to(DEV), mask, bank_index=obj.to(DEV))
+    assert torch.isfinite(good).all()
+
+
+def test_inference_only_guard():
+    """No autograd through the kernels: an input that requires grad under grad mode raises instead of silently
+    cutting the graph (the reference calls these functions in forward_train)."""
+    from picopose_b200.corr_lookup import CorrLookup, bilinear_sample
+    from picopose_b200.matching import matching_features_similarity, matching_templates
+    src, tar, _ = synth.planted_match_inputs(1, 3, 64, 8, seed=1)
+    mask = synth.disc_mask(1).to(DEV)
+    t = tar.to(DEV).requires_grad_(True)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        matching_templates(src.to(DEV), t, None, mask, topk=2)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        matching_features_similarity(src[:, 0].to(DEV), t, mask, None)
+    with torch.no_grad():
+        matching_templates(src.to(DEV), t, None, mask, topk=2)        # fine under no_grad, as run_test.py:165 calls it
+    pyr, flow = synth.lookup_inputs(1, 8, 1, seed=1)
+    fl = flow.to(DEV).requires_grad_(True)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        CorrLookup(radius=2)([p.to(DEV) for p in pyr], fl)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        bilinear_sample(torch.randn(1, 4, 8, 8, device=DEV), fl, align_corners=True)
 
 
 @pytest.mark.parametrize("name", ["small", "medium"])
@@ -615,6 +734,33 @@ def test_matching_templates_dense_call_paths(monkeypatch):
         assert torch.equal(i0, i) and torch.equal(s0, s)
     assert i0[:, 0].cpu().tolist() == top1.tolist()
     _lib.check_device_faults()
+
+
+def test_topk_exchange_chunks_batches_beyond_one_wave():
+    """A block of the exchange kernel spins until its peers' blocks of the same detection have run, so a launch must not
+    exceed the blocks the device holds at once: pp_topk_exchange cuts larger batches into launches that fit (one rank
+    here, so only the chunk bookkeeping is exercised: 3000 detections > 148 SMs x 8 blocks)."""
+    import ctypes as C
+    lib = _lib.load()
+    B, N, k = 3000, 9, 4
+    nbytes = lib.pp_xchg_bytes(1, B, k)
+    buf, handle = C.c_void_p(), C.create_string_buffer(64)
+    _lib.check(lib.pp_xchg_create(nbytes, C.byref(buf), handle), "pp_xchg_create")
+    try:
+        peers = torch.tensor([buf.value], dtype=torch.int64, device=DEV)
+        g = torch.Generator().manual_seed(8)
+        full = torch.randn(B, N, generator=g).to(DEV)
+        sc = torch.empty(B, k, dtype=torch.float32, device=DEV)
+        ix = torch.empty(B, k, dtype=torch.int64, device=DEV)
+        for epoch in (1, 2):
+            _lib.check(lib.pp_topk_exchange(_lib.ptr(full), B, N, k, 100, _lib.ptr(peers), 0, 1, B, k, epoch, _lib.ptr(sc),
+                                            _lib.ptr(ix), torch.cuda.current_stream().cuda_stream), "pp_topk_exchange")
+            torch.cuda.synchronize()
+            rs, ri = torch.topk(full, k, dim=1)
+            assert torch.equal(sc, rs) and torch.equal(ix, ri + 100)
+        _lib.check_device_faults()
+    finally:
+        lib.pp_xchg_destroy(buf.value)
 
 
 def test_topk_exchange_three_ranks_on_one_gpu():

@@ -132,3 +132,56 @@ def test_stage3_correspondences():
     tar, src = OC.stage3_correspondences(torch.from_numpy(g["flow_r"]), torch.from_numpy(g["cert_r"]))
     np.testing.assert_array_equal(tar.numpy(), g["tar_r"])
     np.testing.assert_array_equal(src.numpy(), g["src_r"])
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: hypothesis selection, lookup + first motion-encoder conv, the FlowDecoder loop
+# ------------------------------------------------------------------------------------------------
+
+def _hyp_inputs(g):
+    ep = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in_")}
+    return ep, torch.from_numpy(g["pred_id"])
+
+
+def test_select_template_data_matches_reference():
+    from oracle import hypotheses_oracle as OH
+    g = load("hyp_select.npz")
+    ep, pred_id = _hyp_inputs(g)
+    for k in range(pred_id.shape[1]):
+        sel = OH.select_template_data(ep, pred_id, k)
+        assert set(sel) == set(OH.TEMPLATE_KEYS) | set(OH.REAL_KEYS)
+        for key, v in sel.items():
+            np.testing.assert_array_equal(v.numpy(), g[f"out{k}_{key}"])
+
+
+def test_lookup_then_first_motion_conv_matches_reference():
+    """corr_net[0] of the reference's MotionEncoder on the reference's lookup output: a 1x1 conv + ReLU, i.e. a
+    (256 x 50) matrix applied per query -- the step libpicopose_b200 fuses into the correlation kernel (f-3)."""
+    g = load("motion_conv.npz")
+    f1, f2, flow = (torch.from_numpy(g[k]) for k in ("f1", "f2", "flow"))
+    corr = OL.corr_lookup(OL.correlation_pyramid(f1, f2, 2), flow, 2)
+    np.testing.assert_allclose(corr.numpy(), g["corr"], rtol=0, atol=3e-6)
+    out = OL.conv1x1_relu(corr, torch.from_numpy(g["weight"]), torch.from_numpy(g["bias"]))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=0, atol=1e-5)
+
+
+def test_flow_decoder_restatement_matches_reference():
+    """The seeded restatement reproduces the reference FlowDecoder's weights (checksums of all 27 M parameters) and its
+    outputs on the seeded inputs (tests/golden/flow_decoder.npz was produced by the reference's own class)."""
+    import json
+    from oracle import flow_decoder_oracle as OF
+    g = load("flow_decoder.npz")
+    seed = int(g["seed"])
+    torch.manual_seed(seed)
+    dec = OF.FlowDecoder(3, 4).eval()
+    want = json.loads(str(g["checksums"]))
+    got = OF.weight_checksums(dec)
+    assert sorted(got) == sorted(want)
+    for k, (s, a) in want.items():
+        assert got[k][0] == pytest.approx(s, rel=1e-9, abs=1e-9) and got[k][1] == pytest.approx(a, rel=1e-9, abs=1e-9), k
+    render, real, flow0, cert0 = OF.decoder_inputs(seed + 1)
+    with torch.no_grad():
+        flows, certs = dec(render, real, flow0, cert0)
+    for i in range(3):
+        np.testing.assert_allclose(flows[i].numpy(), g[f"flow{i}"], rtol=0, atol=2e-4)
+        np.testing.assert_allclose(certs[i].numpy(), g[f"cert{i}"], rtol=0, atol=2e-4)
