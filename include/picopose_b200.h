@@ -71,6 +71,16 @@ PP_API int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, const i
                    const float* flow, int B, int H, int W, int radius,
                    float* out, void* stream);
 
+/* Same lookup on volumes in the TILED layout pp_correlation_pyramid_tiled writes: every (h x w) slice stored as 4-row x
+ * 8-column tiles of 32 floats (one 128-byte line per tile), tiles row-major inside the slice; element (y, x) lives at
+ * ((y/4) * (w/8) + x/8) * 32 + (y%4) * 8 + x%8.  DRAM moves whole 128-byte lines, and a lookup window crosses ~40 % fewer
+ * tiles than row segments.  Every level needs h % 4 == 0 and w % 8 == 0; radius 1..8.  Same output as pp_corr_lookup. */
+PP_API int pp_corr_lookup_tiled(const void* const* pyr_ptrs, const int* pyr_h, const int* pyr_w, int L,
+                         const float* flow, int B, int H, int W, int radius,
+                         float* out, void* stream);
+/* Layout change of `slices` (h x w) fp32 slices: to_tiled != 0 reference row-major -> tiled, else the way back. */
+PP_API int pp_volume_retile(const float* in, float* out, int64_t slices, int h, int w, int to_tiled, void* stream);
+
 /* Replaces bilinear_sample, utils/corr_lookup.py:29-65 (mode='bilinear', padding_mode='zeros');
  * used by FlowDecoder.feature_sample, model/stage3/flow_decoder.py:49-56.
  *   feat (N,C,Hf,Wf) fp32; grid (N,Ho,Wo,2) if grid_chw == 0 else (N,2,Ho,Wo); out (N,C,Ho,Wo).
@@ -202,6 +212,10 @@ PP_API int pp_match_similarity(const void* q_prep, const float* q_rnorm, const v
  *   level_ptrs[l]    : (N*H*W, 1, H>>l, W>>l) fp32 outputs (HOST array of DEVICE pointers), scale = 1/sqrt(C) */
 PP_API int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
                            int num_levels, void* const* level_ptrs, int cluster, void* stream);
+/* same volumes in the tiled layout of pp_corr_lookup_tiled (written that way by the contraction's epilogue and the
+ * pooling kernel; no extra pass) */
+PP_API int pp_correlation_pyramid_tiled(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
+                                 int num_levels, void* const* level_ptrs, int cluster, void* stream);
 
 /* Fused CorrelationPyramid + CorrLookup (model/stage3/raft_decoder.py:30-53 followed by
  * utils/corr_lookup.py:100-134, as called back to back in model/stage3/flow_decoder.py:59-61) that never builds the

@@ -25,6 +25,8 @@ SIGNATURES = {
     "pp_launch_count": (C.c_longlong, []),
     "pp_profile_gemm_events": (None, [_vp, _vp]),
     "pp_corr_lookup": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "pp_corr_lookup_tiled": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "pp_volume_retile": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     "pp_bilinear_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_match_kp": (_i, [_i, _i]),
     "pp_match_prepare": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -53,6 +55,7 @@ SIGNATURES = {
     "pp_match_similarity_workspace": (_sz, [_i, _i]),
     "pp_match_similarity": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pp_correlation_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), _i, _vp]),
+    "pp_correlation_pyramid_tiled": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), _i, _vp]),
     "pp_windowed_correlation_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_windowed_correlation_prepare_all": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.POINTER(_vp), _vp]),
     "pp_windowed_correlation": (_i, [_vp, C.POINTER(_vp), _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

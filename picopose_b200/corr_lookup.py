@@ -50,7 +50,14 @@ def bilinear_sample(feat: Tensor, grid: Tensor, mode: str = 'bilinear', padding_
 
 
 def corr_lookup(corr_pyramid: Sequence[Tensor], flow: Tensor, radius: int) -> Tensor:
-    """Functional form of CorrLookup.forward -> (B, L*(2r+1)^2, H, W) fp32."""
+    """Functional form of CorrLookup.forward -> (B, L*(2r+1)^2, H, W) fp32.  A `TiledPyramid` is read in its own
+    layout (radius 1..8), anything else as the reference's list of row-major volumes."""
+    from .correlation import TiledPyramid
+    tiled = isinstance(corr_pyramid, TiledPyramid)
+    if tiled and not 1 <= int(radius) <= 8:
+        tiled, corr_pyramid = False, corr_pyramid.rowmajor()
+    if tiled:
+        corr_pyramid = corr_pyramid.tiled_levels
     _lib.require_cuda(flow, *corr_pyramid)
     _lib.require_inference("CorrLookup", flow, *corr_pyramid)
     lib = _lib.load()
@@ -71,9 +78,10 @@ def corr_lookup(corr_pyramid: Sequence[Tensor], flow: Tensor, radius: int) -> Te
     ptrs = (C.c_void_p * L)(*[v.data_ptr() for v in vols])
     hs = (C.c_int * L)(*[v.shape[2] for v in vols])
     ws = (C.c_int * L)(*[v.shape[3] for v in vols])
+    fn = lib.pp_corr_lookup_tiled if tiled else lib.pp_corr_lookup
     with torch.cuda.device(flow.device):
-        _lib.check(lib.pp_corr_lookup(ptrs, hs, ws, L, _lib.ptr(flow), B, H, W, int(radius), _lib.ptr(out),
-                                      _lib.stream_of(flow)), "pp_corr_lookup")
+        _lib.check(fn(ptrs, hs, ws, L, _lib.ptr(flow), B, H, W, int(radius), _lib.ptr(out), _lib.stream_of(flow)),
+                   "pp_corr_lookup")
     return out
 
 
@@ -102,5 +110,5 @@ class CorrLookup(nn.Module):
             if corr_pyramid.fusable(self.r):
                 # fused CorrelationPyramid + lookup: the all-pairs volume is never built
                 return windowed_correlation(corr_pyramid.feat1, corr_pyramid.feat2, flow, corr_pyramid.num_levels, self.r)
-            corr_pyramid = corr_pyramid.materialise()
+            corr_pyramid = corr_pyramid.for_lookup(self.r)
         return corr_lookup(corr_pyramid, flow, self.r)

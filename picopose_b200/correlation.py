@@ -20,9 +20,65 @@ def default_corr_mode() -> str:
     return os.environ.get("PICOPOSE_B200_CORR_MODE", "fp32")
 
 
+def tileable(H: int, W: int, num_levels: int) -> bool:
+    """Every level of an (H x W) pyramid can be stored as 4 x 8 tiles (h % 4 == 0, w % 8 == 0, exact halvings)."""
+    s = 1 << (num_levels - 1)
+    return H % s == 0 and W % s == 0 and (H // s) % 4 == 0 and (W // s) % 8 == 0
+
+
+def retile_volume(vol: torch.Tensor, to_tiled: bool = True) -> torch.Tensor:
+    """(Q, 1, h, w) fp32 slices: reference row-major layout <-> the tiled layout of `TiledPyramid` (a permutation
+    inside every slice; the tensor keeps its logical shape)."""
+    _lib.require_cuda(vol)
+    lib = _lib.load()
+    vol = vol.float().contiguous()
+    Q, _, h, w = vol.shape
+    out = torch.empty_like(vol)
+    with torch.cuda.device(vol.device):
+        _lib.check(lib.pp_volume_retile(_lib.ptr(vol), _lib.ptr(out), Q, h, w, int(bool(to_tiled)), _lib.stream_of(vol)),
+                   "pp_volume_retile")
+    return out
+
+
+class TiledPyramid(Sequence):
+    """A correlation pyramid whose slices are stored as 4-row x 8-column tiles, one 128-byte line per tile.
+
+    DRAM moves whole 128-byte lines on this GPU, so what a lookup window costs is the number of lines it touches: a
+    (2r+2)^2 window crosses ~6.9 tiles at r = 4 against ~11.7 row segments in the reference's row-major slices.  Our own
+    CorrelationPyramid can write this layout at no extra cost (the contraction's epilogue and the pooling kernel address
+    it directly); `CorrLookup` recognises the type and reads it with `pp_corr_lookup_tiled`.  Any other consumer that
+    indexes or iterates it gets the reference's row-major volumes (converted once, on demand).
+    """
+
+    def __init__(self, tiled_levels):
+        self.tiled_levels = list(tiled_levels)        # logical shape (Q, 1, h, w), tiled storage
+        self._rowmajor = None
+
+    @classmethod
+    def from_volumes(cls, volumes) -> "TiledPyramid":
+        return cls([retile_volume(v, True) for v in volumes])
+
+    def rowmajor(self):
+        if self._rowmajor is None:
+            self._rowmajor = [retile_volume(v, False) for v in self.tiled_levels]
+        return self._rowmajor
+
+    def __len__(self):
+        return len(self.tiled_levels)
+
+    def __getitem__(self, i):
+        return self.rowmajor()[i]
+
+    def __iter__(self):
+        return iter(self.rowmajor())
+
+
 def correlation_pyramid(feat1: torch.Tensor, feat2: torch.Tensor, num_levels: int,
-                        mode: Optional[str] = None) -> Sequence[torch.Tensor]:
-    """-> [ (N*H*W, 1, H>>l, W>>l) fp32 for l in range(num_levels) ], corr = <f1, f2> / sqrt(C), 2x2 average pools."""
+                        mode: Optional[str] = None, layout: str = "rowmajor"):
+    """-> [ (N*H*W, 1, H>>l, W>>l) fp32 for l in range(num_levels) ], corr = <f1, f2> / sqrt(C), 2x2 average pools.
+    layout="tiled" returns a `TiledPyramid` (same values, lookup-friendly storage)."""
+    if layout not in ("rowmajor", "tiled"):
+        raise ValueError("layout must be 'rowmajor' or 'tiled'")
     _lib.require_cuda(feat1, feat2)
     _lib.require_inference("CorrelationPyramid", feat1, feat2)
     lib = _lib.load()
@@ -35,11 +91,17 @@ def correlation_pyramid(feat1: torch.Tensor, feat2: torch.Tensor, num_levels: in
     levels = [torch.empty(N * H * W, 1, H >> l, W >> l, dtype=torch.float32, device=feat1.device)
               for l in range(num_levels)]
     ptrs = (C.c_void_p * num_levels)(*[t.data_ptr() for t in levels])
+    if layout == "tiled" and not tileable(H, W, num_levels):
+        raise ValueError(f"a {H}x{W} pyramid of {num_levels} levels cannot be tiled (every level needs h % 4 == 0, w % 8 == 0)")
+    fn = lib.pp_correlation_pyramid_tiled if layout == "tiled" else lib.pp_correlation_pyramid
     with torch.cuda.device(feat1.device):
-        _lib.check(lib.pp_correlation_pyramid(_lib.ptr(a), _lib.ptr(b), N, H, W, a.shape[-1], 1.0 / math.sqrt(Cc),
-                                              num_levels, ptrs, default_cluster(), _lib.stream_of(feat1)),
-                   "pp_correlation_pyramid")
-    return levels
+        _lib.check(fn(_lib.ptr(a), _lib.ptr(b), N, H, W, a.shape[-1], 1.0 / math.sqrt(Cc),
+                      num_levels, ptrs, default_cluster(), _lib.stream_of(feat1)), "pp_correlation_pyramid")
+    return TiledPyramid(levels) if layout == "tiled" else levels
+
+
+def tiled_layout_enabled() -> bool:
+    return os.environ.get("PICOPOSE_B200_TILED_VOLUME", "1") != "0"
 
 
 def fused_corr_enabled() -> bool:
@@ -91,6 +153,16 @@ class LazyCorrelationPyramid(Sequence):
         if self._volumes is None:
             self._volumes = correlation_pyramid(self.feat1, self.feat2, self.num_levels)
         return self._volumes
+
+    def for_lookup(self, radius: int):
+        """The volumes for a CorrLookup that cannot take the fused path: tiled when the shapes allow (nobody else sees
+        them), else the reference layout."""
+        if self._volumes is not None:
+            return self._volumes
+        H, W = self.feat1.shape[-2:]
+        if tiled_layout_enabled() and 1 <= radius <= 8 and tileable(H, W, self.num_levels):
+            return correlation_pyramid(self.feat1, self.feat2, self.num_levels, layout="tiled")
+        return self.materialise()
 
     def fusable(self, radius: int) -> bool:
         Cc = self.feat1.shape[1]

@@ -25,6 +25,7 @@ struct LookupParams {
     int vh[LOOKUP_MAX_LEVELS];
     int vw[LOOKUP_MAX_LEVELS];
     int vec_ok[LOOKUP_MAX_LEVELS];  // 16-byte path usable (width % 4 == 0, base aligned)
+    int tiled;                      // slices stored as 4 x 8 tiles of 32 floats (one 128-byte line each), tiles row-major
     int L;
     const float* flow;
     float* out;
@@ -80,7 +81,13 @@ struct LookupCfg {
     static constexpr int WARP_WORDS = 32 * QS;
 };
 
-template <int R, int JB>
+// TILED: every (Hl x Wl) slice is stored as 4-row x 8-column tiles, one 128-byte line per tile (our own
+// CorrelationPyramid writes it that way on request).  DRAM moves whole 128-byte lines on this GPU
+// (profiles/r1w_dram_granularity.md), and a (2r+2)^2 window crosses ((2r+1)/8 + 1) * ((2r+1)/4 + 1) tiles on average --
+// 6.9 lines at r = 4 -- instead of (2r+2) * 1.17 row segments (11.7 lines) in the reference's row-major slices.  Only the
+// global address of a 16-byte piece changes: pieces are 4-aligned in x, tile rows are 8 floats, so a piece never
+// straddles two tiles; the staged footprint in shared memory and everything after it are the same.
+template <int R, int JB, bool TILED>
 __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupParams p) {
     using Cfg = LookupCfg<R, JB>;
     constexpr int D = Cfg::D, NB = Cfg::NB, NRB = Cfg::NRB, NV = Cfg::NV, PITCH = Cfg::PITCH, QS = Cfg::QS;
@@ -156,7 +163,10 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                         const int x = qx + 4 * v;
                         const bool need = slot_ok && row < (qp >> 26) && v < ((qp >> 20) & 63);
                         const bool inb = (unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl && ql < nq;
-                        const float* src = vol_g + (size_t)(inb ? ql : 0) * slice + (uint32_t)(inb ? y * Wl + x : 0);
+                        const uint32_t off = !inb ? 0u
+                                             : TILED ? (uint32_t)((((y >> 2) * (Wl >> 3) + (x >> 3)) << 5) + ((y & 3) << 3) + (x & 7))
+                                                     : (uint32_t)(y * Wl + x);
+                        const float* src = vol_g + (size_t)(inb ? ql : 0) * slice + off;
                         if (need) cp_async16_zfill(dst0 + ql * QS, src, inb ? 16u : 0u);
                     }
                 }
@@ -376,25 +386,29 @@ static int grid_for(long long items, int wpb, size_t smem) {
     return (int)(want < cap ? want : cap);
 }
 
-template <int R, int JB>
-static int launch_banded(const LookupParams& p, cudaStream_t st) {
+template <int R, int JB, bool TILED>
+static int launch_banded_l(const LookupParams& p, cudaStream_t st) {
     using Cfg = LookupCfg<R, JB>;
     const size_t per_warp = (size_t)Cfg::WARP_WORDS * sizeof(float);
     // blocks of up to 4 warps, sized so that at least two blocks share an SM
     int wpb = (int)((110 * 1024) / per_warp);
     wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
     const size_t smem = per_warp * wpb;
-    PP_CUDA(cudaFuncSetAttribute(corr_lookup_banded_kernel<R, JB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_lookup_banded_kernel<R, JB><<<grid_for((long long)p.total_groups * p.L, wpb, smem), wpb * 32, smem, st>>>(p);
+    PP_CUDA(cudaFuncSetAttribute(corr_lookup_banded_kernel<R, JB, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    corr_lookup_banded_kernel<R, JB, TILED><<<grid_for((long long)p.total_groups * p.L, wpb, smem), wpb * 32, smem, st>>>(p);
     PP_LAUNCHED();
     return PP_OK;
+}
+template <int R, int JB>
+static int launch_banded(const LookupParams& p, cudaStream_t st) {
+    return p.tiled ? launch_banded_l<R, JB, true>(p, st) : launch_banded_l<R, JB, false>(p, st);
 }
 
 }  // namespace pp
 
-extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, const int* pyr_w, int L,
-                              const float* flow, int B, int H, int W, int radius, float* out, void* stream) {
-    using namespace pp;
+namespace pp {
+static int corr_lookup_impl(const void* const* pyr_ptrs, const int* pyr_h, const int* pyr_w, int L,
+                            const float* flow, int B, int H, int W, int radius, float* out, void* stream, bool tiled) {
     if (int rc = require_sm100()) return rc;
     if (B == 0) return PP_OK;  // empty batch: nothing to do (pointers of empty tensors may be null)
     PP_CHECK_ARG(pyr_ptrs && pyr_h && pyr_w && flow && out, "pp_corr_lookup: null pointer");
@@ -413,7 +427,13 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
         p.vw[l] = pyr_w[l];
         p.vec_ok[l] = (pyr_w[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(pyr_ptrs[l]) & 15) == 0);
         all_vec = all_vec && p.vec_ok[l];
+        if (tiled)
+            PP_CHECK_ARG(pyr_w[l] % 8 == 0 && pyr_h[l] % 4 == 0 && p.vec_ok[l],
+                         "pp_corr_lookup_tiled: level %d is %dx%d; tiled slices need H %% 4 == 0, W %% 8 == 0, 16-byte alignment", l,
+                         pyr_h[l], pyr_w[l]);
     }
+    p.tiled = tiled ? 1 : 0;
+    PP_CHECK_ARG(!tiled || (radius >= 1 && radius <= 8), "pp_corr_lookup_tiled: radius 1..8 (got %d)", radius);
     const int D = 2 * radius + 1;
     PP_CHECK_ARG((long long)L * D * D * H * W < (1LL << 31), "pp_corr_lookup: output per detection exceeds 2^31 elements");
     p.flow = flow;
@@ -453,6 +473,17 @@ extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, con
     corr_lookup_generic_kernel<<<grid_for(p.total_groups, wpb, smem), wpb * 32, smem, st>>>(p);
     PP_LAUNCHED();
     return PP_OK;
+}
+}  // namespace pp
+
+extern "C" int pp_corr_lookup(const void* const* pyr_ptrs, const int* pyr_h, const int* pyr_w, int L,
+                              const float* flow, int B, int H, int W, int radius, float* out, void* stream) {
+    return pp::corr_lookup_impl(pyr_ptrs, pyr_h, pyr_w, L, flow, B, H, W, radius, out, stream, false);
+}
+
+extern "C" int pp_corr_lookup_tiled(const void* const* pyr_ptrs, const int* pyr_h, const int* pyr_w, int L,
+                                    const float* flow, int B, int H, int W, int radius, float* out, void* stream) {
+    return pp::corr_lookup_impl(pyr_ptrs, pyr_h, pyr_w, L, flow, B, H, W, radius, out, stream, true);
 }
 
 extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, int C, int Hf, int Wf, int Ho,

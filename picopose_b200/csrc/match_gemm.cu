@@ -63,6 +63,8 @@ struct GemmParams {
     unsigned long long* colkey;    // (B, N, T)
     float* emit;                   // EPI_EMIT: (B*N, T, T) raw products times emit_scale
     float emit_scale;
+    int emit_tile_w;               // EPI_EMIT: 0 = rows of T keys (reference layout); W > 0 = every row is an (T/W x W) key map
+                                   // stored as 4 x 8 tiles of 32 floats (one 128-byte line each), see corr_lookup.cu
     int* fault;                    // host-mapped fault record
 };
 
@@ -443,7 +445,25 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     const int s0 = tc.nt * BLOCK_N + c * 32;
                     if (s0 >= T) continue;  // warp-uniform: chunk entirely past the last template patch
                     const int ncols = min(32, T - s0);
-                    if (row_ok) {
+                    if (row_ok && p.emit_tile_w > 0) {
+                        // tiled key map: 8 consecutive keys (one row segment of a 4 x 8 tile) = 32 contiguous bytes
+                        const int Wk = p.emit_tile_w, tpr = Wk >> 3;
+                        float* slice = p.emit + (bn * T + t) * (size_t)T;
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {
+                            const int s = s0 + 8 * gq;
+                            if (s < T) {  // T % 8 == 0 (checked on the host)
+                                const int y = s / Wk, x = s - y * Wk;
+                                float* dst = slice + (size_t)(((y >> 2) * tpr + (x >> 3)) * 32 + (y & 3) * 8);
+                                *reinterpret_cast<float4*>(dst) =
+                                    make_float4(__uint_as_float(v[8 * gq]) * p.emit_scale, __uint_as_float(v[8 * gq + 1]) * p.emit_scale,
+                                                __uint_as_float(v[8 * gq + 2]) * p.emit_scale, __uint_as_float(v[8 * gq + 3]) * p.emit_scale);
+                                *reinterpret_cast<float4*>(dst + 4) =
+                                    make_float4(__uint_as_float(v[8 * gq + 4]) * p.emit_scale, __uint_as_float(v[8 * gq + 5]) * p.emit_scale,
+                                                __uint_as_float(v[8 * gq + 6]) * p.emit_scale, __uint_as_float(v[8 * gq + 7]) * p.emit_scale);
+                            }
+                        }
+                    } else if (row_ok) {
                         float* dst = p.emit + (bn * T + t) * (size_t)T + s0;
                         if (ncols == 32 && (T & 3) == 0) {
 #pragma unroll
@@ -549,7 +569,9 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                    int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
                    const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
-                   cudaStream_t st) {
+                   cudaStream_t st, int emit_tile_w) {
+    PP_CHECK_ARG(emit_tile_w == 0 || (epi == EPI_EMIT && emit_tile_w % 8 == 0 && T % emit_tile_w == 0 && (T / emit_tile_w) % 4 == 0),
+                 "tiled emit needs a key map of W %% 8 == 0 columns and H %% 4 == 0 rows (W=%d, T=%d)", emit_tile_w, T);
     PP_CHECK_ARG(Kp > 0 && Kp % BLOCK_K == 0, "Kp must be a positive multiple of %d (got %d)", BLOCK_K, Kp);
     PP_CHECK_ARG((reinterpret_cast<uintptr_t>(q_prep) & 127) == 0 && (reinterpret_cast<uintptr_t>(bank_prep) & 127) == 0,
                  "prepared operands must be 128-byte aligned");
@@ -580,6 +602,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.colkey = colkey;
     p.emit = emit;
     p.emit_scale = emit_scale;
+    p.emit_tile_w = emit_tile_w;
     p.fault = g_fault_dev;
     if (p.total_tiles == 0) return PP_OK;
     // A = M-side operand (box of 128 rows), B = N-side operand (box of 256 / cluster rows); EPI_MATCH puts the template

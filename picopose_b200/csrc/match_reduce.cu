@@ -10,7 +10,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                    int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
                    const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
-                   cudaStream_t st);
+                   cudaStream_t st, int emit_tile_w = 0);
 
 int prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm, int Wm, int mode,
                        void* q_prep, float* q_rnorm, void* q_meta, void* clear, size_t clear_bytes, void* stream);
@@ -217,6 +217,71 @@ __global__ void avgpool2_kernel(const float* __restrict__ in, long long slices, 
     }
 }
 
+// Offset of key (y, x) inside a slice stored as 4 x 8 tiles (32 floats = one 128-byte line per tile), tiles row-major.
+__host__ __device__ __forceinline__ int tiled_offset(int y, int x, int w) {
+    return ((y >> 2) * (w >> 3) + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7);
+}
+
+// AvgPool2d(2, 2) between two TILED levels: a thread makes one output tile row (8 outputs) from a 2 x 16 patch of the
+// level below, i.e. 16-byte loads and two 16-byte stores.
+__global__ void avgpool2_tiled_kernel(const float* __restrict__ in, long long slices, int h, int w, float* __restrict__ out) {
+    const int ho = h >> 1, wo = w >> 1;
+    const int rows_per_slice = ho * (wo >> 3);       // output tile rows of 8 floats
+    const long long total = slices * rows_per_slice;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i / rows_per_slice;
+        const int r = (int)(i - q * rows_per_slice);
+        // enumerate in the OUTPUT's memory order: tile (ty, tx), row-in-tile ry
+        const int tpr = wo >> 3;
+        const int tile = r >> 2, ry = r & 3;
+        const int ty = tile / tpr, tx = tile - ty * tpr;
+        const int y = ty * 4 + ry, x = tx * 8;
+        const float* s = in + q * (long long)h * w;
+        float o[8];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {          // input columns 2x .. 2x+15 = two input tiles side by side
+            const int xi = 2 * x + 8 * half;
+            const float4 a0 = *reinterpret_cast<const float4*>(s + tiled_offset(2 * y, xi, w));
+            const float4 a1 = *reinterpret_cast<const float4*>(s + tiled_offset(2 * y, xi, w) + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s + tiled_offset(2 * y + 1, xi, w));
+            const float4 b1 = *reinterpret_cast<const float4*>(s + tiled_offset(2 * y + 1, xi, w) + 4);
+            // same association as the row-major kernel: (s[0] + s[1] + s[w] + s[w+1]) * 0.25
+            o[4 * half + 0] = (a0.x + a0.y + b0.x + b0.y) * 0.25f;
+            o[4 * half + 1] = (a0.z + a0.w + b0.z + b0.w) * 0.25f;
+            o[4 * half + 2] = (a1.x + a1.y + b1.x + b1.y) * 0.25f;
+            o[4 * half + 3] = (a1.z + a1.w + b1.z + b1.w) * 0.25f;
+        }
+        float* d = out + q * (long long)ho * wo + tiled_offset(y, x, wo);
+        *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// Layout change of a stack of (h x w) slices between the reference's row-major form and the tiled one (a permutation
+// inside every slice); a thread moves 8 floats.
+__global__ void retile_kernel(const float* __restrict__ in, long long slices, int h, int w, int to_tiled, float* __restrict__ out) {
+    const int units = h * (w >> 3);
+    const long long total = slices * units;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i / units;
+        const int u = (int)(i - q * units);
+        // u enumerates the TILED order (tile, row in tile): contiguous on the tiled side
+        const int tpr = w >> 3;
+        const int tile = u >> 2, ry = u & 3;
+        const int ty = tile / tpr, tx = tile - ty * tpr;
+        const int y = ty * 4 + ry, x = tx * 8;
+        const long long base = q * (long long)h * w;
+        const long long lin = base + (long long)y * w + x, til = base + (long long)u * 8;
+        const float* s = in + (to_tiled ? lin : til);
+        float* d = out + (to_tiled ? til : lin);
+        const float4 v0 = *reinterpret_cast<const float4*>(s), v1 = *reinterpret_cast<const float4*>(s + 4);
+        *reinterpret_cast<float4*>(d) = v0;
+        *reinterpret_cast<float4*>(d + 4) = v1;
+    }
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace pp
@@ -368,32 +433,65 @@ extern "C" int pp_match_similarity(const void* q_prep, const float* q_rnorm, con
     return PP_OK;
 }
 
-extern "C" int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
-                                      int num_levels, void* const* level_ptrs, int cluster, void* stream) {
-    using namespace pp;
+namespace pp {
+static int correlation_pyramid_impl(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
+                                    int num_levels, void* const* level_ptrs, int cluster, void* stream, bool tiled) {
     if (int rc = require_sm100()) return rc;
     if (N == 0) return PP_OK;
     PP_CHECK_ARG(f1_prep && f2_prep && level_ptrs, "pp_correlation_pyramid: null pointer");
     PP_CHECK_ARG(N > 0 && H > 0 && W > 0 && num_levels >= 1 && num_levels <= 8, "pp_correlation_pyramid: bad shape");
     for (int l = 0; l < num_levels; ++l) PP_CHECK_ARG(level_ptrs[l], "pp_correlation_pyramid: null level %d", l);
     PP_CHECK_ARG((H >> (num_levels - 1)) >= 1 && (W >> (num_levels - 1)) >= 1, "pp_correlation_pyramid: too many levels for %dx%d", H, W);
+    if (tiled)
+        PP_CHECK_ARG((W >> (num_levels - 1)) % 8 == 0 && (H >> (num_levels - 1)) % 4 == 0 && W % (1 << (num_levels - 1)) == 0 &&
+                         H % (1 << (num_levels - 1)) == 0,
+                     "pp_correlation_pyramid_tiled: every level needs W %% 8 == 0 and H %% 4 == 0 (%dx%d, %d levels)", H, W, num_levels);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int T = H * W;
     // all-pairs products <f1[:, q], f2[:, key]> * scale straight into level 0: (N*H*W, 1, H, W) is row-major [q][key]
     if (int rc = run_match_gemm(1, f1_prep, f2_prep, N, nullptr, N, 1, T, Kp, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                nullptr, nullptr, static_cast<float*>(level_ptrs[0]), scale, cluster, st))
+                                nullptr, nullptr, static_cast<float*>(level_ptrs[0]), scale, cluster, st, tiled ? W : 0))
         return rc;
     int h = H, w = W;
     for (int l = 1; l < num_levels; ++l) {
         const long long slices = (long long)N * T;
-        const long long total = slices * (h >> 1) * (w >> 1);
+        const long long total = tiled ? slices * (h >> 1) * (w >> 4) : slices * (h >> 1) * (w >> 1);
         int grid = (int)((total + 255) / 256 < (long long)sm_count() * 32 ? (total + 255) / 256 : (long long)sm_count() * 32);
-        avgpool2_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(level_ptrs[l - 1]), slices, h, w,
-                                              static_cast<float*>(level_ptrs[l]));
+        if (tiled)
+            avgpool2_tiled_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(level_ptrs[l - 1]), slices, h, w,
+                                                        static_cast<float*>(level_ptrs[l]));
+        else
+            avgpool2_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(level_ptrs[l - 1]), slices, h, w,
+                                                  static_cast<float*>(level_ptrs[l]));
         PP_LAUNCHED();
         h >>= 1;
         w >>= 1;
     }
+    return PP_OK;
+}
+}  // namespace pp
+
+extern "C" int pp_correlation_pyramid(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
+                                      int num_levels, void* const* level_ptrs, int cluster, void* stream) {
+    return pp::correlation_pyramid_impl(f1_prep, f2_prep, N, H, W, Kp, scale, num_levels, level_ptrs, cluster, stream, false);
+}
+
+extern "C" int pp_correlation_pyramid_tiled(const void* f1_prep, const void* f2_prep, int N, int H, int W, int Kp, float scale,
+                                            int num_levels, void* const* level_ptrs, int cluster, void* stream) {
+    return pp::correlation_pyramid_impl(f1_prep, f2_prep, N, H, W, Kp, scale, num_levels, level_ptrs, cluster, stream, true);
+}
+
+extern "C" int pp_volume_retile(const float* in, float* out, int64_t slices, int h, int w, int to_tiled, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (slices == 0) return PP_OK;
+    PP_CHECK_ARG(in && out && in != out, "pp_volume_retile: null pointer or in-place call");
+    PP_CHECK_ARG(slices > 0 && h > 0 && w > 0 && w % 8 == 0 && h % 4 == 0, "pp_volume_retile: slices of H %% 4 == 0 rows and W %% 8 == 0 columns (got %dx%d)", h, w);
+    PP_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pp_volume_retile: 16-byte alignment");
+    const long long total = (long long)slices * h * (w >> 3);
+    int grid = (int)((total + 255) / 256 < (long long)sm_count() * 32 ? (total + 255) / 256 : (long long)sm_count() * 32);
+    retile_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, (long long)slices, h, w, to_tiled ? 1 : 0, out);
+    PP_LAUNCHED();
     return PP_OK;
 }
 

@@ -69,6 +69,61 @@ def test_corr_lookup_vs_oracle(B, H, L, r, sigma):
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("B,H,L,r,sigma", [
+    (2, 16, 1, 2, 2.0), (1, 32, 2, 2, 3.0), (1, 64, 3, 2, 4.0), (2, 64, 1, 4, 4.0), (1, 64, 1, 5, 4.0), (1, 64, 1, 6, 4.0),
+    (1, 64, 1, 7, 4.0), (1, 64, 1, 8, 4.0), (1, 64, 3, 4, 4.0), (1, 32, 2, 3, 30.0), (1, 64, 2, 1, 1.0), (1, 32, 1, 8, 6.0),
+])
+def test_corr_lookup_tiled_layout_vs_oracle(B, H, L, r, sigma):
+    """The tiled volume layout (4 x 8 tiles = one 128-byte line each): a retiled copy of the oracle's pyramid gives the
+    oracle's lookup; the round trip of the layout change is the identity; and the tiled and row-major kernels agree
+    bit for bit (same taps, same staged footprint, only the global addresses differ)."""
+    from picopose_b200.corr_lookup import CorrLookup, corr_lookup
+    from picopose_b200.correlation import TiledPyramid, retile_volume
+    pyr, flow = synth.lookup_inputs(B, H, L, seed=17 + r, flow_sigma=sigma)
+    ref = OL.corr_lookup(pyr, flow, r)
+    pyr_d = [p.to(DEV) for p in pyr]
+    tp = TiledPyramid.from_volumes(pyr_d)
+    for lv, t in zip(pyr_d, tp.tiled_levels):
+        assert torch.equal(retile_volume(t, False), lv)
+    h, w = pyr[0].shape[-2:]                                             # explicit address check of one element
+    y, x = 5, 11
+    assert float(tp.tiled_levels[0][3].flatten()[((y // 4) * (w // 8) + x // 8) * 32 + (y % 4) * 8 + x % 8]) == float(pyr[0][3, 0, y, x])
+    out = CorrLookup(radius=r)(tp, flow.to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
+    assert torch.equal(out, corr_lookup(pyr_d, flow.to(DEV), r))
+    assert torch.equal(tp[0], pyr_d[0]) and len(tp) == L                 # other consumers see the reference layout
+
+
+def test_tiled_pyramid_from_the_contraction():
+    """CorrelationPyramid written directly in the tiled layout (tcgen05 epilogue + tiled pooling) equals the row-major
+    pyramid retiled, level by level; and a CorrLookup that cannot take the fused path (radius beyond the fused
+    kernels' range is not needed for that: the fused path is switched off) reads it in place."""
+    from picopose_b200.corr_lookup import CorrLookup
+    from picopose_b200.correlation import (CorrelationPyramid, LazyCorrelationPyramid, TiledPyramid, correlation_pyramid,
+                                           retile_volume)
+    gen = torch.Generator().manual_seed(44)
+    for (N, C, H, L) in ((2, 64, 16, 1), (1, 256, 32, 2), (1, 128, 64, 3)):
+        f1 = torch.randn(N, C, H, H, generator=gen).to(DEV)
+        f2 = torch.randn(N, C, H, H, generator=gen).to(DEV)
+        rm = correlation_pyramid(f1, f2, L)
+        tp = correlation_pyramid(f1, f2, L, layout="tiled")
+        assert isinstance(tp, TiledPyramid)
+        for a, b in zip(rm, tp.tiled_levels):
+            assert torch.equal(retile_volume(a, True), b)
+        ref = OL.correlation_pyramid(f1.cpu(), f2.cpu(), L)
+        for a, b in zip(tp, ref):
+            np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=0, atol=3e-5)
+        flow = 3.0 * torch.randn(N, 2, H, H, generator=gen)
+        lazy = LazyCorrelationPyramid(f1, f2, L)
+        vols = lazy.for_lookup(4)
+        assert isinstance(vols, TiledPyramid)
+        out = CorrLookup(radius=4)(vols, flow.to(DEV))
+        np.testing.assert_allclose(out.cpu().numpy(), OL.corr_lookup(ref, flow, 4).numpy(), rtol=0, atol=5e-5)
+    with pytest.raises(ValueError):
+        correlation_pyramid(f1[:, :, :12, :12].contiguous(), f2[:, :, :12, :12].contiguous(), 1, layout="tiled")
+    _lib.check_device_faults()
+
+
 def test_corr_lookup_edge_cases():
     from picopose_b200.corr_lookup import corr_lookup
     # integer flows put every tap exactly on a pixel; huge / non-finite flows fall entirely into padding

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default=None)
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to try (32/64/128), 0 = leave")
+    ap.add_argument("--layouts", nargs="+", default=["rowmajor", "tiled"], help="volume layouts to time (rowmajor = reference, tiled = TiledPyramid)")
+    ap.add_argument("--once", action="store_true", help="one warm-up and one timed launch per case (for ncu captures)")
     args = ap.parse_args()
     if args.l2_fetch:
         import ctypes
@@ -34,6 +36,7 @@ def main():
         rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
         print("cudaLimitMaxL2FetchGranularity set rc=%d now=%d" % (rc, val.value), flush=True)
     from picopose_b200.corr_lookup import corr_lookup
+    from picopose_b200.correlation import TiledPyramid
     dev = "cuda:0"
     B, H, L = args.batch, args.size, args.levels
     Q = B * H * H
@@ -45,28 +48,35 @@ def main():
     if os.path.exists(p):
         peak = float(json.load(open(p)).get("hbm_gbs", peak))
     rows = []
-    for r in args.radii:
-        D = 2 * r + 1
-        per_q = 8 + L * D * D * 4 + sum(min((2 * r + 2) ** 2, (H >> i) ** 2) * 4 for i in range(L))
-        for _ in range(3):
-            out = corr_lookup(pyr, flow, r)
-        torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.iters)]
-        for a, b in ev:
-            a.record()
-            out = corr_lookup(pyr, flow, r)
-            b.record()
-        torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b) for a, b in ev)
-        med = ts[len(ts) // 2]
-        gbs = Q * per_q / (med * 1e-3) / 1e9
-        inb = float((out != 0).float().mean())
-        rows.append({"radius": r, "queries": Q, "bytes_per_query": per_q, "ms_median": med, "ms_min": ts[0],
-                     "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak, "nonzero_fraction_of_outputs": inb,
-                     "Mqueries_per_s": Q / med / 1e3})
-        print("r=%d  %.3f ms (min %.3f)  %.0f GB/s algorithmic = %.1f%% of %.0f GB/s   %.0f Mq/s   nonzero outputs %.1f%%"
-              % (r, med, ts[0], gbs, 100 * gbs / peak, peak, Q / med / 1e3, 100 * inb), flush=True)
-        del out
+    vols = {"rowmajor": pyr}
+    if "tiled" in args.layouts:
+        vols["tiled"] = TiledPyramid.from_volumes(pyr)          # the same values, 4 x 8 tiles per 128-byte line
+    iters, warm = (1, 1) if args.once else (args.iters, 3)
+    for layout in args.layouts:
+        for r in args.radii:
+            D = 2 * r + 1
+            per_q = 8 + L * D * D * 4 + sum(min((2 * r + 2) ** 2, (H >> i) ** 2) * 4 for i in range(L))
+            for _ in range(warm):
+                out = corr_lookup(vols[layout], flow, r)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+            for a, b in ev:
+                a.record()
+                out = corr_lookup(vols[layout], flow, r)
+                b.record()
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in ev)
+            med = ts[len(ts) // 2]
+            gbs = Q * per_q / (med * 1e-3) / 1e9
+            inb = float((out != 0).float().mean())
+            if layout == "tiled" and "rowmajor" in args.layouts:
+                assert torch.equal(out, corr_lookup(pyr, flow, r)), "tiled and row-major lookups differ"
+            rows.append({"layout": layout, "radius": r, "queries": Q, "bytes_per_query": per_q, "ms_median": med, "ms_min": ts[0],
+                         "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak, "nonzero_fraction_of_outputs": inb,
+                         "Mqueries_per_s": Q / med / 1e3})
+            print("%-8s r=%d  %.3f ms (min %.3f)  %.0f GB/s algorithmic = %.1f%% of %.0f GB/s   %.0f Mq/s   nonzero outputs %.1f%%"
+                  % (layout, r, med, ts[0], gbs, 100 * gbs / peak, peak, Q / med / 1e3, 100 * inb), flush=True)
+            del out
     if args.json:
         with open(args.json, "w") as f:
             json.dump({"workload": "corr_lookup B=%d %dx%d L=%d fp32 volume %.1f GB, flow~N(0,16)" % (B, H, H, L, sum(x.numel() for x in pyr) * 4 / 1e9),
