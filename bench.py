@@ -191,40 +191,276 @@ def algorithmic_counts(world, lo, hi):
     return flops, lookup_bytes
 
 
-def lookup_roofline(dev, batch=256, size=64, radius=4, iters=20):
-    """corr_lookup_banded_kernel at the configs[3] shape (batch 256, 64x64 maps, r=4, fp32 volume of 2^20 slices = 17.2 GB,
-    far larger than L2): algorithmic bytes (8 + D^2*4 + (2r+2)^2*4 per query) / CUDA-event time
-    on the launching stream, against the measured HBM copy peak."""
-    from picopose_b200.corr_lookup import corr_lookup
-    _, peak_gbs, _, _ = measured_peaks()
-    Q = batch * size * size
-    g = torch.Generator(device=dev).manual_seed(0)
-    pyr = [torch.randn(Q, 1, size, size, device=dev, generator=g)]
-    flow = 4.0 * torch.randn(batch, 2, size, size, device=dev, generator=g)
-    D = 2 * radius + 1
-    per_q = 8 + D * D * 4 + min((2 * radius + 2) ** 2, size * size) * 4
-    for _ in range(3):
-        corr_lookup(pyr, flow, radius)
+def _timed_ms(fn, iters, warm=3):
+    """Mean / min of `iters` CUDA-event timings of fn() on the current stream after `warm` warm-ups."""
+    for _ in range(warm):
+        fn()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     for a, b in ev:
         a.record()
-        corr_lookup(pyr, flow, radius)
+        fn()
         b.record()
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in ev)
-    ms = sum(ts) / len(ts)
-    achieved = Q * per_q / (ms * 1e-3) / 1e9
-    del pyr, flow
-    return {"bound": "hbm", "kernel": "corr_lookup_banded_kernel<4,5>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "traffic": 1369 * Q + 254 * Q, "kernel_ms": ms, "kernel_ms_min": ts[0],
-            "queries": Q, "algorithmic_bytes_per_query": per_q,
-            "workload": "configs[3] shape: %d x %dx%d queries, L=1 fp32 volume (%.1f GB), r=%d, flow~N(0,16); not part of "
-                        "the timed step" % (batch, size, size, Q * size * size * 4 / 1e9, radius),
-            "note": "traffic = ncu dram bytes of this kernel at this shape (1369 B read + 254 B written per query, "
-                    "profiles/r1c_prof_lookup4_r1c.*): every L2 miss moves a whole 128-byte line on this GPU whatever the "
-                    "load instruction (profiles/r1w_dram_granularity.md), so a 10x10 fp32 window costs ~11.7 lines and the "
-                    "algorithmic fraction of this op is capped at ~0.43 at r=4; frac / 0.43 is the share of that cap"}
+    return sum(ts) / len(ts), ts[0]
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the lookup kernels at the configs[3] shape, from the committed ncu csv of these exact
+    launches (profiles/*_lookup_traffic.csv: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over
+    `tools/bench_lookup.py --once --radii 4 8`, B=256, 64x64).  -> {kernel name: (read + write bytes, csv file)}."""
+    import csv
+    import glob
+    out = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_lookup_traffic.csv"))):
+        hdr, acc = None, {}
+        with open(path) as f:
+            for row in csv.reader(f):
+                if row and row[0] == "ID":
+                    hdr = row
+                elif hdr and len(row) == len(hdr):
+                    d = dict(zip(hdr, row))
+                    if d["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        key = (d["Kernel Name"].split("(")[0].replace("void ", "").replace(" ", ""), d["ID"])
+                        acc[key] = acc.get(key, 0.0) + float(d["Metric Value"].replace(",", ""))
+        by_kernel = {}
+        for (name, _), v in acc.items():
+            by_kernel.setdefault(name, []).append(v)
+        for name, vals in by_kernel.items():
+            out[name] = (sum(vals) / len(vals), os.path.basename(path))     # later files (later rounds) win
+    return out
+
+
+def lookup_rooflines(dev, batch=256, size=64, radii=(4, 8), iters=20):
+    """Stage-3 lookup at the configs[3] shape (batch 256, 64x64 maps, fp32 volume of 2^20 slices = 17.2 GB, far larger
+    than L2; flow ~ N(0, 16)): per radius the row-major volume (the reference's layout), the tiled volume (TiledPyramid,
+    what our CorrelationPyramid writes for a CorrLookup) and the fused path that never builds a volume.  achieved =
+    algorithmic bytes (8 + D^2*4 + (2r+2)^2*4 per query) / CUDA-event time on the launching stream against
+    the measured HBM copy peak; `traffic` = DRAM bytes of that exact launch from the committed ncu csv."""
+    from picopose_b200.corr_lookup import corr_lookup
+    from picopose_b200.correlation import TiledPyramid, windowed_correlation
+    _, peak_gbs, _, _ = measured_peaks()
+    Q = batch * size * size
+    g = torch.Generator(device=dev).manual_seed(0)
+    pyr = [torch.randn(Q, 1, size, size, device=dev, generator=g)]
+    tiled = TiledPyramid.from_volumes(pyr)
+    flow = 4.0 * torch.randn(batch, 2, size, size, device=dev, generator=g)
+    traffic = measured_traffic()
+    jb = {1: 3, 2: 5, 3: 4, 4: 5, 5: 4, 6: 5, 7: 5, 8: 3}
+    blocks = {}
+    for r in radii:
+        D = 2 * r + 1
+        per_q = 8 + D * D * 4 + min((2 * r + 2) ** 2, size * size) * 4
+        for name, vol, flag in (("rowmajor", pyr, 0), ("tiled", tiled, 1)):
+            ms, ms_min = _timed_ms(lambda: corr_lookup(vol, flow, r), iters)
+            achieved = Q * per_q / (ms * 1e-3) / 1e9
+            kname = LOOKUP_KERNEL.get((name, r)) or "corr_lookup_banded_kernel<%d,%d,%d>" % (r, jb[r], flag)
+            tr = traffic.get(kname)
+            blocks["%s_r%d" % (name, r)] = {
+                "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": tr[0] if tr else None, "traffic_source": tr[1] if tr else None,
+                "dram_frac_of_peak": (tr[0] / (ms * 1e-3) / 1e9 / peak_gbs) if tr else None,
+                "kernel_ms": ms, "kernel_ms_min": ms_min, "queries": Q, "algorithmic_bytes_per_query": per_q,
+                "layout": name, "radius": r}
+    assert torch.equal(corr_lookup(tiled, flow, 4), corr_lookup(pyr, flow, 4))
+    del pyr, tiled
+    # fused CorrelationPyramid + CorrLookup on 256-channel features of the same shape: no volume at all (what FlowDecoder
+    # runs through the overlay); its FLOPs (2 * (2r+2)^2 * C per query, fp32 FMAs) bound it, not HBM
+    fused = {}
+    C = 256
+    nb = 32                                                       # 2^17 queries timed, scaled to 2^20
+    f1 = torch.randn(nb, C, size, size, device=dev, generator=g)
+    f2 = torch.randn(nb, C, size, size, device=dev, generator=g)
+    for r in radii:
+        ms, _ = _timed_ms(lambda: windowed_correlation(f1, f2, flow[:nb], 1, r), 5, warm=2)
+        fused["r%d" % r] = {"ms_per_2^20_queries": ms * (batch / nb), "timed_queries": nb * size * size, "C": C,
+                            "fp32_gflop_per_2^20_queries": 2.0 * (2 * r + 2) ** 2 * C * Q / 1e9}
+    del f1, f2, flow
+    head = blocks["rowmajor_r4"]
+    out = dict(head)
+    out["workload"] = ("configs[3] shape: %d x %dx%d queries, L=1 fp32 volume (%.1f GB), flow~N(0,16); not part of the timed "
+                       "step" % (batch, size, size, Q * size * size * 4 / 1e9))
+    out["by_layout"] = blocks
+    out["fused_no_volume"] = fused
+    out["note"] = ("the top-level keys are the reference's row-major layout at r=4 (as in round 1); by_layout lists row-major "
+                   "and tiled volumes at r=4 and r=8 with `traffic` measured by ncu on these launches (%s). DRAM moves whole "
+                   "128-byte lines on this GPU (profiles/r1w_dram_granularity.md): a (2r+2)^2 fp32 window costs ~11.7 lines in "
+                   "row-major slices and ~6.9 as 4x8 tiles at r=4, so the algorithmic fraction is capped at ~0.43 / ~0.60; "
+                   "fused_no_volume is the windowed correlation on C=256 features (no volume is ever written or read)"
+                   % ", ".join(sorted({b["traffic_source"] for b in blocks.values() if b["traffic_source"]}) or ["no csv committed"]))
+    return out
+
+
+LOOKUP_KERNEL = {}   # (layout, radius) -> kernel name override (set when a different kernel serves that case)
+
+
+def _config_banks(dev, lo, hi, n_obj, N, C, H, n_queries, keep_cpu_object=None):
+    """configs[2]/[4] inputs: `n_obj` object banks of N views (drawn on the device, same seeds on every rank), of which
+    this rank prepares and keeps views [lo, hi); `n_queries` detections (object = b mod n_obj), each a noisy copy of one
+    view of its object, so the expected top-1 is known.  -> (TemplateBank, queries, obj (cpu), top1 (cpu), cpu bank or None)."""
+    from picopose_b200 import matching as M
+    preps, rns = [], []
+    queries = torch.empty(n_queries, C, H, H, device=dev)
+    top1 = torch.randint(0, N, (n_queries,), generator=torch.Generator().manual_seed(1))
+    obj = torch.arange(n_queries) % n_obj
+    cpu_bank = None
+    for o in range(n_obj):
+        g = torch.Generator(device=dev).manual_seed(100 + o)
+        bank = torch.randn(N, C, H, H, device=dev, generator=g)            # 2.7 GB fp32 at 642 x 1024 x 32^2
+        for b in range(n_queries):
+            if int(obj[b]) == o:
+                gq = torch.Generator(device=dev).manual_seed(1000 + b)
+                queries[b] = bank[int(top1[b])] + 0.5 * torch.randn(C, H, H, device=dev, generator=gq)
+        p, rn = M.prepare_features(bank[lo:hi].unsqueeze(0))
+        preps.append(p)
+        rns.append(rn)
+        if keep_cpu_object == o:
+            cpu_bank = bank.cpu()
+        del bank
+    bank = M.TemplateBank(torch.cat(preps), torch.cat(rns), C, H, H, M.default_mode())
+    return bank, queries, obj, top1, cpu_bank
+
+
+def config_blocks(args, dev, world, rank, dist):
+    """BASELINE configs[2] and configs[4] inside the driver-run line (every N).
+
+    config2: 64 detections x 642 views x 1024 ch x 32^2 patches, 8 shared object banks prepared once and resident, bank
+             sharded over the ranks along the view axis, all queries on every rank, top-k exchange: STRONG scaling
+             (total work fixed) -- the configuration north_star names for the >= 6.5x target.
+    config4: 512 detections x 642 views stage 1 (same sharding) + stage 3 of every detection's top-1 hypothesis on the
+             FlowDecoder ladder (16^2 L1 / 32^2 L2 / 64^2 L3, 256 channels, r=4) through the fused windowed
+             correlation, detections sharded over the ranks (no collective); det/s = D / (t1 + t3)."""
+    from picopose_b200 import _lib
+    from picopose_b200 import matching as M
+    from picopose_b200 import synth
+    from picopose_b200.correlation import windowed_correlation
+    from picopose_b200.sharded import ShardedMatcher, shard_range
+    lib = _lib.load()
+    N, C, H, n_obj, k = (642, 1024, 32, 8, 5) if not SMALL else (10, 64, 8, 2, 3)
+    D2, D4 = (64, 512) if not SMALL else (4, 8)
+    lo, hi = shard_range(N, rank, world)
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    bank, queries, obj, top1, cpu_bank = _config_banks(dev, lo, hi, n_obj, N, C, H, D4, keep_cpu_object=0 if want_cpu else None)
+    mask = synth.disc_mask(D4).to(dev)
+    bidx = obj.to(device=dev, dtype=torch.int32)
+    matcher = ShardedMatcher(N)
+    peak_tf, _, _, sustained_tf = measured_peaks()
+    rows_exec, _ = executed_rows(mask[:1].cpu(), H)                        # the same disc mask for every detection
+    T = H * H
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def stage1(nd, iters, warm):
+        run = lambda: matcher.match(bank, queries[:nd], mask[:nd], topk=k, bank_index=bidx[:nd])   # noqa: E731
+        score, idx = run()
+        _lib.check_device_faults()
+        ok = bool((idx[:, 0].cpu() == top1[:nd]).all())
+        for _ in range(warm):
+            run()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(iters):
+            run()
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1) / iters
+        return ms, ok, idx
+
+    out = {}
+    # ---------------- config2 ----------------
+    ms2, ok2, _ = stage1(D2, 5 if not SMALL else 2, 2)
+    t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2 = float(t)
+    flops_exec = 2.0 * D2 * (hi - lo) * rows_exec * T * C                 # MMA FLOPs this rank issues (compacted query rows)
+    out["config2"] = {
+        "workload": "configs[2]: %d detections x %d views, %dx%d patches, C=%d, %d shared prepared banks resident, top-%d; "
+                    "bank sharded x%d along views, all queries on every rank, one top-k exchange" % (D2, N, H, H, C, n_obj, k, world),
+        "scaling": "strong", "n_gpus": world, "ms_per_batch": ms2, "detections_per_s": D2 * 1e3 / ms2,
+        "matches_per_s": D2 * N * T * 1e3 / ms2, "views_per_rank": hi - lo,
+        "issued_tflops_per_gpu": flops_exec / (ms2 * 1e-3) / 1e12,
+        "frac_of_sustained_bf16_peak": (flops_exec / (ms2 * 1e-3) / 1e12 / sustained_tf) if sustained_tf else None,
+        "frac_of_burst_bf16_peak": flops_exec / (ms2 * 1e-3) / 1e12 / peak_tf,
+        "algorithmic_tflops_all_gpus": 2.0 * D2 * N * T * T * C / (ms2 * 1e-3) / 1e12,
+        "top1_recovered": ok2,
+        "note": "whole batch by CUDA events (query prologue + contraction + finalisation + exchange), max over ranks; issued "
+                "FLOPs count the compacted query rows (%d of %d per detection after the disc mask)" % (rows_exec, T)}
+    # ---------------- config4 ----------------
+    ms1, ok4, idx4 = stage1(D4, 2, 1)
+    my = list(range(rank, D4, world))                                      # this rank's detections for stage 3
+    r3, Cf = 4, 256
+    ladder = ((16, 1), (32, 2), (64, 3)) if not SMALL else ((8, 1),)
+    chunk = 64
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    feats = [(torch.randn(min(chunk, len(my)), Cf, h, h, device=dev, generator=g),
+              torch.randn(min(chunk, len(my)), Cf, h, h, device=dev, generator=g),
+              1.5 * torch.randn(min(chunk, len(my)), 2, 1, 1, device=dev, generator=g)
+              + 0.5 * torch.randn(min(chunk, len(my)), 2, h, h, device=dev, generator=g), L) for h, L in ladder]
+
+    def stage3():
+        # the same synthetic feature chunk stands for every chunk of this rank's detections (values do not change the work)
+        for c0 in range(0, len(my), chunk):
+            n = min(chunk, len(my) - c0)
+            for f1, f2, fl, L in feats:
+                windowed_correlation(f1[:n], f2[:n], fl[:n], L, r3)
+
+    stage3()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2):
+        stage3()
+    e1.record()
+    barrier()
+    ms3 = e0.elapsed_time(e1) / 2
+    t = torch.tensor([ms1, ms3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms1, ms3 = [float(x) for x in t.tolist()]
+    out["config4"] = {
+        "workload": "configs[4]: %d detections x %d views stage-1 ranking (as config2) + stage-3 correlation lookups of every "
+                    "detection's top-1 hypothesis on the ladder %s, C=%d, r=%d, fused CorrelationPyramid+CorrLookup (no volume), "
+                    "detections sharded x%d" % (D4, N, "/".join("%d^2xL%d" % (h, L) for h, L in ladder), Cf, r3, world),
+        "n_gpus": world, "stage1_ms": ms1, "stage3_ms": ms3, "detections_per_s": D4 * 1e3 / (ms1 + ms3),
+        "stage1_detections_per_s": D4 * 1e3 / ms1, "top1_recovered": ok4,
+        "algorithmic_tflops_all_gpus_stage1": 2.0 * D4 * N * T * T * C / (ms1 * 1e-3) / 1e12,
+        "note": "det/s = D / (t_stage1 + t_stage3) (SURVEY 8(d) config 5), each the max over ranks; the conv stacks between "
+                "the three lookups (reference code, out of scope) are not part of the time"}
+    # ---------------- CPU port on a sample of config4 (N=1 only) ----------------
+    if want_cpu and cpu_bank is not None:
+        match_fn, lookup_fn, kind = _reference_impl()
+        from oracle import corr_lookup_oracle as OL
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        dets = [b for b in range(D4) if int(obj[b]) == 0][:4 if not SMALL else 2]
+        cpu_feats = [(f1[:1].cpu(), f2[:1].cpu(), fl[:1].cpu(), L) for f1, f2, fl, L in feats]
+        mask_c = mask[:1].cpu()
+        t_all, agree = 0.0, True
+        with torch.no_grad():
+            for n_done, b in enumerate([dets[0]] + dets):                  # first pass = warm-up
+                q = queries[b:b + 1].cpu()
+                t0 = time.perf_counter()
+                _, i_cpu = match_fn(cpu_bank[None], q, None, mask_c, k)
+                for f1, f2, fl, L in cpu_feats:
+                    lookup_fn(OL.correlation_pyramid(f1, f2, L), fl, r3)
+                dt = time.perf_counter() - t0
+                if n_done > 0:
+                    t_all += dt
+                agree = agree and int(i_cpu[0, 0]) == int(top1[b]) == int(idx4[b, 0])
+        out["config4"]["cpu_baseline"] = {
+            "value": len(dets) / t_all, "unit": "detections/s", "cores": cores, "kind": kind,
+            "sample": "%d detections of config4, one at a time (a B=1 similarity tensor is 2.7 GB): full %d-view "
+                      "matching_templates + CorrelationPyramid/CorrLookup on the three ladder levels, %d threads; top-1 agrees "
+                      "with the GPU result: %s" % (len(dets), N, cores, agree)}
+    matcher.close()
+    del bank, queries
+    return out
 
 
 def run_ours(args):
@@ -396,8 +632,14 @@ def run_ours(args):
 
     # ---- extra (N=1): the stage-3 lookup at the BASELINE configs[3] shape against the HBM roofline ----
     lookup_roof = None
-    if world == 1 and not args.no_lookup_roofline:
-        lookup_roof = lookup_roofline(dev)
+    if world == 1 and not args.no_lookup_roofline and not SMALL:
+        lookup_roof = lookup_rooflines(dev)
+
+    # ---- extra (every N): BASELINE configs[2] (strong scaling) and configs[4] (stage 1 + stage 3) ----
+    del src_d, look_d
+    matcher.close()
+    torch.cuda.empty_cache()
+    blocks = {} if args.no_config_blocks else config_blocks(args, dev, world, rank, dist)
 
     # ---- max over ranks ----
     times = torch.tensor([ms_total, e2e_ms_total, warm_ms_total, gemm_avg_ms], dtype=torch.float64, device=dev)
@@ -461,6 +703,7 @@ def run_ours(args):
         }
         if sharded_check:
             line["sharded_equals_single_gpu"] = sharded_check
+        line.update(blocks)
         if lookup_roof is not None:
             line["roofline_lookup"] = lookup_roof
         if world == 1 and not args.no_cpu_baseline:
@@ -631,6 +874,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-lookup-roofline", action="store_true", help="skip the configs[3]-shape lookup roofline block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config-blocks", action="store_true", help="skip the configs[2] / configs[4] blocks")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup

@@ -40,6 +40,12 @@ typedef enum pp_status {
     PP_ERR_KERNEL = -6     /* a kernel reported an internal fault (pipeline timeout) */
 } pp_status;
 
+/* OR into the `cluster` argument of pp_match_scores: cheaper reduction keys in the contraction's epilogue (similarities
+ * resolved to 7.6e-6 absolute instead of 2^-19 relative).  Meant for PP_MODE_BF16 operands, whose own error is ~3e-4; the
+ * one-call entry points (pp_match_templates, pp_match_templates_dense) set it themselves for that mode.  Query masks must
+ * lie in [0, 1] (the reference's are 0/1). */
+#define PP_MATCH_FAST_KEYS 0x100
+
 /* arithmetic mode of the stage-1 contraction */
 typedef enum pp_mode {
     PP_MODE_BF16 = 0,   /* bf16 operands, fp32 accumulate (tcgen05 kind::f16)                 */
@@ -105,8 +111,10 @@ PP_API int pp_match_prepare(const float* feats, int64_t G, int C, int P, int mod
                      void* prepared, float* rnorm, void* stream);
 
 /* Query side of pp_match_scores: resizes the query masks (nearest, as F.interpolate at utils/matching.py:38-39),
- * drops masked patches (they are rows of zeros in the reference and never need the tensor cores), prepares the
- * remaining patches like pp_match_prepare and records the bookkeeping pp_match_scores needs.
+ * drops masked patches (they are rows of zeros in the reference and never need the tensor cores), and prepares the
+ * remaining patches NORMALISED and multiplied by their mask value (x * m / max(||x||, 1e-12), utils/matching.py:40-41,48)
+ * before the bf16 split, so the contraction's epilogue has no per-row factor left to apply (q_rnorm is 1 for live rows);
+ * also records the bookkeeping pp_match_scores needs.
  *   tar_feat (B,C,H,W) fp32, tar_mask (B,Hm,Wm) fp32  ->  q_prep (B, H*W, Kp) bf16 (unmasked patches first),
  *   q_rnorm (B, H*W) fp32, q_meta: pp_match_query_meta_bytes(B, H*W) bytes (opaque). */
 PP_API size_t pp_match_query_meta_bytes(int B, int T);
@@ -231,6 +239,17 @@ PP_API int pp_windowed_correlation_prepare_all(const float* feat1, const float* 
                                         float* f1t, void* const* f2t_levels, void* stream);
 PP_API int pp_windowed_correlation(const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
                             int H, int W, int radius, float* out, void* stream);
+
+/* The same with the first layer of the reference's MotionEncoder fused in: the 1x1 convolution
+ * corr_inch = L*(2r+1)^2 -> cout of MotionEncoder.corr_net[0] (model/stage3/raft_decoder.py:113-116,127-129, applied at
+ * :157 to the lookup of flow_decoder.py:61) runs on the block's lookup tile while it is still in shared memory; the
+ * (N, L*D*D, H, W) lookup tensor is never written.
+ *   weight (cout, L*D*D) fp32 = Conv2d.weight[:, :, 0, 0]; bias (cout) or NULL; relu != 0 applies max(0, .)
+ *   out (N, cout, H, W) fp32.  Covered shapes: radius <= 2, C % 32 == 0, L <= 4, cout % 8 == 0, cout * L*D*D <= 40960;
+ *   anything else returns PP_ERR_ARG and is the caller's to run unfused. */
+PP_API int pp_windowed_correlation_conv1x1(const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N,
+                                    int C, int H, int W, int radius, const float* weight, const float* bias, int cout,
+                                    int relu, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Correspondence glue.

@@ -31,11 +31,11 @@ class ConvAct(nn.Module):
     def __init__(self, cin, cout, k, padding=0, act=True):
         super().__init__()
         self.conv = nn.Conv2d(cin, cout, k, 1, padding)
-        self.act = act
+        self.act = nn.ReLU() if act else None
 
     def forward(self, x):
         x = self.conv(x)
-        return F.relu(x) if self.act else x
+        return self.act(x) if self.act is not None else x
 
 
 class MotionEncoder(nn.Module):
@@ -109,7 +109,10 @@ class FlowDecoder(nn.Module):
     def forward_flow(self, feat_render, feat_real, flow, level):
         pyr = self.ops.pyramid(feat_render, feat_real, level + 1)                               # :59
         corr = self.ops.lookup(pyr, flow, self.r)                                               # :61
-        motion = self.encoder[level](corr, flow)                                                # :62
+        if hasattr(self.ops, "encode"):      # lets the CUDA ops fuse the lookup with the encoder's first 1x1 convolution
+            motion = self.ops.encode(self.encoder[level], corr, flow)
+        else:
+            motion = self.encoder[level](corr, flow)                                            # :62
         B, _, H, W = flow.shape
         grid = (self.ops.coords(B, H, W, flow.device) + flow).permute(0, 2, 3, 1)               # :50-54
         warped = self.ops.warp(feat_real, grid)                                                 # :64

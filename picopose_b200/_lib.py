@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpicopose_b200.so")
 
 MODE_BF16, MODE_FP32, MODE_BF16X3 = 0, 1, 2
 MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "bf16x3": MODE_BF16X3}
+MATCH_FAST_KEYS = 0x100   # PP_MATCH_FAST_KEYS
 
 # name -> (restype, argtypes); must list every symbol include/picopose_b200.h declares
 _vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
@@ -59,6 +60,7 @@ SIGNATURES = {
     "pp_windowed_correlation_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_windowed_correlation_prepare_all": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, C.POINTER(_vp), _vp]),
     "pp_windowed_correlation": (_i, [_vp, C.POINTER(_vp), _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pp_windowed_correlation_conv1x1": (_i, [_vp, C.POINTER(_vp), _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "pp_select_templates": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i, _i, _i, _vp, _i, _i, _vp]),
     "pp_init_correspondences": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_stage3_correspondences": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),

@@ -105,8 +105,11 @@ class CorrLookup(nn.Module):
             raise NotImplementedError(
                 "picopose_b200.CorrLookup implements the configuration PicoPose uses "
                 "(bilinear, zeros padding, align_corners=True)")
-        from .correlation import LazyCorrelationPyramid, windowed_correlation
+        from .correlation import LazyCorrelationPyramid, LazyLookup, encoder_fusion_enabled, windowed_correlation
         if isinstance(corr_pyramid, LazyCorrelationPyramid):
+            if corr_pyramid.fusable(self.r) and encoder_fusion_enabled():
+                # our MotionEncoder consumes the result (overlay): leave the lookup to it, fused with its first 1x1 conv
+                return LazyLookup(corr_pyramid, flow, self.r)
             if corr_pyramid.fusable(self.r):
                 # fused CorrelationPyramid + lookup: the all-pairs volume is never built
                 return windowed_correlation(corr_pyramid.feat1, corr_pyramid.feat2, flow, corr_pyramid.num_levels, self.r)

@@ -125,16 +125,111 @@ def windowed_correlation(feat1: torch.Tensor, feat2: torch.Tensor, flow: torch.T
     D = 2 * int(radius) + 1
     with torch.cuda.device(dev):
         st = _lib.stream_of(f1)
-        f1t = torch.empty(N, H * W, Cc, dtype=torch.float32, device=dev)
-        levels = [torch.empty(N, (H >> l) * (W >> l), Cc, dtype=torch.float32, device=dev) for l in range(num_levels)]
-        ptrs = (C.c_void_p * num_levels)(*[t.data_ptr() for t in levels])
-        # one launch: position-major copies of feat1 and of feat2 average-pooled to every level
-        _lib.check(lib.pp_windowed_correlation_prepare_all(_lib.ptr(f1), _lib.ptr(f2), N, Cc, H, W, num_levels,
-                                                           _lib.ptr(f1t), ptrs, st), "pp_windowed_correlation_prepare_all")
+        f1t, levels, ptrs = _position_major(f1, f2, num_levels)
         out = torch.empty(N, num_levels * D * D, H, W, dtype=torch.float32, device=dev)
         _lib.check(lib.pp_windowed_correlation(_lib.ptr(f1t), ptrs, num_levels, _lib.ptr(fl), N, Cc, H, W, int(radius),
                                                _lib.ptr(out), st), "pp_windowed_correlation")
     return out
+
+
+def _position_major(feat1, feat2, num_levels):
+    """One launch: position-major copies of feat1 and of feat2 average-pooled to every level (inputs of the fused kernels)."""
+    lib = _lib.load()
+    f1 = feat1.float().contiguous()
+    f2 = feat2.float().contiguous()
+    N, Cc, H, W = f1.shape
+    dev = f1.device
+    f1t = torch.empty(N, H * W, Cc, dtype=torch.float32, device=dev)
+    levels = [torch.empty(N, (H >> l) * (W >> l), Cc, dtype=torch.float32, device=dev) for l in range(num_levels)]
+    ptrs = (C.c_void_p * num_levels)(*[t.data_ptr() for t in levels])
+    _lib.check(lib.pp_windowed_correlation_prepare_all(_lib.ptr(f1), _lib.ptr(f2), N, Cc, H, W, num_levels,
+                                                       _lib.ptr(f1t), ptrs, _lib.stream_of(f1)), "pp_windowed_correlation_prepare_all")
+    return f1t, levels, ptrs
+
+
+def conv_fusable(feat1: torch.Tensor, num_levels: int, radius: int, cout: int) -> bool:
+    """Shapes pp_windowed_correlation_conv1x1 covers (the TMA-tiled kernel with the weight matrix in its stage buffers)."""
+    Cc = feat1.shape[1]
+    D = 2 * int(radius) + 1
+    return (1 <= radius <= 2 and Cc % 32 == 0 and 1 <= num_levels <= 4 and cout % 8 == 0 and cout * num_levels * D * D <= 40960
+            and num_levels * D * D * 65 * 4 + 2 * (24 * 24 + 64) * 32 * 4 + 64 * (D + 2) ** 2 * 4 + num_levels * 64 * 4 * D * 4 < 215 * 1024)
+
+
+def windowed_correlation_conv(feat1: torch.Tensor, feat2: torch.Tensor, flow: torch.Tensor, num_levels: int, radius: int,
+                              weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
+    """act(conv1x1(CorrLookup(radius)(CorrelationPyramid(num_levels)(feat1, feat2), flow))) in one kernel after the layout
+    pass: the lookup tile is multiplied by the (cout x L*D*D) weight matrix while it sits in shared memory (SURVEY 8(f)-3;
+    reference: model/stage3/flow_decoder.py:59-62 + model/stage3/raft_decoder.py:113-116,157).  -> (N, cout, H, W) fp32."""
+    _lib.require_cuda(feat1, feat2, flow, weight, bias)
+    _lib.require_inference("fused lookup + 1x1 conv", feat1, feat2, flow, weight)
+    lib = _lib.load()
+    N, Cc, H, W = feat1.shape
+    D = 2 * int(radius) + 1
+    w = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
+    cout = w.shape[0]
+    if w.shape[1] != num_levels * D * D:
+        raise ValueError(f"weight has {w.shape[1]} input channels, the lookup produces {num_levels * D * D}")
+    b = None if bias is None else bias.detach().float().contiguous()
+    fl = flow.float().contiguous()
+    with torch.cuda.device(feat1.device):
+        f1t, levels, ptrs = _position_major(feat1, feat2, num_levels)
+        out = torch.empty(N, cout, H, W, dtype=torch.float32, device=feat1.device)
+        _lib.check(lib.pp_windowed_correlation_conv1x1(_lib.ptr(f1t), ptrs, num_levels, _lib.ptr(fl), N, Cc, H, W, int(radius),
+                                                       _lib.ptr(w), _lib.ptr(b), cout, int(bool(relu)), _lib.ptr(out),
+                                                       _lib.stream_of(feat1)), "pp_windowed_correlation_conv1x1")
+    return out
+
+
+class LazyLookup:
+    """What CorrLookup returns for a LazyCorrelationPyramid when the consumer is our MotionEncoder (the overlay's
+    model/stage3/raft_decoder.py): the lookup not yet computed, so that the encoder's first 1x1 convolution can be fused
+    into it.  `materialise()` gives the plain (N, L*D*D, H, W) lookup tensor for anybody else."""
+
+    def __init__(self, pyramid: "LazyCorrelationPyramid", flow: torch.Tensor, radius: int):
+        self.pyramid, self.flow, self.radius = pyramid, flow, int(radius)
+
+    def materialise(self) -> torch.Tensor:
+        p = self.pyramid
+        return windowed_correlation(p.feat1, p.feat2, self.flow, p.num_levels, self.radius)
+
+    def conv1x1(self, weight, bias=None, relu=True):
+        """-> act(conv1x1(lookup)) fused, or None when the shapes are outside the fused kernel's range."""
+        p = self.pyramid
+        cout = weight.shape[0]
+        if not conv_fusable(p.feat1, p.num_levels, self.radius, cout) or p.feat1.shape[-1] * p.feat1.shape[-2] < 64:
+            return None
+        return windowed_correlation_conv(p.feat1, p.feat2, self.flow, p.num_levels, self.radius, weight, bias, relu)
+
+
+ENCODER_FUSION = False     # set by the overlay's raft_decoder once OUR MotionEncoder is the consumer of CorrLookup's result
+
+
+def encoder_fusion_enabled() -> bool:
+    return ENCODER_FUSION and os.environ.get("PICOPOSE_B200_FUSE_CONV", "1") != "0"
+
+
+def motion_encoder_forward(encoder, corr, flow):
+    """MotionEncoder.forward (model/stage3/raft_decoder.py:146-161) with the first corr_net layer fused into the lookup
+    when `corr` is a LazyLookup; `encoder` is the reference's module (its weights, its remaining layers)."""
+    corr_feat = None
+    if isinstance(corr, LazyLookup):
+        first = encoder.corr_net[0]
+        conv = getattr(first, "conv", None)
+        act = getattr(first, "activate", getattr(first, "act", None))
+        plain = (isinstance(conv, nn.Conv2d) and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
+                 and conv.padding == (0, 0) and conv.groups == 1 and not getattr(first, "with_norm", False)
+                 and isinstance(act, nn.ReLU))
+        x = corr.conv1x1(conv.weight, conv.bias, relu=True) if plain else None
+        if x is None:
+            corr = corr.materialise()
+        else:
+            rest = encoder.corr_net[1:]
+            corr_feat = rest(x) if len(rest) else x
+    if corr_feat is None:
+        corr_feat = encoder.corr_net(corr)
+    flow_feat = encoder.flow_net(flow)
+    out = encoder.out_net(torch.cat([corr_feat, flow_feat], dim=1))
+    return torch.cat([out, flow], dim=1)
 
 
 class LazyCorrelationPyramid(Sequence):

@@ -45,19 +45,24 @@ constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;              // ~2 s: a 
 
 constexpr int MAX_DETS_PER_LAUNCH = 1024;  // tile prefix table lives in shared memory
 
-enum { EPI_MATCH = 0, EPI_EMIT = 1 };
+// EPI_MATCH_FAST: same reductions with cheaper keys (bf16 mode): the similarity is offset by 2.0 so that every key is a
+// positive float -- no sign handling, no rounding add -- at a resolution of 2^-17 (7.6e-6 absolute), far below the bf16
+// operands' own error; EPI_MATCH keeps 2^-19 relative for the fp32-accurate modes.
+enum { EPI_MATCH = 0, EPI_EMIT = 1, EPI_MATCH_FAST = 2 };
 
 struct GemmParams {
     int B, N, T;  // detections, views per bank, patches (T == S)
     int num_k_blocks;
     int num_mt, num_nt;  // tiles along T (per 128*CL rows) and S (per 256 columns)
-    uint32_t total_tiles;
+    uint32_t num_groups;  // ceil(B / chunk) * N * num_mt work groups
+    int chunk;            // detections per group (>= 1): consecutive entries of det_order
+    const int32_t* det_order;  // (B,) detections sorted by bank (null = identity): a chunk then shares its M-side tiles
     int n_banks;
     const int32_t* bank_of_det;    // (B,) or null = identity; entries outside [0, n_banks) are clamped and reported (fault 6)
     const float* mrow;             // (B, T) nearest-resized query mask, indexed by patch
     const int* tv;                 // (B) unmasked query patches per detection (EPI_MATCH: rows are compacted); null = T
     const int* rowmap;             // (B, T) patch index of compact query row r
-    const float* ra;               // (B, T) inverse norms of the (compact) query rows
+    const float* ra;               // (B, T) EPI_EMIT only: inverse norms of the query rows (EPI_MATCH: folded into the operand)
     const float* rb;               // (n_banks, N, T) inverse norms of the template patches
     unsigned long long* rowkey;    // (B, N, T)
     unsigned long long* colkey;    // (B, N, T)
@@ -76,8 +81,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int RB_BYTES = NUM_EPI_WARPS * EPI_COLS * 8;  // per epilogue warp: factor + patch index of its columns
-    static constexpr int PREFIX_BYTES = (MAX_DETS_PER_LAUNCH + 1) * 4;  // per-detection tile prefix (compacted rows)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + PREFIX_BYTES + 1024;  // + alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + 1024;  // + alignment slack
 };
 
 __device__ __noinline__ void report_fault(int* fault, int code, int a, int b) {
@@ -103,52 +107,52 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fa
 
 struct TileCoord {
     int b, n, nt, mt;
-    int ncols;  // EPI_MATCH: accumulator columns of this tile (UMMA N), a multiple of 32
+    int nct;    // column tiles of this (b, n, mt) group
+    int ncols;  // accumulator columns of a tile (UMMA N), a multiple of 32
     int rows;   // EPI_MATCH: live compact query rows of detection b
 };
-__device__ __forceinline__ TileCoord decode_tile(uint32_t tile, const GemmParams& p) {
-    TileCoord c;
-    uint32_t r = tile / (uint32_t)p.num_mt;
-    c.mt = (int)(tile - r * (uint32_t)p.num_mt);
-    uint32_t r2 = r / (uint32_t)p.num_nt;
-    c.nt = (int)(r - r2 * (uint32_t)p.num_nt);
-    const uint32_t b = r2 / (uint32_t)p.N;
-    c.n = (int)(r2 - b * (uint32_t)p.N);
-    c.b = (int)b;
-    c.ncols = BLOCK_N;
-    c.rows = p.T;
-    return c;
-}
 
-// EPI_MATCH: detection b owns N * num_mt * ceil(tv[b] / 256) tiles (template-patch tiles x query-column tiles);
-// prefix[] (shared memory) holds the running tile count, a binary search maps a flat tile index back to its
-// detection.  Column tiles of one (view, patch tile) are neighbours in the flat order, so the clusters that run
-// them at the same time read the same template rows (L2 hits).
+// Work is handed out in GROUPS (detection chunk, n, mt): one 128*CL-row tile of the M-side operand (a template-patch tile,
+// 256 x Kp bf16) against ALL column tiles of up to `chunk` detections.  A cluster walks them back to back, so the M-side
+// tile is read from HBM once and comes out of L2 for the rest of the group; with det_order sorting the detections by bank,
+// detections that share an object bank share those reads (8 detections per bank in BASELINE configs[2]).
+// (r1 dealt single tiles round-robin; the column tiles of one M-side tile then ran on neighbouring clusters, which drift
+// apart over a long batch until the shared tile has left L2: ncu showed 25 GB of DRAM reads for 10.8 GB of operands on an
+// 8 x 642 batch, and every detection streamed its whole bank again.)
 __device__ __forceinline__ int live_rows(const GemmParams& p, int b) { return p.tv ? __ldg(p.tv + b) : p.T; }
+__device__ __forceinline__ uint32_t col_tiles(int rows) { return (uint32_t)((rows + BLOCK_N - 1) / BLOCK_N); }
 // bank of detection b, forced into range: a bad index must not become an out-of-bounds TMA coordinate / rnorm read
 __device__ __forceinline__ int bank_of(const GemmParams& p, int b) {
     if (!p.bank_of_det) return b;
     const int v = __ldg(p.bank_of_det + b);
     return v < 0 ? 0 : (v >= p.n_banks ? p.n_banks - 1 : v);
 }
-__device__ __forceinline__ uint32_t col_tiles(int rows) { return (uint32_t)((rows + BLOCK_N - 1) / BLOCK_N); }
-__device__ __forceinline__ TileCoord decode_tile_prefix(uint32_t tile, const GemmParams& p, const uint32_t* prefix) {
-    int lo = 0, hi = p.B;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (prefix[mid] <= tile) lo = mid; else hi = mid;
-    }
+// group -> (first detection position, n, mt)
+__device__ __forceinline__ void decode_group(uint32_t g, const GemmParams& p, int& pos0, int& n, int& mt) {
+    const uint32_t r = g / (uint32_t)p.num_mt;
+    mt = (int)(g - r * (uint32_t)p.num_mt);
+    const uint32_t c = r / (uint32_t)p.N;
+    n = (int)(r - c * (uint32_t)p.N);
+    pos0 = (int)c * p.chunk;
+}
+// detection at position `pos` of the (bank-sorted) order: its tile shape
+template <bool MATCH>
+__device__ __forceinline__ TileCoord det_tiles(int pos, int n, int mt, const GemmParams& p) {
     TileCoord c;
-    c.b = lo;
-    c.rows = live_rows(p, lo);
-    const uint32_t nct = col_tiles(c.rows);
-    c.ncols = (int)((((uint32_t)c.rows + nct - 1) / nct + 31u) & ~31u);
-    const uint32_t local = tile - prefix[lo];
-    const uint32_t r = local / nct;
-    c.nt = (int)(local - r * nct);
-    const uint32_t n = r / (uint32_t)p.num_mt;
-    c.mt = (int)(r - n * (uint32_t)p.num_mt);
-    c.n = (int)n;
+    c.b = p.det_order ? __ldg(p.det_order + pos) : pos;
+    c.n = n;
+    c.mt = mt;
+    c.nt = 0;
+    if (MATCH) {
+        // a detection with tv unmasked patches is cut into ceil(tv / 256) column tiles of round_up(tv / tiles, 32) columns
+        c.rows = live_rows(p, c.b);
+        c.nct = (int)col_tiles(c.rows);
+        c.ncols = c.nct ? (int)((((uint32_t)c.rows + (uint32_t)c.nct - 1) / (uint32_t)c.nct + 31u) & ~31u) : 0;
+    } else {
+        c.rows = p.T;
+        c.nct = p.num_nt;
+        c.ncols = BLOCK_N;
+    }
     return c;
 }
 
@@ -171,8 +175,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + NUM_ACC + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
     float* rb_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
-    uint32_t* tile_prefix = reinterpret_cast<uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::RB_BYTES);
-    constexpr bool MATCH = EPI == EPI_MATCH;  // template patches on the M side, compact query rows on the N side
+    constexpr bool MATCH = EPI != EPI_EMIT;  // template patches on the M side, compact query rows on the N side
+    constexpr bool FAST = EPI == EPI_MATCH_FAST;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -199,42 +203,25 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::fence_barrier_init();
     } else if (warp == 2) {
         ptx::tmem_alloc<CL>(ptx::smem_u32((const void*)tmem_slot), 512);
-    } else if (warp == 3 && MATCH) {
-        // inclusive scan of the per-detection tile counts (B <= MAX_DETS_PER_LAUNCH), 32 detections per step
-        uint32_t run = 0;
-        if (lane == 0) tile_prefix[0] = 0;
-        for (int b0 = 0; b0 < p.B; b0 += 32) {
-            const int b = b0 + lane;
-            uint32_t cnt = 0;
-            if (b < p.B) cnt = col_tiles(live_rows(p, b)) * (uint32_t)(p.N * p.num_mt);
-            if (b < p.B && p.bank_of_det && blockIdx.x == 0) {
-                // range check of the caller's bank indices (the loads above clamp): reported, not trapped
-                const int v = __ldg(p.bank_of_det + b);
-                if ((v < 0 || v >= p.n_banks) && p.fault) {
-                    p.fault[1] = b;
-                    p.fault[2] = v;
-                    p.fault[3] = p.n_banks;
-                    p.fault[4] = 0;
-                    __threadfence_system();
-                    p.fault[0] = 6;
-                }
+    } else if (warp == 3 && MATCH && blockIdx.x == 0 && p.bank_of_det) {
+        // range check of the caller's bank indices (the loads clamp): reported through the fault record, not trapped
+        for (int b = lane; b < p.B; b += 32) {
+            const int v = __ldg(p.bank_of_det + b);
+            if ((v < 0 || v >= p.n_banks) && p.fault) {
+                p.fault[1] = b;
+                p.fault[2] = v;
+                p.fault[3] = p.n_banks;
+                p.fault[4] = 0;
+                __threadfence_system();
+                p.fault[0] = 6;
             }
-            uint32_t inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += up;
-            }
-            if (b < p.B) tile_prefix[b + 1] = run + inc;
-            run += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
     ptx::tc_fence_before();
     if (CL > 1) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t total_tiles = MATCH ? tile_prefix[p.B] : p.total_tiles;
-    auto decode = [&](uint32_t tile) { return MATCH ? decode_tile_prefix(tile, p, tile_prefix) : decode_tile(tile, p); };
+    const uint32_t num_groups = p.num_groups;
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA) =====================
@@ -242,11 +229,15 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // one elected lane issues the copies and the barrier arrivals.
         int stage = 0;
         uint32_t phase = 0;
-        for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-            const TileCoord tc = decode(tile);
-            const int bank = bank_of(p, tc.b);
-            const int q_row0 = tc.b * p.T;                                       // query operand: rows of detection b
-            const int t_row0 = (int)(((long long)bank * p.N + tc.n) * p.T);      // bank operand: rows of view n
+        for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
+         int pos0, gn, gmt;
+         decode_group(grp, p, pos0, gn, gmt);
+         for (int pos = pos0; pos < min(pos0 + p.chunk, p.B); ++pos) {
+          TileCoord tc = det_tiles<MATCH>(pos, gn, gmt, p);
+          const int bank = bank_of(p, tc.b);
+          const int q_row0 = tc.b * p.T;                                       // query operand: rows of detection b
+          const int t_row0 = (int)(((long long)bank * p.N + tc.n) * p.T);      // bank operand: rows of view n
+          for (tc.nt = 0; tc.nt < tc.nct; ++tc.nt) {
             // A = M-side operand (128 rows per CTA), B = N-side operand (each CTA of a pair holds half of the columns;
             // the box is always B_ROWS rows, the MMA reads the first ncols / CL of them)
             const int a_row = (MATCH ? t_row0 : q_row0) + tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M;
@@ -271,14 +262,21 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
+          }
+         }
         }
     } else if (warp == 1 && leader) {
         // ===================== MMA issuer (leader CTA; converged warp, one elected lane issues) =====================
         int stage = 0;
         uint32_t phase = 0;
         uint32_t iter = 0;
-        for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
-            const uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, MATCH ? decode(tile).ncols : BLOCK_N);
+        for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
+         int pos0, gn, gmt;
+         decode_group(grp, p, pos0, gn, gmt);
+         for (int pos = pos0; pos < min(pos0 + p.chunk, p.B); ++pos) {
+          const TileCoord gc = det_tiles<MATCH>(pos, gn, gmt, p);
+          const uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, gc.ncols);
+          for (int nt = 0; nt < gc.nct; ++nt, ++iter) {
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             mbar_wait(tempty_bar(as), aphase ^ 1u, p.fault, 2, as);
@@ -302,6 +300,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
+          }
+         }
         }
     } else if (warp >= FIRST_EPI_WARP) {
         // ===================== epilogue (every CTA) =====================
@@ -309,8 +309,16 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int q = warp & 3;   // TMEM lane quarter this warp may read
         const int hh = e >> 2;    // first 32-column chunk of the tile this warp reads (then hh + 4)
         uint32_t iter = 0;
-        for (uint32_t tile = cluster_id; tile < total_tiles; tile += num_clusters, ++iter) {
-            const TileCoord tc = decode(tile);
+        for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
+         int pos0, gn, gmt;
+         decode_group(grp, p, pos0, gn, gmt);
+         for (int pos = pos0; pos < min(pos0 + p.chunk, p.B); ++pos) {
+          TileCoord tc = det_tiles<MATCH>(pos, gn, gmt, p);
+          // column maxima (over the query rows, lane-local) run across all column tiles of the group: one atomic per
+          // (template patch, group) instead of one per tile
+          float best = -INFINITY;
+          int best_t = 0;
+          for (tc.nt = 0; tc.nt < tc.nct; ++tc.nt, ++iter) {
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             const int T = p.T;
@@ -328,27 +336,25 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             };
 
             if (MATCH) {
-                // lane = template patch s (TMEM lane), columns = compact query rows r of detection b; t = rowmap[r]
+                // lane = template patch s (TMEM lane), columns = compact query rows r of detection b; t = rowmap[r].
+                // The query operand is already normalised and multiplied by its mask value (pp_match_prepare_query), so
+                // acc * rb[s] IS the masked similarity m[t] * sim[t, s]; no per-column factor is left.
                 const int s_row = warp_row0 + lane;
                 const bool s_ok = s_row < T;
                 const int bank = bank_of(p, tc.b);
-                // row maxima (over s, across lanes): value = acc * rb[s] + 0.0 (-0.0 is canonicalised); lanes past the
-                // last template patch get a huge negative value and lose against everything
                 const float rb_l = s_ok ? __ldg(p.rb + ((size_t)bank * p.N + tc.n) * T + s_row) : 0.f;
-                const float c_add = s_ok ? 0.0f : -3.0e38f;
+                // lanes past the last template patch must lose every comparison
+                const float c_add = FAST ? (s_ok ? 2.0f : 0.0f) : (s_ok ? 0.0f : -3.0e38f);
                 const int col0 = tc.nt * tc.ncols;  // first compact query row of the tile
-                // per-column factor (query mask x inverse query norm) and patch index of this warp's <= 2 chunks,
-                // staged before waiting for the accumulator so the global latency hides behind the MMAs
-                float* fa_s = rb_stage + e * (2 * EPI_COLS);
-                int* tp_s = reinterpret_cast<int*>(fa_s + EPI_COLS);
+                // patch index of this warp's <= 2 chunks of columns, staged before waiting for the accumulator so the
+                // global latency hides behind the MMAs
+                int* tp_s = reinterpret_cast<int*>(rb_stage + e * (2 * EPI_COLS));
                 __syncwarp();  // previous tile's readers are done
 #pragma unroll
                 for (int i = 0; i < EPI_CHUNKS; ++i) {
                     const int r = col0 + (hh + 4 * i) * 32 + lane;
                     const bool r_ok = (hh + 4 * i) * 32 < tc.ncols && r < tc.rows;
-                    const int t = r_ok ? (p.rowmap ? __ldg(p.rowmap + (size_t)tc.b * T + r) : r) : 0;
-                    fa_s[i * 32 + lane] = r_ok ? __ldg(p.mrow + (size_t)tc.b * T + t) * __ldg(p.ra + (size_t)tc.b * T + r) : 0.f;
-                    tp_s[i * 32 + lane] = t;
+                    tp_s[i * 32 + lane] = r_ok ? (p.rowmap ? __ldg(p.rowmap + (size_t)tc.b * T + r) : r) : 0;
                 }
                 __syncwarp();
 
@@ -356,8 +362,6 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 ptx::tc_fence_after();
                 if (hh * 32 >= tc.ncols) release_tmem();  // narrow tile: nothing for this warp to read
 
-                float best = -INFINITY;
-                int best_t = 0;
 #pragma unroll 1
                 for (int i = 0; i < EPI_CHUNKS; ++i) {
                     const int c = hh + 4 * i;
@@ -369,42 +373,48 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     const int r0 = col0 + c * 32;
                     const int ncols = min(32, tc.rows - r0);
                     if (ncols <= 0) continue;  // warp-uniform: chunk entirely past the last live query row
-                    // ---- lane-local: first-argmax over t of m[t] * ra[t] * acc (rb[s] > 0 commutes with the max;
-                    // strict > keeps the first index on ties, columns are in increasing t).
-                    // ---- across lanes: first-argmax over s of acc * rb[s] (the row's own positive factor ra[t]
-                    // commutes with the max and is applied when finalising).  Each value becomes a float key whose
-                    // 5 low mantissa bits hold the lane (31 - lane for x >= 0, lane for x < 0), the value rounded to nearest
-                    // at that position: a float max then means "largest value, then lowest lane" for either sign; values
-                    // closer than 2^-19 relative count as ties.
+                    // ---- lane-local: first-argmax over t (this lane's columns, in increasing t) of the masked similarity.
+                    // ---- across lanes: first-argmax over s (the lanes) for every column.  Each value becomes a float key
+                    // whose 5 low mantissa bits carry the lane, so that a float max means "largest value, then lowest
+                    // lane"; a 31-shuffle butterfly transposes and reduces the 32 x 32 keys of the warp.
                     float k[32];
-                    float cbest = -INFINITY;
-                    int cj = 0;
-                    // payload: for x >= 0 a larger payload is a larger float, for x < 0 a smaller one, so the lane goes in
-                    // as 31 - lane resp. lane: in both cases the lowest lane (= first template patch) wins a tie
-                    const uint32_t lane_pos = (uint32_t)(31 - lane), lane_neg = (uint32_t)lane;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 f4 = *reinterpret_cast<const float4*>(fa_s + i * 32 + j);  // broadcast read
-                        const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float x = __uint_as_float(v[j + u]);
-                            const float xt = x * ff[u];
-                            if (xt > cbest) { cbest = xt; cj = j + u; }
-                            const float xs = fmaf(x, rb_l, c_add);
-                            const uint32_t xb = __float_as_uint(xs);
-                            k[j + u] = __uint_as_float(((xb + 0x10u) & 0xFFFFFFE0u) | ((xb >> 31) ? lane_neg : lane_pos));
-                        }
-                    }
-                    if (ncols < 32) {
-                        // ragged last chunk: redo the lane-local scan over the live columns only
-                        cbest = -INFINITY;
-                        cj = 0;
+                    float cbest;
+                    int cj;
+                    if (FAST) {
+                        // keys are bits(sim + 2.0) with the low 5 bits replaced: all positive, ordered like the values;
+                        // payload 31 - lane (rows) resp. 31 - j (columns) lets the lowest index win a tie
+                        const uint32_t lane_pos = (uint32_t)(31 - lane);
+                        float ck = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float xt = __uint_as_float(v[j]) * fa_s[i * 32 + j];
-                            if (j < ncols && xt > cbest) { cbest = xt; cj = j; }
+                            const uint32_t xb = __float_as_uint(fmaf(__uint_as_float(v[j]), rb_l, c_add)) & 0xFFFFFFE0u;
+                            k[j] = __uint_as_float(xb | lane_pos);
+                            ck = fmaxf(ck, __uint_as_float(xb | (uint32_t)(31 - j)));
                         }
+                        if (ncols < 32) {  // ragged last chunk: columns past the last live row hold zeros (= 2.0): leave them out
+                            ck = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < ncols) ck = fmaxf(ck, __uint_as_float((__float_as_uint(k[j]) & 0xFFFFFFE0u) | (uint32_t)(31 - j)));
+                        }
+                        cj = 31 - (int)(__float_as_uint(ck) & 31u);
+                        cbest = __uint_as_float(__float_as_uint(ck) & 0xFFFFFFE0u) - 2.0f;
+                    } else {
+                        // exact compare on the lane's own columns (rb[s] > 0 commutes with the max; strict > keeps the
+                        // first index); row keys: value rounded to nearest at bit 5 (2^-19 relative), payload 31 - lane
+                        // for x >= 0 and lane for x < 0 so that the lowest lane wins for either sign
+                        cbest = -INFINITY;
+                        cj = 0;
+                        const uint32_t lane_pos = (uint32_t)(31 - lane), lane_neg = (uint32_t)lane;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __uint_as_float(v[j]);
+                            if (j < ncols && x > cbest) { cbest = x; cj = j; }
+                            const uint32_t xb = __float_as_uint(fmaf(x, rb_l, c_add));
+                            k[j] = __uint_as_float(((xb + 0x10u) & 0xFFFFFFE0u) | ((xb >> 31) ? lane_neg : lane_pos));
+                        }
+                        cbest *= rb_l;  // the masked similarity itself (the sign of the column maximum matters: masked
+                                        // query rows compete with the value 0, see finalize_scores_kernel)
                     }
                     if (cbest > best) { best = cbest; best_t = tp_s[i * 32 + cj]; }
                     // butterfly transpose-reduce: after the 5 exchanges lane j holds the warp's winner of column j
@@ -421,14 +431,14 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     {
                         const uint32_t kb = __float_as_uint(k[0]);
-                        const int win_lane = (kb >> 31) ? (int)(kb & 31u) : 31 - (int)(kb & 31u);
-                        const int win_s = warp_row0 + win_lane;
+                        const int win_lane = FAST ? 31 - (int)(kb & 31u) : ((kb >> 31) ? (int)(kb & 31u) : 31 - (int)(kb & 31u));
+                        const float val = FAST ? __uint_as_float(kb & 0xFFFFFFE0u) - 2.0f : __uint_as_float(kb & 0xFFFFFFE0u);
                         if (lane < ncols && warp_row0 < T)
-                            atomicMax(p.rowkey + bn * T + tp_s[i * 32 + lane],
-                                      pack_key(__uint_as_float(kb & 0xFFFFFFE0u), (uint32_t)win_s));
+                            atomicMax(p.rowkey + bn * T + tp_s[i * 32 + lane], pack_key(val + 0.0f, (uint32_t)(warp_row0 + win_lane)));
                     }
                 }
-                if (s_ok && best > -INFINITY) atomicMax(p.colkey + bn * T + s_row, pack_key(best + 0.0f, (uint32_t)best_t));
+                if (tc.nt == tc.nct - 1 && s_ok && best > -INFINITY)
+                    atomicMax(p.colkey + bn * T + s_row, pack_key(best + 0.0f, (uint32_t)best_t));
             } else {
                 // EPI_EMIT: lane = query patch t, columns = template patches s; the scaled products go to HBM
                 const int t = warp_row0 + lane;
@@ -479,6 +489,8 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                 }
             }
+          }
+         }
         }
     }
 
@@ -542,7 +554,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     auto kern = match_gemm_kernel<CL, EPI>;
     PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     long long clusters = sm_count() / CL;
-    if (clusters > (long long)p.total_tiles) clusters = p.total_tiles;
+    if (clusters > (long long)p.num_groups) clusters = p.num_groups;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clusters * CL));
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -569,7 +581,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                    int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
                    const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
-                   cudaStream_t st, int emit_tile_w) {
+                   cudaStream_t st, int emit_tile_w, const int32_t* det_order) {
     PP_CHECK_ARG(emit_tile_w == 0 || (epi == EPI_EMIT && emit_tile_w % 8 == 0 && T % emit_tile_w == 0 && (T / emit_tile_w) % 4 == 0),
                  "tiled emit needs a key map of W %% 8 == 0 columns and H %% 4 == 0 rows (W=%d, T=%d)", emit_tile_w, T);
     PP_CHECK_ARG(Kp > 0 && Kp % BLOCK_K == 0, "Kp must be a positive multiple of %d (got %d)", BLOCK_K, Kp);
@@ -577,7 +589,10 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                  "prepared operands must be 128-byte aligned");
     PP_CHECK_ARG((long long)n_banks * N * T < (1LL << 31) && (long long)B * T < (1LL << 31),
                  "operand row count exceeds the 2^31 TMA coordinate range; split the call");
-    PP_CHECK_ARG(epi != EPI_MATCH || B <= MAX_DETS_PER_LAUNCH, "at most %d detections per launch (got %d)", MAX_DETS_PER_LAUNCH, B);
+    if (cluster & PP_MATCH_FAST_KEYS) {
+        cluster &= ~PP_MATCH_FAST_KEYS;
+        if (epi == EPI_MATCH) epi = EPI_MATCH_FAST;
+    }
     if (cluster == 0) cluster = 2;
     PP_CHECK_ARG(cluster == 1 || cluster == 2, "cluster must be 0, 1 or 2 (got %d)", cluster);
     if (int rc = ensure_fault_buffer()) return rc;
@@ -588,9 +603,18 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.num_k_blocks = Kp / BLOCK_K;
     p.num_mt = (T + BLOCK_M * cluster - 1) / (BLOCK_M * cluster);
     p.num_nt = (T + BLOCK_N - 1) / BLOCK_N;
-    const long long tiles_ll = (long long)B * N * p.num_mt * p.num_nt;
-    PP_CHECK_ARG(tiles_ll < (1LL << 31), "too many tiles in one launch (%lld); split the detection batch", tiles_ll);
-    p.total_tiles = (uint32_t)tiles_ll;
+    // detections per group: as many as share M-side tiles usefully (8) while leaving >= 4 groups per cluster
+    const long long per_det = (long long)N * p.num_mt;
+    int chunk = 1;
+    if (det_order && bank_of_det) {
+        const long long want = (long long)B * per_det / (4LL * (sm_count() / cluster));
+        chunk = (int)(want < 1 ? 1 : (want > 8 ? 8 : want));
+    }
+    p.chunk = chunk;
+    p.det_order = chunk > 1 ? det_order : nullptr;
+    const long long groups_ll = (long long)((B + chunk - 1) / chunk) * per_det;
+    PP_CHECK_ARG(groups_ll < (1LL << 31), "too many tile groups in one launch (%lld); split the detection batch", groups_ll);
+    p.num_groups = (uint32_t)groups_ll;
     p.n_banks = (int)n_banks;
     p.bank_of_det = bank_of_det;
     p.mrow = mrow;
@@ -604,20 +628,23 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.emit_scale = emit_scale;
     p.emit_tile_w = emit_tile_w;
     p.fault = g_fault_dev;
-    if (p.total_tiles == 0) return PP_OK;
+    if (p.num_groups == 0) return PP_OK;
     // A = M-side operand (box of 128 rows), B = N-side operand (box of 256 / cluster rows); EPI_MATCH puts the template
     // bank on the M side and the compact query rows on the N side, EPI_EMIT the other way round
     CUtensorMap ta, tb;
-    const void* m_op = epi == EPI_MATCH ? bank_prep : q_prep;
-    const void* n_op = epi == EPI_MATCH ? q_prep : bank_prep;
-    const uint64_t m_rows = epi == EPI_MATCH ? (uint64_t)n_banks * N * T : (uint64_t)B * T;
-    const uint64_t n_rows = epi == EPI_MATCH ? (uint64_t)B * T : (uint64_t)n_banks * N * T;
+    const bool match = epi != EPI_EMIT;
+    const void* m_op = match ? bank_prep : q_prep;
+    const void* n_op = match ? q_prep : bank_prep;
+    const uint64_t m_rows = match ? (uint64_t)n_banks * N * T : (uint64_t)B * T;
+    const uint64_t n_rows = match ? (uint64_t)B * T : (uint64_t)n_banks * N * T;
     if (int rc = make_tmap(&ta, m_op, m_rows, (uint64_t)Kp, BLOCK_M)) return rc;
     if (int rc = make_tmap(&tb, n_op, n_rows, (uint64_t)Kp, BLOCK_N / cluster)) return rc;
     if (cluster == 1) {
-        return epi == EPI_MATCH ? launch_gemm<1, EPI_MATCH>(ta, tb, p, st) : launch_gemm<1, EPI_EMIT>(ta, tb, p, st);
+        return epi == EPI_MATCH ? launch_gemm<1, EPI_MATCH>(ta, tb, p, st)
+               : epi == EPI_MATCH_FAST ? launch_gemm<1, EPI_MATCH_FAST>(ta, tb, p, st) : launch_gemm<1, EPI_EMIT>(ta, tb, p, st);
     }
-    return epi == EPI_MATCH ? launch_gemm<2, EPI_MATCH>(ta, tb, p, st) : launch_gemm<2, EPI_EMIT>(ta, tb, p, st);
+    return epi == EPI_MATCH ? launch_gemm<2, EPI_MATCH>(ta, tb, p, st)
+           : epi == EPI_MATCH_FAST ? launch_gemm<2, EPI_MATCH_FAST>(ta, tb, p, st) : launch_gemm<2, EPI_EMIT>(ta, tb, p, st);
 }
 
 int fault_buffer(int** dev_ptr) {

@@ -156,13 +156,41 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
             for (int i = 0; i < 8; ++i) dst[i] = (j * PREP_CT + warp * 8 + i < C) ? __ldg(xc + i * strideP) : 0.f;
         }
     };
+    // QM: the query operand is written NORMALISED and multiplied by its mask value, x * m / max(||x||, 1e-12)
+    // (utils/matching.py:40-41,48), so the contraction's epilogue has no per-row factor to apply.  That needs the norm
+    // before the first store: a first pass over the patch's channels (the second one hits L2; query features are a few
+    // MB per detection, the kernel is latency-bound and runs beside the bank prologue).
+    float qscale = 1.0f;
+    if (QM) {
+        float s2 = 0.f;
+        float pa[8], pb[8];
+        load_chunk(pa, 0);
+        for (int j = 0; j < nchunks; j += 2) {
+            load_chunk(pb, j + 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s2 = fmaf(pa[i], pa[i], s2);
+            if (j + 1 < nchunks) {
+                load_chunk(pa, j + 2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s2 = fmaf(pb[i], pb[i], s2);
+            }
+        }
+        s_part[warp][lane] = s2;
+        __syncthreads();
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < PREP_WARPS; ++w) t += s_part[w][lane];
+        const float m = live ? qm.mrow[(size_t)g * P + p0 + lane] : 0.f;   // written by warp 0 above (before a __syncthreads)
+        qscale = m / fmaxf(sqrtf(t), 1e-12f);
+        __syncthreads();  // s_part is reused for the epilogue of this kernel
+    }
     float ss = 0.f;
     auto process = [&](const float (&cur)[8], int j) {
         const int c0 = j * PREP_CT;
         __align__(16) __nv_bfloat16 part[NPARTS][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float v = cur[i];
+            float v = QM ? cur[i] * qscale : cur[i];
             ss = fmaf(v, v, ss);
 #pragma unroll
             for (int k = 0; k < NPARTS; ++k) {
@@ -218,7 +246,7 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
 #pragma unroll
         for (int w = 0; w < PREP_WARPS; ++w) t += s_part[w][lane];
         const int orow = QM ? s_rank[lane] : p0 + lane;
-        if (orow >= 0) rnorm[(size_t)g * P + orow] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
+        if (orow >= 0) rnorm[(size_t)g * P + orow] = QM ? 1.0f : 1.0f / fmaxf(sqrtf(t), 1e-12f);   // QM: already applied
     }
     // ---- zero the K padding [nseg*C, Kp) ----
     const int pad0 = nseg * C, npad = Kp - pad0;

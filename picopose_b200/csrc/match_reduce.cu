@@ -10,7 +10,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                    int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
                    const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
-                   cudaStream_t st, int emit_tile_w = 0);
+                   cudaStream_t st, int emit_tile_w = 0, const int32_t* det_order = nullptr);
 
 int prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm, int Wm, int mode,
                        void* q_prep, float* q_rnorm, void* q_meta, void* clear, size_t clear_bytes, void* stream);
@@ -24,6 +24,22 @@ __global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm
         const int r = i - b * H * W;
         const int y = r / W, x = r - y * W;
         out[i] = mask[((size_t)b * Hm + nearest_src(y, Hm, H)) * Wm + nearest_src(x, Wm, W)];
+    }
+}
+
+// Stable sort of the detections by bank (B <= 1024, one block): order[i] = detection at position i.  Detections that share
+// an object bank become neighbours, and the contraction hands neighbours to one cluster so that they share the bank's
+// tiles in L2 instead of each streaming the bank from HBM.
+__global__ void __launch_bounds__(1024) det_order_kernel(const int32_t* __restrict__ bank_of_det, int B, int32_t* __restrict__ order) {
+    __shared__ int s_bank[1024];
+    const int i = threadIdx.x;
+    if (i < B) s_bank[i] = bank_of_det[i];
+    __syncthreads();
+    if (i < B) {
+        const int mine = s_bank[i];
+        int rank = 0;
+        for (int j = 0; j < B; ++j) rank += (s_bank[j] < mine) || (s_bank[j] == mine && j < i);
+        order[rank] = i;
     }
 }
 
@@ -50,9 +66,9 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
         ck = ck > zero_key ? ck : zero_key;
         // a masked query row is all zeros in the reference: max 0 at index 0
         const bool on = m != 0.f;
-        // row key holds max_s(acc * rb[s]); the row's own inverse norm and mask value complete sim[t, argmax]
-        const int rj = rank[(size_t)b * T + j];  // compact row of patch j (its inverse norm is stored there)
-        const float sc = (on && rk && rj >= 0) ? key_value(rk) * ra[(size_t)b * T + rj] * m : 0.f;
+        // row key holds max_s of the masked similarity m[t] * sim[t, s] (the query operand carries norm and mask)
+        const int rj = rank[(size_t)b * T + j];  // compact row of patch j
+        const float sc = (on && rk && rj >= 0) ? key_value(rk) * ra[(size_t)b * T + rj] : 0.f;
         const int it = (on && rk) ? (int)key_index(rk) : 0;
         const int is = ck ? (int)key_index(ck) : 0;
         const float valid = (it != 0 && is != 0) ? m : 0.f;  // tar_mask * (idx_src2tar != 0) * (idx_tar2src != 0)
@@ -289,7 +305,8 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 extern "C" size_t pp_match_scores_workspace(int B, int N, int T) {
     if (B < 0 || N < 0 || T < 0) return 0;
     const size_t keys = (size_t)B * N * T * sizeof(unsigned long long);
-    return 2 * pp::align_up(keys, 256) + pp::align_up((size_t)B * sizeof(int), 256);
+    // row keys | column keys | per-detection finished-view counters | bank-sorted detection order
+    return 2 * pp::align_up(keys, 256) + 2 * pp::align_up((size_t)B * sizeof(int), 256);
 }
 
 namespace pp {
@@ -315,11 +332,17 @@ static int match_scores_impl(const void* q_prep, const float* q_rnorm, const voi
     unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(workspace);
     unsigned long long* colkey = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + keys);
     int* done = reinterpret_cast<int*>(static_cast<char*>(workspace) + 2 * keys);  // per-detection finished-view counters
+    int32_t* order = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + 2 * keys + align_up((size_t)B * sizeof(int), 256));
     // the key arrays and the per-detection counters start at zero (a caller that has already cleared the scratch,
     // e.g. on a forked stream beside the bank prologue, says so)
     if (!keys_cleared) PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys + align_up((size_t)B * sizeof(int), 256), st));
+    const bool sort_dets = bank_of_det != nullptr && B > 1 && B <= 1024;
+    if (sort_dets) {
+        det_order_kernel<<<1, 1024, 0, st>>>(bank_of_det, B, order);
+        PP_LAUNCHED();
+    }
     if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, qm.mrow, qm.tv, qm.rowmap, q_rnorm,
-                                bank_rnorm, rowkey, colkey, nullptr, 1.0f, cluster, st))
+                                bank_rnorm, rowkey, colkey, nullptr, 1.0f, cluster, st, 0, sort_dets ? order : nullptr))
         return rc;
     size_t smem = 0;
     if (k > 0) {
@@ -543,6 +566,7 @@ extern "C" int pp_match_templates(const float* tar_feat, const float* tar_mask, 
                                     pp_match_scores_workspace(B, N, T), stream))
         return rc;
     const bool rank_it = k > 0 && out_score && out_idx;
+    if (mode == PP_MODE_BF16) cluster |= PP_MATCH_FAST_KEYS;
     return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
                              n_banks, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
                              rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
@@ -610,6 +634,7 @@ extern "C" int pp_match_templates_dense(const float* src_feats, int64_t G, const
     PP_CUDA(e1);
     PP_CUDA(e2);
     const bool rank_it = k > 0 && out_score && out_idx;
+    if (mode == PP_MODE_BF16) cluster |= PP_MATCH_FAST_KEYS;
     return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
                              G, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
                              rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,

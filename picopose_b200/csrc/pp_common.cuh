@@ -54,6 +54,17 @@ QueryMeta split_query_meta(void* q_meta, int B, int T);
 // codes: 1-4 contraction pipeline time-outs (the kernel traps), 5 exchange peer missing, 6 bank index out of range.
 int fault_buffer(int** dev_ptr);
 
+// 1x1 convolution applied to the block's lookup tile while it is still in shared memory: the first
+// layer of the reference's MotionEncoder.corr_net (model/stage3/raft_decoder.py:113-116,127-129,157), corr_inch = L*D*D ->
+// cout channels (+ bias, + ReLU), i.e. a (cout x L*D*D) matrix applied per query.
+struct WConv {
+    const float* weight = nullptr;  // (cout, L*D*D) row-major = Conv2d.weight[:, :, 0, 0]
+    const float* bias = nullptr;    // (cout) or null
+    float* out = nullptr;           // (N, cout, H, W)
+    int cout = 0;
+    int relu = 0;
+};
+
 // Verifies the current device is sm_100 (cached per device).
 int require_sm100();
 int sm_count();

@@ -22,7 +22,7 @@
 namespace pp {
 
 int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
-                       int H, int W, float* out, cudaStream_t st, bool* handled);  // windowed_corr_tiled.cu
+                       int H, int W, float* out, cudaStream_t st, bool* handled, const WConv* conv = nullptr);  // windowed_corr_tiled.cu
 
 constexpr int WC_MAX_LEVELS = 8;
 constexpr int WC_QUERIES = 32;  // queries per block (one output line)
@@ -457,3 +457,36 @@ extern "C" int pp_windowed_correlation(const float* f1t, const void* const* f2t_
         default: return launch_wcorr<8>(p, st);
     }
 }
+
+// Fused CorrelationPyramid + CorrLookup + first MotionEncoder convolution (model/stage3/flow_decoder.py:59-62 with
+// model/stage3/raft_decoder.py:113-116,157): the lookup tile never leaves shared memory.
+extern "C" int pp_windowed_correlation_conv1x1(const float* f1t, const void* const* f2t_levels, int L, const float* flow,
+                                               int N, int C, int H, int W, int radius, const float* weight, const float* bias,
+                                               int cout, int relu, float* out, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (N == 0) return PP_OK;
+    PP_CHECK_ARG(f1t && f2t_levels && flow && weight && out, "pp_windowed_correlation_conv1x1: null pointer");
+    PP_CHECK_ARG(L >= 1 && L <= WC_MAX_LEVELS && N > 0 && H > 0 && W > 0 && (H >> (L - 1)) > 0 && (W >> (L - 1)) > 0,
+                 "pp_windowed_correlation_conv1x1: bad shape");
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(f1t) & 15) == 0, "pp_windowed_correlation_conv1x1: features must be 16-byte aligned");
+    for (int l = 0; l < L; ++l)
+        PP_CHECK_ARG(f2t_levels[l] && (reinterpret_cast<uintptr_t>(f2t_levels[l]) & 15) == 0,
+                     "pp_windowed_correlation_conv1x1: bad level %d", l);
+    WConv conv;
+    conv.weight = weight;
+    conv.bias = bias;
+    conv.out = out;
+    conv.cout = cout;
+    conv.relu = relu ? 1 : 0;
+    bool handled = false;
+    if (int rc = launch_wcorr_tiled(radius, f1t, f2t_levels, L, flow, N, C, H, W, nullptr, static_cast<cudaStream_t>(stream), &handled,
+                                    &conv))
+        return rc;
+    // the fusion lives in the TMA-tiled kernel: r <= 2 (what FlowDecoder uses), C % 32 == 0, L <= 4, cout % 8 == 0 and a
+    // weight matrix that fits the kernel's stage buffers; other shapes are the caller's to run unfused
+    PP_CHECK_ARG(handled, "pp_windowed_correlation_conv1x1: shape not covered by the fused kernel (radius %d, C %d, L %d, cout %d)",
+                 radius, C, L, cout);
+    return PP_OK;
+}
+

@@ -24,7 +24,7 @@ namespace pp {
 
 // called from windowed_corr.cu
 int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
-                       int H, int W, float* out, cudaStream_t st, bool* handled);
+                       int H, int W, float* out, cudaStream_t st, bool* handled, const WConv* conv = nullptr);
 
 namespace {
 
@@ -51,6 +51,7 @@ struct WTileParams {
     int N, C, H, W, HW, L;
     float scale;
     int tiles_x, tiles_y;
+    WConv conv;         // conv.weight != null: fused 1x1 convolution epilogue; `out` may then be null (lookup not stored)
 };
 
 // same arithmetic as corr_lookup.cu::axis_tap / windowed_corr.cu::wc_axis_tap
@@ -420,6 +421,52 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
         __syncwarp();
     }
     __syncthreads();
+    if (p.conv.weight) {
+        // ---- fused 1x1 convolution: y[co, q] = act(bias[co] + sum_row W[co, row] * lookup[row, q]) for the tile's 64 queries.
+        // The TMA stages are free now: the weight matrix is staged there transposed ([row][co]) so that a thread's 8
+        // output channels are two 16-byte loads; a thread owns 8 channels x 4 queries (one row segment of the 8 x 8 tile).
+        const int cout = p.conv.cout;
+        float* w_s = stage0;
+        for (int i = tid; i < cout * rows; i += WT_THREADS) {
+            const int co = i / rows, row = i - co * rows;
+            w_s[row * cout + co] = __ldg(p.conv.weight + i);
+        }
+        __syncthreads();
+        const int qg = tid & 15, q0 = qg * 4;
+        const int qh = ty * 8 + (q0 >> 3), qw = tx * 8 + (q0 & 7);
+        for (int co0 = (tid >> 4) * 8; co0 < cout; co0 += (WT_THREADS >> 4) * 8) {
+            float acc[8][4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const float bv = p.conv.bias ? __ldg(p.conv.bias + co0 + a) : 0.f;
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = bv;
+            }
+            for (int row = 0; row < rows; ++row) {
+                const float4 w0 = *reinterpret_cast<const float4*>(w_s + row * cout + co0);
+                const float4 w1 = *reinterpret_cast<const float4*>(w_s + row * cout + co0 + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float* xr = out_tile + (size_t)row * (TQ + 1) + q0;
+                const float xv[4] = {xr[0], xr[1], xr[2], xr[3]};
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) acc[a][b2] = fmaf(wv[a], xv[b2], acc[a][b2]);
+            }
+            if (qh < p.H) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    float* dst = p.conv.out + (((size_t)n * cout + co0 + a) * p.H + qh) * p.W + qw;
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) {
+                        const float v = p.conv.relu ? fmaxf(acc[a][b2], 0.f) : acc[a][b2];
+                        if (qw + b2 < p.W) __stcs(dst + b2, v);
+                    }
+                }
+            }
+        }
+        if (!p.out) return;
+    }
     // out[n, row, tile]: 8-float (32-byte sector) runs, 8 of them per row
     float* out_n = p.out + (size_t)n * rows * p.HW;
     for (int row = warp; row < rows; row += WT_WARPS) {
@@ -473,11 +520,17 @@ int launch(const WTileMaps& maps, const WTileParams& p, cudaStream_t st) {
 
 // Runs the tiled kernel when it covers the problem (*handled = true); otherwise leaves it to the per-query kernel.
 int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_levels, int L, const float* flow, int N, int C,
-                       int H, int W, float* out, cudaStream_t st, bool* handled) {
+                       int H, int W, float* out, cudaStream_t st, bool* handled, const WConv* conv) {
     *handled = false;
     if (radius < 1 || radius > 2 || L > WT_MAX_LEVELS || C % WT_CH != 0) return PP_OK;
     const size_t smem = radius == 1 ? WT<1>::smem_bytes(L) : WT<2>::smem_bytes(L);
     if (smem > 220 * 1024) return PP_OK;
+    if (conv) {
+        // the transposed weight matrix must fit the two TMA stages it reuses; 8 output channels per thread step
+        const int D = 2 * radius + 1;
+        const size_t stage_words = 2 * (size_t)(WT<2>::KEY_WORDS + WT<2>::F1_WORDS);
+        if (conv->cout <= 0 || conv->cout % 8 != 0 || (size_t)conv->cout * L * D * D > stage_words) return PP_OK;
+    }
     WTileMaps maps;
     WTileParams p{};
     if (int rc = make_map(&maps.f1, f1t, N, H, W, C, 8, 8)) return rc;
@@ -500,6 +553,7 @@ int launch_wcorr_tiled(int radius, const float* f1t, const void* const* f2t_leve
     p.scale = 1.0f / sqrtf((float)C);
     p.tiles_x = (W + 7) / 8;
     p.tiles_y = (H + 7) / 8;
+    if (conv) p.conv = *conv;
     *handled = true;
     return radius == 1 ? launch<1>(maps, p, st) : launch<2>(maps, p, st);
 }

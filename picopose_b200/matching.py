@@ -297,6 +297,8 @@ def template_scores(src_feats, tar_feat: torch.Tensor, tar_mask: torch.Tensor, *
         it = torch.empty(B, N, T, dtype=torch.int32, device=dev)
         is_ = torch.empty(B, N, T, dtype=torch.int32, device=dev)
     cl = default_cluster() if cluster is None else cluster
+    if mid == _lib.MODE_BF16:
+        cl |= _lib.MATCH_FAST_KEYS          # cheaper reduction keys, resolution 7.6e-6 (include/picopose_b200.h)
     # bound the scratch (two 64-bit keys per (b, n, t)) by slicing the detection batch
     per_det = max(1, lib.pp_match_scores_workspace(1, N, T))
     chunk = max(1, min(B, _WORKSPACE_LIMIT // per_det, _MAX_DETS_PER_LAUNCH))

@@ -43,8 +43,8 @@ def test_pure_host_entry_points(lib):
     assert lib.pp_match_kp(40, 0) == 64                      # K padded to the 64-element swizzle row
     assert lib.pp_match_kp(384, 2) == 1152 and lib.pp_match_kp(384, 1) == 2304
     assert lib.pp_match_kp(0, 0) < 0 and lib.pp_match_kp(64, 7) < 0
-    # two 64-bit keys per (b, n, t); query bookkeeping = 3 words per patch + 2 per detection
-    assert lib.pp_match_scores_workspace(1, 162, 1024) == 2 * 162 * 1024 * 8 + 256
+    # two 64-bit keys per (b, n, t) + two per-detection int arrays; query bookkeeping = 3 words per patch + 2 per detection
+    assert lib.pp_match_scores_workspace(1, 162, 1024) == 2 * 162 * 1024 * 8 + 2 * 256
     assert lib.pp_match_query_meta_bytes(2, 1024) == (3 * 2 * 1024 + 4) * 4
     assert lib.pp_match_similarity_workspace(2, 256) == 2048 + 2 * 256 * 256 * 4
     assert isinstance(lib.pp_launch_count(), int)

@@ -39,10 +39,19 @@ class CudaOps:
         from picopose_b200.corr_lookup import coords_grid
         return coords_grid(B, torch.arange(0, W, device=device), torch.arange(0, H, device=device))
 
+    def encode(self, encoder, corr, flow):
+        # what the overlay's MotionEncoder.forward does: first 1x1 conv of corr_net inside the lookup kernel when it can
+        from picopose_b200.correlation import motion_encoder_forward
+        return motion_encoder_forward(encoder, corr, flow)
 
-@pytest.mark.parametrize("fused", ["1", "0"])
+
+@pytest.mark.parametrize("fused", ["conv", "1", "0"])
 def test_flow_decoder_loop_against_the_reference(fused, monkeypatch):
-    monkeypatch.setenv("PICOPOSE_B200_FUSED_CORR", fused)      # 1: windowed correlation (no volume); 0: pyramid + lookup
+    import picopose_b200.correlation as _corr
+    # conv: windowed correlation + MotionEncoder's first 1x1 conv in one kernel (what the overlay runs);
+    # 1: windowed correlation (no volume); 0: materialised (tiled) pyramid + lookup
+    monkeypatch.setenv("PICOPOSE_B200_FUSED_CORR", "0" if fused == "0" else "1")
+    monkeypatch.setattr(_corr, "ENCODER_FUSION", fused == "conv")
     g = np.load(os.path.join(GOLDEN, "flow_decoder.npz"))
     seed = int(g["seed"])
     torch.manual_seed(seed)

@@ -579,6 +579,38 @@ def test_windowed_correlation_vs_oracle(N, C, H, L, r, sigma, kernel, monkeypatc
     np.testing.assert_allclose(out2.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5)
 
 
+def test_fused_lookup_and_first_motion_conv():
+    """CorrelationPyramid -> CorrLookup -> MotionEncoder.corr_net[0] (1x1 conv + ReLU) in one kernel, against
+    the reference's own modules (tests/golden/motion_conv.npz) and against the oracle at the FlowDecoder's shapes; shapes
+    the fused kernel does not cover report it instead of computing something else."""
+    from picopose_b200.correlation import LazyCorrelationPyramid, LazyLookup, windowed_correlation, windowed_correlation_conv
+    g = load("motion_conv.npz")
+    f1, f2, flow, w, b = (cuda(g[k]) for k in ("f1", "f2", "flow", "weight", "bias"))
+    out = windowed_correlation_conv(f1, f2, flow, 2, 2, w, b, relu=True)
+    _lib.check_device_faults()
+    assert tuple(out.shape) == g["out"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=0, atol=2e-5)
+    gen = torch.Generator().manual_seed(91)
+    for (N, C, H, L, cout, relu, use_bias) in ((2, 256, 16, 1, 256, True, True), (1, 256, 32, 2, 256, True, True),
+                                               (1, 256, 64, 3, 256, True, True), (1, 64, 24, 2, 64, False, False),
+                                               (3, 32, 20, 1, 8, True, False)):
+        a = torch.randn(N, C, H, H, generator=gen)
+        c = torch.randn(N, C, H, H, generator=gen)
+        fl = 2.0 * torch.randn(N, 2, H, H, generator=gen)
+        fl[0, :, 0, 0] = 3e8                                              # an outlier query (deferred path of the kernel)
+        wt = torch.randn(cout, L * 25, 1, 1, generator=gen) / 5.0
+        bs = torch.randn(cout, generator=gen) if use_bias else None
+        ref = OL.conv1x1_relu(OL.corr_lookup(OL.correlation_pyramid(a, c, L), fl, 2), wt, bs, relu=relu)
+        got = windowed_correlation_conv(a.to(DEV), c.to(DEV), fl.to(DEV), L, 2, wt.to(DEV), None if bs is None else bs.to(DEV), relu)
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-4)
+        lazy = LazyLookup(LazyCorrelationPyramid(a.to(DEV), c.to(DEV), L), fl.to(DEV), 2)
+        assert torch.equal(lazy.materialise(), windowed_correlation(a.to(DEV), c.to(DEV), fl.to(DEV), L, 2))
+        assert torch.equal(lazy.conv1x1(wt.to(DEV), None if bs is None else bs.to(DEV), relu), got)
+    with pytest.raises(RuntimeError, match="not covered"):               # radius 3: outside the fused kernel
+        windowed_correlation_conv(a.to(DEV), c.to(DEV), fl.to(DEV), 1, 3, torch.randn(8, 49, device=DEV))
+    assert LazyLookup(LazyCorrelationPyramid(a.to(DEV), c.to(DEV), 1), fl.to(DEV), 3).conv1x1(torch.randn(8, 49, device=DEV)) is None
+
+
 def test_correlation_pyramid():
     from picopose_b200.correlation import correlation_pyramid
     g = load("pyramid.npz")

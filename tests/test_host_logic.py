@@ -81,8 +81,11 @@ def test_overlay_shadows_exactly_three_reference_modules(tmp_path):
         fd = importlib.import_module("model.stage3.flow_decoder")
         assert rd.__file__.startswith(launcher.OVERLAY) and rd.ORIGIN == "reference" and hasattr(rd, "MotionEncoder")
         assert rd.CorrelationPyramid.__module__ == "picopose_b200.correlation"
+        assert rd.MotionEncoder.__mro__[1].__module__ == "model.stage3._reference_raft_decoder"   # subclass of the reference's
         assert fd.ORIGIN == "reference"
     finally:
+        import picopose_b200.correlation as _c
+        _c.ENCODER_FUSION = False
         sys.path[:] = saved_path
         for k in list(sys.modules):
             if ours(k):
@@ -166,7 +169,11 @@ def test_reference_flow_decoder_builds_on_the_overlay():
         assert [type(m).__module__ for m in dec.corr_lookup] == ["picopose_b200.corr_lookup"] * 3
         assert [type(m).__module__ for m in dec.corr_block] == ["picopose_b200.correlation"] * 3
         assert dec.corr_lookup[0].r == 2                                  # flow_decoder.py:24 halves the radius
-        assert type(dec.encoder[0]).__module__ == "model.stage3._reference_raft_decoder"
+        enc = type(dec.encoder[0])       # our subclass (lookup + first 1x1 conv fusion) of the reference's MotionEncoder
+        assert enc.__module__ == "model.stage3.raft_decoder" and enc.__mro__[1].__module__ == "model.stage3._reference_raft_decoder"
+        ref_keys = [k for k, _ in enc.__mro__[1](num_levels=1, radius=2, net_type="Basic", conv_cfg=None, norm_cfg=None,
+                                                 act_cfg=dict(type="ReLU")).state_dict().items()]
+        assert list(dec.encoder[0].state_dict()) == ref_keys                                  # checkpoints load unchanged
         m = importlib.import_module("utils.matching")
         c = importlib.import_module("utils.correspondence")
         assert m.matching_templates.__module__ == "picopose_b200.matching"
@@ -174,6 +181,8 @@ def test_reference_flow_decoder_builds_on_the_overlay():
         tu = importlib.import_module("utils.torch_utils")
         assert tu.__file__.startswith(REFERENCE)
     finally:
+        import picopose_b200.correlation as _c
+        _c.ENCODER_FUSION = False
         sys.path[:] = saved_path
         for k in list(sys.modules):
             if ours(k):
