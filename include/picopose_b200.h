@@ -205,14 +205,22 @@ PP_API int pp_topk_exchange(const float* scores, int B, int N, int k, int64_t id
                      void* stream);
 
 /* Stage-2 input volume.  Replaces matching_features_similarity, utils/matching.py:6-26.
- *   q_prep/q_rnorm, s_prep/s_rnorm : (B, T, Kp) / (B, T) prepared query / template features; src_mask (B,Hm,Wm) fp32
+ *   q_prep/q_rnorm, s_prep/s_rnorm : (B, T, Kp) / (B, T) prepared query / template features (pp_match_prepare, is_query = 1 / 0);
+ *   src_mask (B,Hm,Wm) fp32
  *   out : (B, S, H, W) fp32 with out[b,s,h,w] = max(0, sim[b, t = w*H+h, s] * mask_s)
- *   workspace >= pp_match_similarity_workspace(B, T) bytes. */
+ * Norms, template mask (nearest-resized on the fly), clamp and the "(w h)" layout are applied by the contraction's
+ * epilogue: one launch, no staging (workspace may be NULL; pp_match_similarity_workspace returns 0). */
 PP_API size_t pp_match_similarity_workspace(int B, int T);
 PP_API int pp_match_similarity(const void* q_prep, const float* q_rnorm, const void* s_prep, const float* s_rnorm,
                         const float* src_mask,
                         int B, int H, int W, int Kp, int Hm, int Wm, float* out,
                         void* workspace, size_t workspace_bytes, int cluster, void* stream);
+/* The same from fp32 features, as the reference calls it (model/picopose.py:81): src_feat, tar_feat (B, C, H, W).
+ * Two launches: one prologue for both operands, one contraction.  workspace >= pp_match_similarity_dense_workspace bytes. */
+PP_API size_t pp_match_similarity_dense_workspace(int B, int C, int H, int W, int mode);
+PP_API int pp_match_similarity_dense(const float* src_feat, const float* tar_feat, const float* src_mask, int B, int C,
+                              int H, int W, int Hm, int Wm, int mode, float* out, void* workspace, size_t workspace_bytes,
+                              int cluster, void* stream);
 
 /* All-pairs correlation pyramid.  Replaces CorrelationPyramid.forward, model/stage3/raft_decoder.py:30-53
  * (torch.matmul / sqrt(C) + AvgPool2d(2,2) levels), the producer of the volumes pp_corr_lookup reads.

@@ -55,6 +55,8 @@ SIGNATURES = {
     "pp_topk_exchange": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp]),
     "pp_match_similarity_workspace": (_sz, [_i, _i]),
     "pp_match_similarity": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
+    "pp_match_similarity_dense_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "pp_match_similarity_dense": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "pp_correlation_pyramid": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), _i, _vp]),
     "pp_correlation_pyramid_tiled": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, C.POINTER(_vp), _i, _vp]),
     "pp_windowed_correlation_prepare": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

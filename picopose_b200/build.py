@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpicopose_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 
-SOURCES = ["capi.cu", "corr_lookup.cu", "correspondence.cu", "match_prep.cu", "match_gemm.cu", "match_reduce.cu", "windowed_corr.cu", "windowed_corr_tiled.cu", "exchange.cu", "select.cu"]
+SOURCES = ["capi.cu", "corr_lookup.cu", "corr_lookup_tma.cu", "correspondence.cu", "match_prep.cu", "match_gemm.cu", "match_reduce.cu", "windowed_corr.cu", "windowed_corr_tiled.cu", "exchange.cu", "select.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

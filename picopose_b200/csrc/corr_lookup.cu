@@ -14,43 +14,12 @@
 // Coordinates follow the reference's float arithmetic op by op (x*2/(W-1)-1 and grid_sample's
 // inverse, utils/corr_lookup.py:61-65 + ATen grid_sampler_unnormalize), so floor/weights agree.
 #include "pp_common.cuh"
+#include "corr_lookup.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace pp {
-
-constexpr int LOOKUP_MAX_LEVELS = 8;
-constexpr int LOOKUP_MAX_RADIUS = 16;
-
-struct LookupParams {
-    const float* vol[LOOKUP_MAX_LEVELS];
-    int vh[LOOKUP_MAX_LEVELS];
-    int vw[LOOKUP_MAX_LEVELS];
-    int vec_ok[LOOKUP_MAX_LEVELS];  // 16-byte path usable (width % 4 == 0, base aligned)
-    int tiled;                      // slices stored as 4 x 8 tiles of 32 floats (one 128-byte line each), tiles row-major
-    int L;
-    const float* flow;
-    float* out;
-    int B, H, W, HW;
-    int radius;
-    int groups_per_b;  // ceil(HW / 32)
-    int total_groups;
-    int nr_max, nv_max;  // generic kernel: staged rows / 16-byte pieces per row
-    int qstride;         // generic kernel: words between two queries' staging areas
-};
-
-// pixel coordinate -> (floor index, weight of the upper tap), replicating
-//   g = p*2/max(size-1,1) - 1 ; i = ((g+1)/2)*(size-1)
-__device__ __forceinline__ void axis_tap(float p, int size, int& i0, float& w1) {
-    float den = (float)(size > 1 ? size - 1 : 1);
-    float g = __fsub_rn(__fdiv_rn(__fmul_rn(p, 2.0f), den), 1.0f);
-    float i = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
-    float f = floorf(i);
-    w1 = __fsub_rn(i, f);
-    // clamp so that far-away (or non-finite) windows stay inside the staged footprint; every tap of
-    // a clamped index is out of bounds and contributes zero, exactly as zero padding does.
-    f = fminf(fmaxf(f, -2.0f), (float)size);
-    i0 = (f == f) ? (int)f : -2;
-    if (!(w1 >= 0.0f && w1 <= 1.0f)) w1 = 0.0f;  // non-finite coordinates: everything is padding
-}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -446,6 +415,17 @@ static int corr_lookup_impl(const void* const* pyr_ptrs, const int* pyr_h, const
     p.groups_per_b = (p.HW + 31) / 32;
     p.total_groups = B * p.groups_per_b;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (tiled) {
+        // PICOPOSE_LOOKUP_KERNEL=tiles: the whole-tile fetch kernel (corr_lookup_tma.cu).  Measured slower than the banded
+        // kernel on the same tiled volume (0.99 vs 0.28 ms at r = 4: two warps per SM cannot fill the issue slots), so it
+        // is opt-in; see DESIGN.md section 3.4 and profiles/r2j_lookup_tiles.*.
+        const char* e = getenv("PICOPOSE_LOOKUP_KERNEL");
+        if (e && strcmp(e, "tiles") == 0) {
+            bool handled = false;
+            if (int rc = launch_lookup_tma(p, st, &handled)) return rc;
+            if (handled) return PP_OK;
+        }
+    }
     if (all_vec) {
         // band height per radius: keeps ~12-25 KB of staging per warp so 8-16 warps share an SM
         switch (radius) {

@@ -48,7 +48,9 @@ constexpr int MAX_DETS_PER_LAUNCH = 1024;  // tile prefix table lives in shared 
 // EPI_MATCH_FAST: same reductions with cheaper keys (bf16 mode): the similarity is offset by 2.0 so that every key is a
 // positive float -- no sign handling, no rounding add -- at a resolution of 2^-17 (7.6e-6 absolute), far below the bf16
 // operands' own error; EPI_MATCH keeps 2^-19 relative for the fp32-accurate modes.
-enum { EPI_MATCH = 0, EPI_EMIT = 1, EPI_MATCH_FAST = 2 };
+// EPI_SIM: the stage-2 similarity volume (utils/matching.py:22-25) straight from the accumulator: norms, template mask,
+// clamp and the "(w h)" transposed layout applied in the epilogue, out[b, s, h, w] = max(0, sim[b, t = w*H + h, s] * m[s]).
+enum { EPI_MATCH = 0, EPI_EMIT = 1, EPI_MATCH_FAST = 2, EPI_SIM = 3 };
 
 struct GemmParams {
     int B, N, T;  // detections, views per bank, patches (T == S)
@@ -70,6 +72,8 @@ struct GemmParams {
     float emit_scale;
     int emit_tile_w;               // EPI_EMIT: 0 = rows of T keys (reference layout); W > 0 = every row is an (T/W x W) key map
                                    // stored as 4 x 8 tiles of 32 floats (one 128-byte line each), see corr_lookup.cu
+    const float* cmask;            // EPI_SIM: (B, Hm, Wm) template masks, nearest-resized to the patch grid on the fly
+    int Hm, Wm, gh, gw;            // EPI_SIM: mask size, patch grid (gh x gw, T = gh * gw)
     int* fault;                    // host-mapped fault record
 };
 
@@ -175,7 +179,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + NUM_ACC + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
     float* rb_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
-    constexpr bool MATCH = EPI != EPI_EMIT;  // template patches on the M side, compact query rows on the N side
+    constexpr bool MATCH = EPI == EPI_MATCH || EPI == EPI_MATCH_FAST;  // template patches on the M side, compact query rows on the N side
     constexpr bool FAST = EPI == EPI_MATCH_FAST;
 
     const int warp = threadIdx.x >> 5;
@@ -439,6 +443,52 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 if (tc.nt == tc.nct - 1 && s_ok && best > -INFINITY)
                     atomicMax(p.colkey + bn * T + s_row, pack_key(best + 0.0f, (uint32_t)best_t));
+            } else if (EPI == EPI_SIM) {
+                // lane = query patch t, columns = template patches s: sim = acc * ra[t] * rb[s], times the template mask,
+                // clamped at 0, written at out[b, s, h, w] with t = w * gh + h ("b (w h) c -> b c h w", utils/matching.py:25).
+                // For a fixed column the lanes' addresses are gw floats apart: partial sectors that L2 merges (the whole
+                // volume is written exactly once; it is 256 KB per detection at the native 16 x 16 grid).
+                const int t = warp_row0 + lane;
+                const bool row_ok = t < T;
+                const float ra_t = row_ok ? __ldg(p.ra + (size_t)tc.b * T + t) : 0.f;
+                const int th = row_ok ? t % p.gh : 0, tw = row_ok ? t / p.gh : 0;
+                float* out_t = p.emit + (size_t)tc.b * T * T + (size_t)th * p.gw + tw;   // + s * T per column
+                // per-column factor rb[s] * mask[s] of this warp's <= 2 chunks, staged before the accumulator is ready
+                float* cf_s = rb_stage + e * (2 * EPI_COLS);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < EPI_CHUNKS; ++i) {
+                    const int s = tc.nt * BLOCK_N + (hh + 4 * i) * 32 + lane;
+                    float f = 0.f;
+                    if (s < T) {
+                        const int sy = s / p.gw, sx = s - sy * p.gw;
+                        const float m = __ldg(p.cmask + ((size_t)tc.b * p.Hm + nearest_src(sy, p.Hm, p.gh)) * p.Wm + nearest_src(sx, p.Wm, p.gw));
+                        f = __ldg(p.rb + (size_t)tc.b * T + s) * m;
+                    }
+                    cf_s[i * 32 + lane] = f;
+                }
+                __syncwarp();
+                mbar_wait(tfull_bar(as), aphase, p.fault, 4, as);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int i = 0; i < EPI_CHUNKS; ++i) {
+                    const int c = hh + 4 * i;
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    ptx::tmem_ld_wait();
+                    if (i == EPI_CHUNKS - 1) release_tmem();
+                    const int s0 = tc.nt * BLOCK_N + c * 32;
+                    if (s0 >= T || !row_ok) continue;
+                    const int ncols = min(32, T - s0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < ncols) {
+                            // (acc * ra) * (rb * m): same association as the reference up to the folding of m into rb
+                            const float val = (__uint_as_float(v[j]) * ra_t) * cf_s[i * 32 + j];
+                            out_t[(size_t)(s0 + j) * T] = val < 0.f ? 0.f : val;
+                        }
+                    }
+                }
             } else {
                 // EPI_EMIT: lane = query patch t, columns = template patches s; the scaled products go to HBM
                 const int t = warp_row0 + lane;
@@ -581,7 +631,7 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                    int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
                    const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
-                   cudaStream_t st, int emit_tile_w, const int32_t* det_order) {
+                   cudaStream_t st, int emit_tile_w, const int32_t* det_order, const float* cmask, int Hm, int Wm, int gh) {
     PP_CHECK_ARG(emit_tile_w == 0 || (epi == EPI_EMIT && emit_tile_w % 8 == 0 && T % emit_tile_w == 0 && (T / emit_tile_w) % 4 == 0),
                  "tiled emit needs a key map of W %% 8 == 0 columns and H %% 4 == 0 rows (W=%d, T=%d)", emit_tile_w, T);
     PP_CHECK_ARG(Kp > 0 && Kp % BLOCK_K == 0, "Kp must be a positive multiple of %d (got %d)", BLOCK_K, Kp);
@@ -627,12 +677,18 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.emit = emit;
     p.emit_scale = emit_scale;
     p.emit_tile_w = emit_tile_w;
+    p.cmask = cmask;
+    p.Hm = Hm;
+    p.Wm = Wm;
+    p.gh = gh;
+    p.gw = gh > 0 ? T / gh : 0;
+    PP_CHECK_ARG(epi != EPI_SIM || (cmask && ra && rb && emit && gh > 0 && gh * p.gw == T && Hm > 0 && Wm > 0), "similarity epilogue: bad arguments");
     p.fault = g_fault_dev;
     if (p.num_groups == 0) return PP_OK;
     // A = M-side operand (box of 128 rows), B = N-side operand (box of 256 / cluster rows); EPI_MATCH puts the template
     // bank on the M side and the compact query rows on the N side, EPI_EMIT the other way round
     CUtensorMap ta, tb;
-    const bool match = epi != EPI_EMIT;
+    const bool match = epi == EPI_MATCH || epi == EPI_MATCH_FAST;
     const void* m_op = match ? bank_prep : q_prep;
     const void* n_op = match ? q_prep : bank_prep;
     const uint64_t m_rows = match ? (uint64_t)n_banks * N * T : (uint64_t)B * T;
@@ -641,10 +697,12 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     if (int rc = make_tmap(&tb, n_op, n_rows, (uint64_t)Kp, BLOCK_N / cluster)) return rc;
     if (cluster == 1) {
         return epi == EPI_MATCH ? launch_gemm<1, EPI_MATCH>(ta, tb, p, st)
-               : epi == EPI_MATCH_FAST ? launch_gemm<1, EPI_MATCH_FAST>(ta, tb, p, st) : launch_gemm<1, EPI_EMIT>(ta, tb, p, st);
+               : epi == EPI_MATCH_FAST ? launch_gemm<1, EPI_MATCH_FAST>(ta, tb, p, st)
+               : epi == EPI_SIM ? launch_gemm<1, EPI_SIM>(ta, tb, p, st) : launch_gemm<1, EPI_EMIT>(ta, tb, p, st);
     }
     return epi == EPI_MATCH ? launch_gemm<2, EPI_MATCH>(ta, tb, p, st)
-           : epi == EPI_MATCH_FAST ? launch_gemm<2, EPI_MATCH_FAST>(ta, tb, p, st) : launch_gemm<2, EPI_EMIT>(ta, tb, p, st);
+           : epi == EPI_MATCH_FAST ? launch_gemm<2, EPI_MATCH_FAST>(ta, tb, p, st)
+           : epi == EPI_SIM ? launch_gemm<2, EPI_SIM>(ta, tb, p, st) : launch_gemm<2, EPI_EMIT>(ta, tb, p, st);
 }
 
 int fault_buffer(int** dev_ptr) {

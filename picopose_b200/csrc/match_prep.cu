@@ -51,10 +51,13 @@ struct QueryMaskArgs {
     unsigned long long clear_n16;   // its size in 16-byte units
 };
 
+// feats2 / g_split: groups g >= g_split read feats2[g - g_split] and are written as the BANK side of the split pairing --
+// one launch prepares both operands of a product (query rows first, template rows after them in the same output).
 template <int NPARTS, bool QM>
 __global__ void __launch_bounds__(PREP_THREADS)
 match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int nseg, int is_query,
-                     __nv_bfloat16* __restrict__ prep, float* __restrict__ rnorm, const QueryMaskArgs qm) {
+                     __nv_bfloat16* __restrict__ prep, float* __restrict__ rnorm, const QueryMaskArgs qm,
+                     const float* __restrict__ feats2 = nullptr, int g_split = 0x7fffffff) {
     // QM: row compaction -- patch p of detection g is written to row rank(p) = number of unmasked patches before
     // it (skipped if masked), so masked query patches never reach the tensor cores.  Every block recounts the
     // detection's mask itself (P values), so the prologue stays a single launch with no inter-block dependency.
@@ -137,7 +140,8 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
         }
     }
     const bool live = p0 + lane < P;
-    const float* x = feats + (size_t)g * C * P + (live ? p0 + lane : P - 1);
+    if (!QM && g >= g_split) is_query = 0;
+    const float* x = ((!QM && g >= g_split) ? feats2 + (size_t)(g - g_split) * C * P : feats + (size_t)g * C * P) + (live ? p0 + lane : P - 1);
     __nv_bfloat16* out_g = prep + (size_t)g * P * Kp;
     const int* seg_tab = (is_query ? SEG_Q : SEG_B) + (6 - nseg);
     const int nchunks = (C + PREP_CT - 1) / PREP_CT;
@@ -300,6 +304,26 @@ extern "C" int pp_match_prepare(const float* feats, int64_t G, int C, int P, int
 }
 
 namespace pp {
+// query features (G, C, P) and template features (G, C, P) -> prepared (2G, P, Kp) [queries | templates], rnorm (2G, P): one launch
+int prepare_pair_impl(const float* q_feats, const float* s_feats, int64_t G, int C, int P, int mode, void* prepared, float* rnorm,
+                      void* stream) {
+    if (int rc = require_sm100()) return rc;
+    PP_CHECK_ARG(q_feats && s_feats && prepared && rnorm, "prepare_pair: null pointer");
+    PP_CHECK_ARG(mode >= 0 && mode <= 2, "prepare_pair: unknown mode %d", mode);
+    PP_CHECK_ARG(C > 0 && C % 8 == 0 && P > 0 && G > 0 && 2 * G <= 65535, "prepare_pair: bad shape (G=%lld, C=%d, P=%d)", (long long)G, C, P);
+    const int Kp = pp_match_kp(C, mode);
+    const int nseg = mode_segments(mode), nparts = mode_parts(mode);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((P + PREP_PT - 1) / PREP_PT, (unsigned)(2 * G));
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(prepared);
+    const QueryMaskArgs none{};
+    if (nparts == 1) match_prepare_kernel<1, false><<<grid, PREP_THREADS, 0, st>>>(q_feats, C, P, Kp, nseg, 1, o, rnorm, none, s_feats, (int)G);
+    else if (nparts == 2) match_prepare_kernel<2, false><<<grid, PREP_THREADS, 0, st>>>(q_feats, C, P, Kp, nseg, 1, o, rnorm, none, s_feats, (int)G);
+    else match_prepare_kernel<3, false><<<grid, PREP_THREADS, 0, st>>>(q_feats, C, P, Kp, nseg, 1, o, rnorm, none, s_feats, (int)G);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
 QueryMeta split_query_meta(void* q_meta, int B, int T) {
     QueryMeta m;
     char* p = static_cast<char*>(q_meta);

@@ -1,5 +1,6 @@
-// Stage-1 reductions around the tensor-core contraction: mask resize, score finalisation, top-k,
-// and the stage-2 similarity-volume layout pass.  (Reference: utils/matching.py:16-17,38-39,54-68,23-25.)
+// Stage-1 reductions around the tensor-core contraction: score finalisation, top-k, pyramid pooling, and the host side
+// of the one-call entry points.  (Reference: utils/matching.py:54-68; the stage-2 volume of :22-25 is written by the
+// contraction's own epilogue.)
 #include "pp_common.cuh"
 
 #include <cstdlib>
@@ -10,22 +11,13 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
                    int B, int N, int T, int Kp, const float* mrow, const int* tv, const int* rowmap, const float* ra,
                    const float* rb,
                    unsigned long long* rowkey, unsigned long long* colkey, float* emit, float emit_scale, int cluster,
-                   cudaStream_t st, int emit_tile_w = 0, const int32_t* det_order = nullptr);
+                   cudaStream_t st, int emit_tile_w = 0, const int32_t* det_order = nullptr, const float* cmask = nullptr,
+                   int Hm = 0, int Wm = 0, int gh = 0);
+int prepare_pair_impl(const float* q_feats, const float* s_feats, int64_t G, int C, int P, int mode, void* prepared, float* rnorm,
+                      void* stream);
 
 int prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int C, int H, int W, int Hm, int Wm, int mode,
                        void* q_prep, float* q_rnorm, void* q_meta, void* clear, size_t clear_bytes, void* stream);
-
-// F.interpolate(mask[:,None], size=(H,W)) (nearest) flattened to (B, H*W): utils/matching.py:38-39 / :16-17
-__global__ void resize_mask_kernel(const float* __restrict__ mask, int B, int Hm, int Wm, int H, int W,
-                                   float* __restrict__ out) {
-    const int total = B * H * W;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int b = i / (H * W);
-        const int r = i - b * H * W;
-        const int y = r / W, x = r - y * W;
-        out[i] = mask[((size_t)b * Hm + nearest_src(y, Hm, H)) * Wm + nearest_src(x, Wm, W)];
-    }
-}
 
 // Stable sort of the detections by bank (B <= 1024, one block): order[i] = detection at position i.  Detections that share
 // an object bank become neighbours, and the contraction hands neighbours to one cluster so that they share the bank's
@@ -197,25 +189,6 @@ topk_merge_kernel(const double* __restrict__ pairs, int R, int B, int k_in, int 
             s_keys[pos] = 0ull;
         }
         __syncwarp();
-    }
-}
-
-// stage-2 volume: out[b, s, h, w] = max(0, sim[b, t = w*H + h, s] * mask_s)   (utils/matching.py:23-25)
-__global__ void similarity_layout_kernel(const float* __restrict__ sim, const float* __restrict__ mcol,
-                                         const float* __restrict__ ra, const float* __restrict__ rb, int B, int H,
-                                         int W, float* __restrict__ out) {
-    const int T = H * W;
-    const long long total = (long long)B * T * T;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(i / ((long long)T * T));
-        const int r = (int)(i - (long long)b * T * T);
-        const int s = r / T;
-        const int hw = r - s * T;
-        const int h = hw / W, w = hw - h * W;
-        const int t = w * H + h;
-        float v = sim[((size_t)b * T + t) * T + s] * ra[(size_t)b * T + t] * rb[(size_t)b * T + s] * mcol[(size_t)b * T + s];
-        out[i] = v < 0.f ? 0.f : v;
     }
 }
 
@@ -418,8 +391,10 @@ extern "C" int pp_topk_merge(const double* pairs, int R, int B, int k_in, int k,
 }
 
 extern "C" size_t pp_match_similarity_workspace(int B, int T) {
-    if (B < 0 || T < 0) return 0;
-    return pp::align_up((size_t)B * T * sizeof(float), 256) + pp::align_up((size_t)B * T * T * sizeof(float), 256);
+    // the similarity volume is written by the contraction's epilogue; nothing is staged any more (kept for the ABI)
+    (void)B;
+    (void)T;
+    return 0;
 }
 
 extern "C" int pp_match_similarity(const void* q_prep, const float* q_rnorm, const void* s_prep, const float* s_rnorm,
@@ -427,33 +402,50 @@ extern "C" int pp_match_similarity(const void* q_prep, const float* q_rnorm, con
                                    int Kp, int Hm, int Wm, float* out, void* workspace, size_t workspace_bytes,
                                    int cluster, void* stream) {
     using namespace pp;
+    (void)workspace;
+    (void)workspace_bytes;
     if (int rc = require_sm100()) return rc;
     if (B == 0) return PP_OK;
     PP_CHECK_ARG(q_prep && q_rnorm && s_prep && s_rnorm && src_mask && out, "pp_match_similarity: null pointer");
     PP_CHECK_ARG(H == W, "pp_match_similarity: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
     PP_CHECK_ARG(B >= 0 && H > 0 && Hm > 0 && Wm > 0, "pp_match_similarity: bad shape");
-    if (B == 0) return PP_OK;
     const int T = H * W;
-    const size_t need = pp_match_similarity_workspace(B, T);
+    // one "view" per detection: banks == detections, N = 1; norms, template mask, clamp and the (w h) layout in the epilogue
+    return run_match_gemm(3, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, q_rnorm, s_rnorm, nullptr, nullptr,
+                          out, 1.0f, cluster & ~PP_MATCH_FAST_KEYS, static_cast<cudaStream_t>(stream), 0, nullptr, src_mask, Hm, Wm, H);
+}
+
+// matching_features_similarity as the reference calls it (utils/matching.py:6-26, from model/picopose.py:81): fp32 features
+// in, TWO launches: one prologue for both operands, one contraction whose epilogue writes the finished volume.
+extern "C" size_t pp_match_similarity_dense_workspace(int B, int C, int H, int W, int mode) {
+    const int Kp = pp_match_kp(C, mode);
+    if (B < 0 || H <= 0 || W <= 0 || Kp <= 0) return 0;
+    const size_t T = (size_t)H * W;
+    return pp::align_up(2 * (size_t)B * T * Kp * 2, 256) + pp::align_up(2 * (size_t)B * T * 4, 256);
+}
+
+extern "C" int pp_match_similarity_dense(const float* src_feat, const float* tar_feat, const float* src_mask, int B, int C,
+                                         int H, int W, int Hm, int Wm, int mode, float* out, void* workspace,
+                                         size_t workspace_bytes, int cluster, void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (B == 0) return PP_OK;
+    PP_CHECK_ARG(src_feat && tar_feat && src_mask && out, "pp_match_similarity_dense: null pointer");
+    PP_CHECK_ARG(H == W, "pp_match_similarity_dense: the reference asserts a square patch grid (H == W), got %dx%d", H, W);
+    const int Kp = pp_match_kp(C, mode);
+    PP_CHECK_ARG(Kp > 0 && Hm > 0 && Wm > 0, "pp_match_similarity_dense: bad feature dim %d / mode %d / mask", C, mode);
+    const size_t need = pp_match_similarity_dense_workspace(B, C, H, W, mode);
     if (!workspace || workspace_bytes < need)
-        return fail(PP_ERR_WORKSPACE, "pp_match_similarity: workspace of %zu bytes needed, %zu given", need,
-                    workspace_bytes);
-    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_similarity: workspace must be 256-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+        return fail(PP_ERR_WORKSPACE, "pp_match_similarity_dense: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_match_similarity_dense: workspace must be 256-byte aligned");
+    const int T = H * W;
     char* ws = static_cast<char*>(workspace);
-    float* mcol = reinterpret_cast<float*>(ws);
-    float* sim = reinterpret_cast<float*>(ws + align_up((size_t)B * T * sizeof(float), 256));
-    resize_mask_kernel<<<(B * T + 255) / 256, 256, 0, st>>>(src_mask, B, Hm, Wm, H, W, mcol);
-    PP_LAUNCHED();
-    // one "view" per detection: banks == detections, N = 1
-    if (int rc = run_match_gemm(1, q_prep, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                nullptr, nullptr, sim, 1.0f, cluster, st))
-        return rc;
-    const long long total = (long long)B * T * T;
-    int grid = (int)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
-    similarity_layout_kernel<<<grid, 256, 0, st>>>(sim, mcol, q_rnorm, s_rnorm, B, H, W, out);
-    PP_LAUNCHED();
-    return PP_OK;
+    float* rn = reinterpret_cast<float*>(ws + align_up(2 * (size_t)B * T * Kp * 2, 256));
+    // rows [0, B): query (tar) patches, rows [B, 2B): template (src) patches
+    if (int rc = prepare_pair_impl(tar_feat, src_feat, B, C, T, mode, ws, rn, stream)) return rc;
+    const char* s_prep = ws + (size_t)B * T * Kp * 2;
+    return run_match_gemm(3, ws, s_prep, B, nullptr, B, 1, T, Kp, nullptr, nullptr, nullptr, rn, rn + (size_t)B * T, nullptr, nullptr,
+                          out, 1.0f, cluster & ~PP_MATCH_FAST_KEYS, static_cast<cudaStream_t>(stream), 0, nullptr, src_mask, Hm, Wm, H);
 }
 
 namespace pp {

@@ -385,17 +385,20 @@ def matching_features_similarity(src_feat, tar_feat, src_mask, tar_mask, *, mode
     B, Cc, H, W = src_feat.shape
     if H != W:
         raise AssertionError("matching_features_similarity expects a square patch grid (H == W)")
-    mode = default_mode() if mode is None else mode
-    q, q_rn = prepare_features(tar_feat, mode, is_query=True)
-    s, s_rn = prepare_features(src_feat, mode, is_query=False)
-    mask = _as_f32(src_mask)
+    mid = _mode_id(mode)
+    if tuple(tar_feat.shape) != (B, Cc, H, W):
+        raise ValueError("src_feat and tar_feat must have the same shape")
+    src, tar, mask = _as_f32(src_feat), _as_f32(tar_feat), _as_f32(src_mask)
     Hm, Wm = mask.shape[-2:]
     T = H * W
     out = torch.empty(B, T, H, W, dtype=torch.float32, device=src_feat.device)
-    ws = torch.empty(lib.pp_match_similarity_workspace(B, T), dtype=torch.uint8, device=src_feat.device)
-    with torch.cuda.device(src_feat.device):
-        _lib.check(lib.pp_match_similarity(_lib.ptr(q), _lib.ptr(q_rn), _lib.ptr(s), _lib.ptr(s_rn), _lib.ptr(mask),
-                                           B, H, W, q.shape[-1], Hm, Wm,
-                                           _lib.ptr(out), _lib.ptr(ws), ws.numel(), default_cluster(),
-                                           _lib.stream_of(src_feat)), "pp_match_similarity")
+    need = lib.pp_match_similarity_dense_workspace(B, Cc, H, W, mid)
+    if need == 0 and B > 0:
+        raise RuntimeError(f"picopose_b200: bad feature dim {Cc}")
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=src_feat.device)
+    with _on_device(src_feat.device):
+        # one prologue launch for both operands + one contraction whose epilogue writes the finished volume
+        _lib.check(lib.pp_match_similarity_dense(_lib.ptr(src), _lib.ptr(tar), _lib.ptr(mask), B, Cc, H, W, Hm, Wm, mid,
+                                                 _lib.ptr(out), _lib.ptr(ws), need, default_cluster(),
+                                                 _lib.stream_of(src_feat)), "pp_match_similarity_dense")
     return out

@@ -46,7 +46,8 @@ def test_pure_host_entry_points(lib):
     # two 64-bit keys per (b, n, t) + two per-detection int arrays; query bookkeeping = 3 words per patch + 2 per detection
     assert lib.pp_match_scores_workspace(1, 162, 1024) == 2 * 162 * 1024 * 8 + 2 * 256
     assert lib.pp_match_query_meta_bytes(2, 1024) == (3 * 2 * 1024 + 4) * 4
-    assert lib.pp_match_similarity_workspace(2, 256) == 2048 + 2 * 256 * 256 * 4
+    assert lib.pp_match_similarity_workspace(2, 256) == 0          # the volume is written by the contraction's epilogue
+    assert lib.pp_match_similarity_dense_workspace(2, 1024, 16, 16, 0) == 2 * 2 * 256 * 1024 * 2 + 2 * 2 * 256 * 4
     assert isinstance(lib.pp_launch_count(), int)
 
 

@@ -73,12 +73,16 @@ def test_corr_lookup_vs_oracle(B, H, L, r, sigma):
     (2, 16, 1, 2, 2.0), (1, 32, 2, 2, 3.0), (1, 64, 3, 2, 4.0), (2, 64, 1, 4, 4.0), (1, 64, 1, 5, 4.0), (1, 64, 1, 6, 4.0),
     (1, 64, 1, 7, 4.0), (1, 64, 1, 8, 4.0), (1, 64, 3, 4, 4.0), (1, 32, 2, 3, 30.0), (1, 64, 2, 1, 1.0), (1, 32, 1, 8, 6.0),
 ])
-def test_corr_lookup_tiled_layout_vs_oracle(B, H, L, r, sigma):
-    """The tiled volume layout (4 x 8 tiles = one 128-byte line each): a retiled copy of the oracle's pyramid gives the
+@pytest.mark.parametrize("kernel", ["banded", "tiles"])
+def test_corr_lookup_tiled_layout_vs_oracle(B, H, L, r, sigma, kernel, monkeypatch):
+    """Both kernels that read tiled volumes: the banded one (default) and the whole-tile fetch kernel (corr_lookup_tma.cu, opt-in).
+    The tiled volume layout (4 x 8 tiles = one 128-byte line each): a retiled copy of the oracle's pyramid gives the
     oracle's lookup; the round trip of the layout change is the identity; and the tiled and row-major kernels agree
     bit for bit (same taps, same staged footprint, only the global addresses differ)."""
     from picopose_b200.corr_lookup import CorrLookup, corr_lookup
     from picopose_b200.correlation import TiledPyramid, retile_volume
+    if kernel == "tiles":
+        monkeypatch.setenv("PICOPOSE_LOOKUP_KERNEL", "tiles")
     pyr, flow = synth.lookup_inputs(B, H, L, seed=17 + r, flow_sigma=sigma)
     ref = OL.corr_lookup(pyr, flow, r)
     pyr_d = [p.to(DEV) for p in pyr]
@@ -92,6 +96,36 @@ def test_corr_lookup_tiled_layout_vs_oracle(B, H, L, r, sigma):
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
     assert torch.equal(out, corr_lookup(pyr_d, flow.to(DEV), r))
     assert torch.equal(tp[0], pyr_d[0]) and len(tp) == L                 # other consumers see the reference layout
+
+
+@pytest.mark.parametrize("kernel", ["banded", "tiles"])
+@pytest.mark.parametrize("r", [2, 4, 8])
+def test_corr_lookup_tiled_adversarial_flows(r, kernel, monkeypatch):
+    """Flows that defeat the whole-tile kernel's packing budget and footprint bounds: every query of a row looks at the
+    SAME place with the worst tile alignment (all 32 lanes of a warp need their largest tile box at once -> some lanes
+    fall back to sampling from global memory), windows hanging over every border, huge and non-finite flows."""
+    from picopose_b200.corr_lookup import corr_lookup
+    from picopose_b200.correlation import TiledPyramid
+    if kernel == "tiles":
+        monkeypatch.setenv("PICOPOSE_LOOKUP_KERNEL", "tiles")
+    H = 64
+    pyr, _ = synth.lookup_inputs(2, H, 2, seed=5, flow_sigma=1.0)
+    xs = torch.arange(H, dtype=torch.float32).view(1, 1, H)
+    ys = torch.arange(H, dtype=torch.float32).view(1, H, 1)
+    flow = torch.zeros(2, 2, H, H)
+    flow[0, 0] = (7.0 + r + 0.5) - xs              # window origin x = 7 (mod 8): widest tile span, same for every query
+    flow[0, 1] = (3.0 + r + 0.25) - ys             # window origin y = 3 (mod 4)
+    flow[1, 0] = torch.where(xs < 32, -xs - 1.5, (H - 0.5) - xs)         # left / right border
+    flow[1, 1] = torch.where(ys < 32, -ys + 0.5, (H + 1.5) - ys)         # top / bottom border
+    flow[1, :, 5, 5] = float("inf")
+    flow[1, :, 6, 6] = -3e9
+    flow[1, 0, 7, 7] = float("nan")
+    ref = OL.corr_lookup(pyr, torch.nan_to_num(flow, nan=1e9, posinf=1e9, neginf=-1e9), r)
+    tp = TiledPyramid.from_volumes([p.to(DEV) for p in pyr])
+    out = corr_lookup(tp, flow.to(DEV), r)
+    _lib.check_device_faults()
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
+    assert torch.equal(out, corr_lookup([p.to(DEV) for p in pyr], flow.to(DEV), r))
 
 
 def test_tiled_pyramid_from_the_contraction():
@@ -527,6 +561,32 @@ def test_similarity_volume_golden(name, mode):
     _lib.check_device_faults()
     assert tuple(out.shape) == g["out"].shape
     np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=0, atol=MODE_TOL[mode])
+
+
+def test_similarity_volume_paths_and_sizes():
+    """The stage-2 volume through both entry points (fp32 features in two launches; prepared operands in one) and at
+    patch grids that span several contraction tiles (32 x 32: T = 1024) or ragged ones (12 x 12)."""
+    import ctypes as C
+    from picopose_b200.matching import matching_features_similarity, prepare_features
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(14)
+    for (B, Cc, H, mode, tol) in ((2, 384, 32, "bf16", 4e-3), (1, 64, 32, "fp32", 1e-5), (3, 40, 12, "fp32", 1e-5), (2, 1024, 16, "bf16x3", 2e-5)):
+        src = torch.randn(B, Cc, H, H, generator=gen)
+        tar = torch.randn(B, Cc, H, H, generator=gen)
+        sm = synth.bernoulli_mask(B, 224, 0.6, 3 + H)
+        ref = OM.similarity_volume(src, tar, sm)
+        out = matching_features_similarity(src.to(DEV), tar.to(DEV), sm.to(DEV), None, mode=mode)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=tol)
+        assert float(out.min()) >= 0.0
+        q, q_rn = prepare_features(tar.to(DEV), mode, is_query=True)
+        t, t_rn = prepare_features(src.to(DEV), mode, is_query=False)
+        out2 = torch.empty_like(out)
+        m = sm.to(DEV)
+        _lib.check(lib.pp_match_similarity(_lib.ptr(q), _lib.ptr(q_rn), _lib.ptr(t), _lib.ptr(t_rn), _lib.ptr(m), B, H, H, q.shape[-1],
+                                           224, 224, _lib.ptr(out2), None, 0, 0, torch.cuda.current_stream().cuda_stream),
+                   "pp_match_similarity")
+        assert torch.equal(out, out2)
+    _lib.check_device_faults()
 
 
 def test_similarity_volume_native_size():
