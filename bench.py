@@ -17,8 +17,13 @@ peer memory, and in the end-to-end loop every rank uploads its own detection and
 with copy-engine peer pushes (picopose_b200/sharded.py; NCCL all-gathers when peer mappings are unavailable).
 
 Extra keys beside the contract's: `roofline` (the tensor-core contraction, timed by its own CUDA events),
-`roofline_lookup` (N=1: the stage-3 lookup at the configs[3] shape against the HBM copy peak, outside the
-timed step), `warm_bank` (template bank prepared once), `cpu_baseline` (oracle port on the host cores).
+`roofline_lookup` (N=1: the stage-3 lookup at the configs[3] shape against the HBM copy peak, row-major and tiled volume
+layouts at r=4 and r=8 with ncu-measured DRAM traffic, plus the fused no-volume path; outside the timed step),
+`config2` / `config4` (every N: BASELINE configs[2] = 64 detections x 642 views against 8 resident banks, STRONG scaling,
+and configs[4] = 512 x 642 stage 1 + the stage-3 lookups of every detection, with the CPU port on a sample at N=1),
+`sharded_equals_single_gpu` (the N-rank result of detection 0 against the unsharded computation on rank 0),
+`warm_bank` (template bank prepared once), `cpu_baseline` (the full step on the host cores, nothing extrapolated).
+`--impl reference` runs that full step on the host cores as its own arm, with the same `config` object.
 """
 from __future__ import annotations
 
