@@ -89,12 +89,12 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
             const int Hl = p.vh[l], Wl = p.vw[l];
             const float inv = 1.0f / (float)(1 << l);  // exact: centroid / 2**l, utils/corr_lookup.py:125
             const float lx = __fmul_rn(cx, inv), ly = __fmul_rn(cy, inv);
-            int xo[D], yo[D];
+            int xo[D], yo[D], yraw[D];
             float xw[D], yw[D];
 #pragma unroll
             for (int a = 0; a < D; ++a) {
                 axis_tap(__fadd_rn(lx, (float)(a - R)), Wl, xo[a], xw[a]);
-                axis_tap(__fadd_rn(ly, (float)(a - R)), Hl, yo[a], yw[a]);
+                axis_tap_raw(__fadd_rn(ly, (float)(a - R)), Hl, yo[a], yw[a], yraw[a]);
             }
             const int xs = xo[0] & ~3;                        // two's complement: rounds towards -inf
             const int pieces = ((xo[D - 1] + 1 - xs) >> 2) + 1;  // 16-byte pieces per row some tap touches
@@ -106,8 +106,16 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
             for (int band = 0; band < NB; ++band) {
                 const int j0 = band * JB;
                 const int j1 = (j0 + JB < D) ? j0 + JB : D;  // compile-time after unrolling
-                const int yb = yo[j0];
-                const int rows = yo[j1 - 1] + 1 - yb + 1;
+                // Regular band: tap j0 + bb sits exactly bb rows below tap j0 (true for all but ~1e-5 of the taps, where the
+                // float round trip moves a floor).  Its rows are then staged from the UNCLAMPED origin -- rows outside
+                // the map are zero-filled, which is what the clamped taps read anyway -- so that tap bb always uses
+                // staged rows bb and bb + 1 and the blend below can walk the rows once.
+                bool regular = true;
+#pragma unroll
+                for (int bb = 1; bb < j1 - j0; ++bb) regular = regular && (yraw[j0 + bb] == yraw[j0] + bb);
+                const int yb = regular ? min(max(yraw[j0], -(JB + 1)), Hl) : yo[j0];
+                const int rows = regular ? (j1 - j0) + 1 : yo[j1 - 1] + 1 - yb + 1;
+                const bool warp_regular = __all_sync(0xffffffffu, regular || !live);
                 __syncwarp();  // previous band's readers are done with the staging area
                 const int packed = (yb + 8) | (pieces << 20) | (rows << 26);
 
@@ -142,8 +150,33 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                 cp_async_wait_all();
                 __syncwarp();
 
-                // ---- lane = query: gather + separable 4-tap blend ----
-                if (live) {
+                // ---- lane = query: gather + separable blend ----
+                if (live && warp_regular) {
+                    // rows once: h[rr][a] = lerp_x(row yb + rr) is shared by the two taps that touch row rr; tap bb blends
+                    // rows bb and bb + 1.  Same expressions as the general form below, so the results are bit-identical;
+                    // 2 shared loads per (row, a) instead of 4 per (tap, a), no per-sample address arithmetic.
+                    const float* win = stage + lane * QS - xs;
+                    const uint32_t obase = (uint32_t)(l * D * D) * (uint32_t)p.HW + (uint32_t)hw;
+                    float hp[D], hc[D], wx0[D];
+#pragma unroll
+                    for (int a = 0; a < D; ++a) {
+                        wx0[a] = __fsub_rn(1.0f, xw[a]);
+                        hp[a] = fmaf(win[xo[a] + 1], xw[a], win[xo[a]] * wx0[a]);
+                    }
+#pragma unroll
+                    for (int bb = 0; bb < JB; ++bb) {
+                        const int j = j0 + bb;
+                        if (j < j1) {
+                            const float wy1 = yw[j], wy0 = __fsub_rn(1.0f, wy1);
+#pragma unroll
+                            for (int a = 0; a < D; ++a) {
+                                hc[a] = fmaf(win[(bb + 1) * PITCH + xo[a] + 1], xw[a], win[(bb + 1) * PITCH + xo[a]] * wx0[a]);
+                                __stcs(out_b + (obase + (uint32_t)(a * D + j) * (uint32_t)p.HW), fmaf(hc[a], wy1, hp[a] * wy0));
+                                hp[a] = hc[a];
+                            }
+                        }
+                    }
+                } else if (live) {
                     const float* win = stage + lane * QS;
                     const uint32_t obase = (uint32_t)(l * D * D) * (uint32_t)p.HW + (uint32_t)hw;
 #pragma unroll

@@ -41,6 +41,20 @@ __device__ __forceinline__ void axis_tap(float p, int size, int& i0, float& w1) 
 }
 
 
+// Same, plus the floor BEFORE the clamp (limited to +-1e6, NaN -> a sentinel): lets a caller recognise the regular case
+// "tap j sits exactly j rows below tap 0" even when some taps were clamped at the border.
+__device__ __forceinline__ void axis_tap_raw(float p, int size, int& i0, float& w1, int& raw) {
+    float den = (float)(size > 1 ? size - 1 : 1);
+    float g = __fsub_rn(__fdiv_rn(__fmul_rn(p, 2.0f), den), 1.0f);
+    float i = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+    float f = floorf(i);
+    w1 = __fsub_rn(i, f);
+    raw = (f == f) ? (int)fminf(fmaxf(f, -1.0e6f), 1.0e6f) : -2000000;
+    f = fminf(fmaxf(f, -2.0f), (float)size);
+    i0 = (f == f) ? (int)f : -2;
+    if (!(w1 >= 0.0f && w1 <= 1.0f)) w1 = 0.0f;
+}
+
 // corr_lookup_tma.cu: tiled volumes fetched with bulk copies (radius 1..8); *handled = false leaves it to the banded kernel
 int launch_lookup_tma(const LookupParams& p, cudaStream_t st, bool* handled);
 

@@ -57,6 +57,7 @@ struct GemmParams {
     int num_k_blocks;
     int num_mt, num_nt;  // tiles along T (per 128*CL rows) and S (per 256 columns)
     uint32_t num_groups;  // ceil(B / chunk) * N * num_mt work groups
+    int tile_mode;        // 1: short launch, single TILES dealt round-robin (per-detection tile prefix in shared memory)
     int chunk;            // detections per group (>= 1): consecutive entries of det_order
     const int32_t* det_order;  // (B,) detections sorted by bank (null = identity): a chunk then shares its M-side tiles
     int n_banks;
@@ -85,7 +86,8 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int RB_BYTES = NUM_EPI_WARPS * EPI_COLS * 8;  // per epilogue warp: factor + patch index of its columns
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + 1024;  // + alignment slack
+    static constexpr int PREFIX_BYTES = (MAX_DETS_PER_LAUNCH + 1) * 4;  // tile mode: per-detection tile prefix
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + PREFIX_BYTES + 1024;  // + alignment slack
 };
 
 __device__ __noinline__ void report_fault(int* fault, int code, int a, int b) {
@@ -131,13 +133,44 @@ __device__ __forceinline__ int bank_of(const GemmParams& p, int b) {
     const int v = __ldg(p.bank_of_det + b);
     return v < 0 ? 0 : (v >= p.n_banks ? p.n_banks - 1 : v);
 }
-// group -> (first detection position, n, mt)
-__device__ __forceinline__ void decode_group(uint32_t g, const GemmParams& p, int& pos0, int& n, int& mt) {
+// Work item of a cluster: detections [pos0, pos1) x column tiles [nt0, nt0 + nts) of (view n, patch tile mt).
+//  * group mode (long launches): all column tiles of up to `chunk` detections (nts < 0 = "all of the detection's");
+//  * tile mode (short launches, e.g. the 1 x 162 and 8 x 21 shapes of BASELINE configs[1]): ONE tile -- a launch of ~30
+//    tile-times per cluster cannot afford groups of 3-6 tiles (28 vs 30 tile-times on the 8 x 21 shape, measured +6.6 %),
+//    and it is over before neighbouring clusters can drift apart, so they still share the template tile in L2.
+struct WorkItem {
+    int pos0, pos1, n, mt, nt0, nts;
+};
+__device__ __forceinline__ WorkItem decode_work(uint32_t g, const GemmParams& p, const uint32_t* prefix) {
+    WorkItem w;
+    if (p.tile_mode) {
+        // flat tile index -> detection by binary search in the per-detection tile prefix, then (n, mt, nt)
+        int lo = 0, hi = p.B;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (prefix[mid] <= g) lo = mid; else hi = mid;
+        }
+        const uint32_t nct = col_tiles(live_rows(p, lo));
+        const uint32_t local = g - prefix[lo];
+        const uint32_t r = local / nct;
+        w.nt0 = (int)(local - r * nct);
+        w.nts = 1;
+        const uint32_t n = r / (uint32_t)p.num_mt;
+        w.mt = (int)(r - n * (uint32_t)p.num_mt);
+        w.n = (int)n;
+        w.pos0 = lo;
+        w.pos1 = lo + 1;
+        return w;
+    }
     const uint32_t r = g / (uint32_t)p.num_mt;
-    mt = (int)(g - r * (uint32_t)p.num_mt);
+    w.mt = (int)(g - r * (uint32_t)p.num_mt);
     const uint32_t c = r / (uint32_t)p.N;
-    n = (int)(r - c * (uint32_t)p.N);
-    pos0 = (int)c * p.chunk;
+    w.n = (int)(r - c * (uint32_t)p.N);
+    w.pos0 = (int)c * p.chunk;
+    w.pos1 = min(w.pos0 + p.chunk, p.B);
+    w.nt0 = 0;
+    w.nts = -1;
+    return w;
 }
 // detection at position `pos` of the (bank-sorted) order: its tile shape
 template <bool MATCH>
@@ -179,6 +212,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + NUM_ACC + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
     float* rb_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
+    uint32_t* tile_prefix = reinterpret_cast<uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::RB_BYTES);
     constexpr bool MATCH = EPI == EPI_MATCH || EPI == EPI_MATCH_FAST;  // template patches on the M side, compact query rows on the N side
     constexpr bool FAST = EPI == EPI_MATCH_FAST;
 
@@ -207,7 +241,25 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::fence_barrier_init();
     } else if (warp == 2) {
         ptx::tmem_alloc<CL>(ptx::smem_u32((const void*)tmem_slot), 512);
-    } else if (warp == 3 && MATCH && blockIdx.x == 0 && p.bank_of_det) {
+    } else if (warp == 3 && MATCH && p.tile_mode) {
+        // inclusive scan of the per-detection tile counts (B <= MAX_DETS_PER_LAUNCH), 32 detections per step
+        uint32_t run = 0;
+        if (lane == 0) tile_prefix[0] = 0;
+        for (int b0 = 0; b0 < p.B; b0 += 32) {
+            const int b = b0 + lane;
+            uint32_t cnt = 0;
+            if (b < p.B) cnt = col_tiles(live_rows(p, b)) * (uint32_t)(p.N * p.num_mt);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            if (b < p.B) tile_prefix[b + 1] = run + inc;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    if (warp == 3 && MATCH && blockIdx.x == 0 && p.bank_of_det) {
         // range check of the caller's bank indices (the loads clamp): reported through the fault record, not trapped
         for (int b = lane; b < p.B; b += 32) {
             const int v = __ldg(p.bank_of_det + b);
@@ -225,7 +277,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (CL > 1) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t num_groups = p.num_groups;
+    const uint32_t num_groups = (MATCH && p.tile_mode) ? tile_prefix[p.B] : p.num_groups;
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA) =====================
@@ -234,14 +286,14 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         int stage = 0;
         uint32_t phase = 0;
         for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
-         int pos0, gn, gmt;
-         decode_group(grp, p, pos0, gn, gmt);
-         for (int pos = pos0; pos < min(pos0 + p.chunk, p.B); ++pos) {
-          TileCoord tc = det_tiles<MATCH>(pos, gn, gmt, p);
+         const WorkItem wi = decode_work(grp, p, tile_prefix);
+         for (int pos = wi.pos0; pos < wi.pos1; ++pos) {
+          TileCoord tc = det_tiles<MATCH>(pos, wi.n, wi.mt, p);
           const int bank = bank_of(p, tc.b);
           const int q_row0 = tc.b * p.T;                                       // query operand: rows of detection b
           const int t_row0 = (int)(((long long)bank * p.N + tc.n) * p.T);      // bank operand: rows of view n
-          for (tc.nt = 0; tc.nt < tc.nct; ++tc.nt) {
+          const int nt_end = wi.nts < 0 ? tc.nct : wi.nt0 + wi.nts;
+          for (tc.nt = wi.nt0; tc.nt < nt_end; ++tc.nt) {
             // A = M-side operand (128 rows per CTA), B = N-side operand (each CTA of a pair holds half of the columns;
             // the box is always B_ROWS rows, the MMA reads the first ncols / CL of them)
             const int a_row = (MATCH ? t_row0 : q_row0) + tc.mt * (BLOCK_M * CL) + (int)cta_rank * BLOCK_M;
@@ -275,12 +327,12 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t phase = 0;
         uint32_t iter = 0;
         for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
-         int pos0, gn, gmt;
-         decode_group(grp, p, pos0, gn, gmt);
-         for (int pos = pos0; pos < min(pos0 + p.chunk, p.B); ++pos) {
-          const TileCoord gc = det_tiles<MATCH>(pos, gn, gmt, p);
+         const WorkItem wi = decode_work(grp, p, tile_prefix);
+         for (int pos = wi.pos0; pos < wi.pos1; ++pos) {
+          const TileCoord gc = det_tiles<MATCH>(pos, wi.n, wi.mt, p);
           const uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, gc.ncols);
-          for (int nt = 0; nt < gc.nct; ++nt, ++iter) {
+          const int nt_end = wi.nts < 0 ? gc.nct : wi.nt0 + wi.nts;
+          for (int nt = wi.nt0; nt < nt_end; ++nt, ++iter) {
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             mbar_wait(tempty_bar(as), aphase ^ 1u, p.fault, 2, as);
@@ -314,15 +366,15 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int hh = e >> 2;    // first 32-column chunk of the tile this warp reads (then hh + 4)
         uint32_t iter = 0;
         for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
-         int pos0, gn, gmt;
-         decode_group(grp, p, pos0, gn, gmt);
-         for (int pos = pos0; pos < min(pos0 + p.chunk, p.B); ++pos) {
-          TileCoord tc = det_tiles<MATCH>(pos, gn, gmt, p);
+         const WorkItem wi = decode_work(grp, p, tile_prefix);
+         for (int pos = wi.pos0; pos < wi.pos1; ++pos) {
+          TileCoord tc = det_tiles<MATCH>(pos, wi.n, wi.mt, p);
+          const int nt_end = wi.nts < 0 ? tc.nct : wi.nt0 + wi.nts;
           // column maxima (over the query rows, lane-local) run across all column tiles of the group: one atomic per
           // (template patch, group) instead of one per tile
           float best = -INFINITY;
           int best_t = 0;
-          for (tc.nt = 0; tc.nt < tc.nct; ++tc.nt, ++iter) {
+          for (tc.nt = wi.nt0; tc.nt < nt_end; ++tc.nt, ++iter) {
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             const int T = p.T;
@@ -441,7 +493,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             atomicMax(p.rowkey + bn * T + tp_s[i * 32 + lane], pack_key(val + 0.0f, (uint32_t)(warp_row0 + win_lane)));
                     }
                 }
-                if (tc.nt == tc.nct - 1 && s_ok && best > -INFINITY)
+                if (tc.nt == nt_end - 1 && s_ok && best > -INFINITY)
                     atomicMax(p.colkey + bn * T + s_row, pack_key(best + 0.0f, (uint32_t)best_t));
             } else if (EPI == EPI_SIM) {
                 // lane = query patch t, columns = template patches s: sim = acc * ra[t] * rb[s], times the template mask,
@@ -653,16 +705,21 @@ int run_match_gemm(int epi, const void* q_prep, const void* bank_prep, int64_t n
     p.num_k_blocks = Kp / BLOCK_K;
     p.num_mt = (T + BLOCK_M * cluster - 1) / (BLOCK_M * cluster);
     p.num_nt = (T + BLOCK_N - 1) / BLOCK_N;
-    // detections per group: as many as share M-side tiles usefully (8) while leaving >= 4 groups per cluster
+    // short launches deal single tiles (see decode_work): fewer than 64 tile-times per cluster on the dense upper bound
     const long long per_det = (long long)N * p.num_mt;
+    const bool match_epi = epi == EPI_MATCH || epi == EPI_MATCH_FAST;
+    p.tile_mode = match_epi && B <= MAX_DETS_PER_LAUNCH &&
+                  (long long)B * per_det * p.num_nt < 64LL * (sm_count() / cluster);
+    // detections per group: as many as share M-side tiles usefully (8) while leaving >= 4 groups per cluster
     int chunk = 1;
-    if (det_order && bank_of_det) {
+    if (det_order && bank_of_det && !p.tile_mode) {
         const long long want = (long long)B * per_det / (4LL * (sm_count() / cluster));
         chunk = (int)(want < 1 ? 1 : (want > 8 ? 8 : want));
     }
     p.chunk = chunk;
     p.det_order = chunk > 1 ? det_order : nullptr;
-    const long long groups_ll = (long long)((B + chunk - 1) / chunk) * per_det;
+    // (tile mode: the dense upper bound of the tile count sizes the grid; the kernel takes the exact count from its prefix table)
+    const long long groups_ll = p.tile_mode ? (long long)B * per_det * p.num_nt : (long long)((B + chunk - 1) / chunk) * per_det;
     PP_CHECK_ARG(groups_ll < (1LL << 31), "too many tile groups in one launch (%lld); split the detection batch", groups_ll);
     p.num_groups = (uint32_t)groups_ll;
     p.n_banks = (int)n_banks;

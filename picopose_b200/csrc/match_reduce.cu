@@ -558,7 +558,7 @@ extern "C" int pp_match_templates(const float* tar_feat, const float* tar_mask, 
                                     pp_match_scores_workspace(B, N, T), stream))
         return rc;
     const bool rank_it = k > 0 && out_score && out_idx;
-    if (mode == PP_MODE_BF16) cluster |= PP_MATCH_FAST_KEYS;
+    if (mode == PP_MODE_BF16 && !getenv("PICOPOSE_B200_EXACT_KEYS")) cluster |= PP_MATCH_FAST_KEYS;
     return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
                              n_banks, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
                              rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
@@ -626,7 +626,7 @@ extern "C" int pp_match_templates_dense(const float* src_feats, int64_t G, const
     PP_CUDA(e1);
     PP_CUDA(e2);
     const bool rank_it = k > 0 && out_score && out_idx;
-    if (mode == PP_MODE_BF16) cluster |= PP_MATCH_FAST_KEYS;
+    if (mode == PP_MODE_BF16 && !getenv("PICOPOSE_B200_EXACT_KEYS")) cluster |= PP_MATCH_FAST_KEYS;
     return match_scores_impl(ws + w.q_prep, reinterpret_cast<float*>(ws + w.q_rnorm), ws + w.q_meta, bank_prep, bank_rnorm,
                              G, bank_of_det, B, N, H, W, Kp, sim_avg, nullptr, nullptr, nullptr, nullptr,
                              rank_it ? k : 0, out_score, out_idx, ws + w.keys, pp_match_scores_workspace(B, N, T), cluster,
