@@ -259,20 +259,6 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
-    if (warp == 3 && MATCH && blockIdx.x == 0 && p.bank_of_det) {
-        // range check of the caller's bank indices (the loads clamp): reported through the fault record, not trapped
-        for (int b = lane; b < p.B; b += 32) {
-            const int v = __ldg(p.bank_of_det + b);
-            if ((v < 0 || v >= p.n_banks) && p.fault) {
-                p.fault[1] = b;
-                p.fault[2] = v;
-                p.fault[3] = p.n_banks;
-                p.fault[4] = 0;
-                __threadfence_system();
-                p.fault[0] = 6;
-            }
-        }
-    }
     ptx::tc_fence_before();
     if (CL > 1) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();

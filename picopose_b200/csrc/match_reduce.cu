@@ -22,9 +22,24 @@ int prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int 
 // Stable sort of the detections by bank (B <= 1024, one block): order[i] = detection at position i.  Detections that share
 // an object bank become neighbours, and the contraction hands neighbours to one cluster so that they share the bank's
 // tiles in L2 instead of each streaming the bank from HBM.
-__global__ void __launch_bounds__(1024) det_order_kernel(const int32_t* __restrict__ bank_of_det, int B, int32_t* __restrict__ order) {
+// The same kernel range-checks the caller's bank indices (the contraction clamps them in its loads): an index outside
+// [0, n_banks) is reported through the fault record (code 6), never trapped.
+__global__ void __launch_bounds__(1024) det_order_kernel(const int32_t* __restrict__ bank_of_det, int B, int n_banks,
+                                                         int32_t* __restrict__ order, int* __restrict__ fault) {
     __shared__ int s_bank[1024];
     const int i = threadIdx.x;
+    for (int b = i; b < B; b += blockDim.x) {
+        const int v = bank_of_det[b];
+        if ((v < 0 || v >= n_banks) && fault) {
+            fault[1] = b;
+            fault[2] = v;
+            fault[3] = n_banks;
+            fault[4] = 0;
+            __threadfence_system();
+            fault[0] = 6;
+        }
+    }
+    if (!order) return;
     if (i < B) s_bank[i] = bank_of_det[i];
     __syncthreads();
     if (i < B) {
@@ -310,8 +325,10 @@ static int match_scores_impl(const void* q_prep, const float* q_rnorm, const voi
     // e.g. on a forked stream beside the bank prologue, says so)
     if (!keys_cleared) PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys + align_up((size_t)B * sizeof(int), 256), st));
     const bool sort_dets = bank_of_det != nullptr && B > 1 && B <= 1024;
-    if (sort_dets) {
-        det_order_kernel<<<1, 1024, 0, st>>>(bank_of_det, B, order);
+    if (bank_of_det) {   // range check of the indices (always) + bank-sorted order (when it can pay off)
+        int* fault = nullptr;
+        if (int rc = fault_buffer(&fault)) return rc;
+        det_order_kernel<<<1, 1024, 0, st>>>(bank_of_det, B, (int)n_banks, sort_dets ? order : nullptr, fault);
         PP_LAUNCHED();
     }
     if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, qm.mrow, qm.tv, qm.rowmap, q_rnorm,
