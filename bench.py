@@ -252,7 +252,8 @@ def lookup_rooflines(dev, batch=256, size=64, radii=(4, 8), iters=20):
     tiled = TiledPyramid.from_volumes(pyr)
     flow = 4.0 * torch.randn(batch, 2, size, size, device=dev, generator=g)
     traffic = measured_traffic()
-    jb = {1: 3, 2: 5, 3: 4, 4: 5, 5: 4, 6: 5, 7: 5, 8: 3}
+    jb = {"rowmajor": {1: 3, 2: 5, 3: 7, 4: 5, 5: 6, 6: 5, 7: 5, 8: 3},      # band heights of csrc/corr_lookup.cu
+          "tiled": {1: 3, 2: 5, 3: 7, 4: 6, 5: 6, 6: 7, 7: 8, 8: 6}}
     blocks = {}
     for r in radii:
         D = 2 * r + 1
@@ -260,7 +261,7 @@ def lookup_rooflines(dev, batch=256, size=64, radii=(4, 8), iters=20):
         for name, vol, flag in (("rowmajor", pyr, 0), ("tiled", tiled, 1)):
             ms, ms_min = _timed_ms(lambda: corr_lookup(vol, flow, r), iters)
             achieved = Q * per_q / (ms * 1e-3) / 1e9
-            kname = LOOKUP_KERNEL.get((name, r)) or "corr_lookup_banded_kernel<%d,%d,%d>" % (r, jb[r], flag)
+            kname = LOOKUP_KERNEL.get((name, r)) or "corr_lookup_banded_kernel<%d,%d,%d>" % (r, jb[name][r], flag)
             tr = traffic.get(kname)
             blocks["%s_r%d" % (name, r)] = {
                 "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                 const int rows = regular ? (j1 - j0) + 1 : yo[j1 - 1] + 1 - yb + 1;
                 const bool warp_regular = __all_sync(0xffffffffu, regular || !live);
                 __syncwarp();  // previous band's readers are done with the staging area
-                const int packed = (yb + 8) | (pieces << 20) | (rows << 26);
+                const int packed = (yb + 16) | (pieces << 20) | (rows << 26);  // yb >= -(JB + 1) >= -10
 
                 // ---- cooperative staging: for query ql (warp-uniform) lane -> (row, piece) of its footprint, so
                 // consecutive lanes fetch consecutive 16-byte pieces of a row; the footprint origin of query ql
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                     for (int ql = 0; ql < 32; ++ql) {
                         const int qx = __shfl_sync(0xffffffffu, xs, ql);
                         const int qp = __shfl_sync(0xffffffffu, packed, ql);
-                        const int y = (qp & 0xFFFFF) - 8 + row;
+                        const int y = (qp & 0xFFFFF) - 16 + row;
                         const int x = qx + 4 * v;
                         const bool need = slot_ok && row < (qp >> 26) && v < ((qp >> 20) & 63);
                         const bool inb = (unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl && ql < nq;
@@ -460,16 +460,19 @@ static int corr_lookup_impl(const void* const* pyr_ptrs, const int* pyr_h, const
         }
     }
     if (all_vec) {
-        // band height per radius: keeps ~12-25 KB of staging per warp so 8-16 warps share an SM
+        // Band height per radius and layout, from the sweeps in profiles/r2u_lookup_sweep*.json.  Row-major volumes want
+        // many warps per SM (small bands); tiled volumes want few bands (a band boundary cuts through tiles, whose lines
+        // are then requested twice) as long as 8-12 warps still fit.
+        const bool t = p.tiled != 0;
         switch (radius) {
             case 1: return launch_banded<1, 3>(p, st);
             case 2: return launch_banded<2, 5>(p, st);
-            case 3: return launch_banded<3, 4>(p, st);
-            case 4: return launch_banded<4, 5>(p, st);
-            case 5: return launch_banded<5, 4>(p, st);
-            case 6: return launch_banded<6, 5>(p, st);
-            case 7: return launch_banded<7, 5>(p, st);
-            case 8: return launch_banded<8, 3>(p, st);
+            case 3: return launch_banded<3, 7>(p, st);
+            case 4: return t ? launch_banded<4, 6>(p, st) : launch_banded<4, 5>(p, st);
+            case 5: return launch_banded<5, 6>(p, st);
+            case 6: return t ? launch_banded<6, 7>(p, st) : launch_banded<6, 5>(p, st);
+            case 7: return t ? launch_banded<7, 8>(p, st) : launch_banded<7, 5>(p, st);
+            case 8: return t ? launch_banded<8, 6>(p, st) : launch_banded<8, 3>(p, st);
             default: break;
         }
     }
