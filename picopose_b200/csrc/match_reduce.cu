@@ -22,24 +22,9 @@ int prepare_query_impl(const float* tar_feat, const float* tar_mask, int B, int 
 // Stable sort of the detections by bank (B <= 1024, one block): order[i] = detection at position i.  Detections that share
 // an object bank become neighbours, and the contraction hands neighbours to one cluster so that they share the bank's
 // tiles in L2 instead of each streaming the bank from HBM.
-// The same kernel range-checks the caller's bank indices (the contraction clamps them in its loads): an index outside
-// [0, n_banks) is reported through the fault record (code 6), never trapped.
-__global__ void __launch_bounds__(1024) det_order_kernel(const int32_t* __restrict__ bank_of_det, int B, int n_banks,
-                                                         int32_t* __restrict__ order, int* __restrict__ fault) {
+__global__ void __launch_bounds__(1024) det_order_kernel(const int32_t* __restrict__ bank_of_det, int B, int32_t* __restrict__ order) {
     __shared__ int s_bank[1024];
     const int i = threadIdx.x;
-    for (int b = i; b < B; b += blockDim.x) {
-        const int v = bank_of_det[b];
-        if ((v < 0 || v >= n_banks) && fault) {
-            fault[1] = b;
-            fault[2] = v;
-            fault[3] = n_banks;
-            fault[4] = 0;
-            __threadfence_system();
-            fault[0] = 6;
-        }
-    }
-    if (!order) return;
     if (i < B) s_bank[i] = bank_of_det[i];
     __syncthreads();
     if (i < B) {
@@ -58,9 +43,25 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
                        const int* __restrict__ fm, int N, int T, float inv_hh, float* __restrict__ sim_avg,
                        float* __restrict__ score_t2s, int32_t* __restrict__ idx_t2s, int32_t* __restrict__ idx_s2t,
                        uint8_t* __restrict__ mutual, int k, int* __restrict__ done, float* __restrict__ topk_score,
-                       long long* __restrict__ topk_idx) {
+                       long long* __restrict__ topk_idx, const int32_t* __restrict__ bank_of_det, int B, int n_banks,
+                       int* __restrict__ fault) {
     const size_t bn = blockIdx.x;
     const int b = (int)(bn / N);
+    if (bn == 0 && bank_of_det) {
+        // range check of the caller's bank indices (the contraction clamps them in its loads): an index outside
+        // [0, n_banks) is reported through the fault record (code 6), never trapped
+        for (int i = threadIdx.x; i < B; i += blockDim.x) {
+            const int v = bank_of_det[i];
+            if ((v < 0 || v >= n_banks) && fault) {
+                fault[1] = i;
+                fault[2] = v;
+                fault[3] = n_banks;
+                fault[4] = 0;
+                __threadfence_system();
+                fault[0] = 6;
+            }
+        }
+    }
     // masked query rows never entered the contraction; in the reference they are rows of zeros that take part in
     // every column max (utils/matching.py:48,51): value 0 at the first masked patch wins ties by index
     const int fmb = fm[b];
@@ -324,13 +325,17 @@ static int match_scores_impl(const void* q_prep, const float* q_rnorm, const voi
     // the key arrays and the per-detection counters start at zero (a caller that has already cleared the scratch,
     // e.g. on a forked stream beside the bank prologue, says so)
     if (!keys_cleared) PP_CUDA(cudaMemsetAsync(rowkey, 0, 2 * keys + align_up((size_t)B * sizeof(int), 256), st));
-    const bool sort_dets = bank_of_det != nullptr && B > 1 && B <= 1024;
-    if (bank_of_det) {   // range check of the indices (always) + bank-sorted order (when it can pay off)
-        int* fault = nullptr;
-        if (int rc = fault_buffer(&fault)) return rc;
-        det_order_kernel<<<1, 1024, 0, st>>>(bank_of_det, B, (int)n_banks, sort_dets ? order : nullptr, fault);
+    // bank-sorted detection order: only for launches long enough to run in group mode (run_match_gemm's rule), where
+    // detections of one bank share its tiles; short launches deal single tiles in the caller's order
+    const long long tiles_bound = (long long)B * N * ((T + 255) / 256) * ((T + 255) / 256);
+    const bool sort_dets = bank_of_det != nullptr && B > 1 && B <= 1024 && tiles_bound >= 64LL * (sm_count() / 2);
+    if (sort_dets) {
+        det_order_kernel<<<1, 1024, 0, st>>>(bank_of_det, B, order);
         PP_LAUNCHED();
     }
+    int* fault = nullptr;
+    if (bank_of_det)
+        if (int rc = fault_buffer(&fault)) return rc;
     if (int rc = run_match_gemm(0, q_prep, bank_prep, n_banks, bank_of_det, B, N, T, Kp, qm.mrow, qm.tv, qm.rowmap, q_rnorm,
                                 bank_rnorm, rowkey, colkey, nullptr, 1.0f, cluster, st, 0, sort_dets ? order : nullptr))
         return rc;
@@ -343,7 +348,7 @@ static int match_scores_impl(const void* q_prep, const float* q_rnorm, const voi
     }
     finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, smem, st>>>(
         rowkey, colkey, qm.mrow, q_rnorm, qm.rank, qm.fm, N, T, 1.0f / (float)(H * H), sim_avg, score_t2s, idx_t2s, idx_s2t,
-        mutual_nn, k, done, topk_score, reinterpret_cast<long long*>(topk_idx));
+        mutual_nn, k, done, topk_score, reinterpret_cast<long long*>(topk_idx), bank_of_det, B, (int)n_banks, fault);
     PP_LAUNCHED();
     return PP_OK;
 }
