@@ -96,6 +96,16 @@ PP_API int pp_bilinear_sample(const float* feat, const float* grid, int N, int C
                        int Ho, int Wo, int grid_chw, int align_corners, int scale,
                        float* out, void* stream);
 
+/* The remaining argument combinations of bilinear_sample / CorrLookup (utils/corr_lookup.py:29-65,88-98 hand `mode` and
+ * `padding_mode` straight to F.grid_sample): nearest and bicubic interpolation, border and reflection padding, after
+ * ATen's GridSampler rules.  PicoPose itself only uses bilinear + zeros (the tuned kernels above); this is the
+ * compatibility path.  Same tensors as pp_bilinear_sample; (PP_SAMPLE_BILINEAR, PP_PAD_ZEROS) forwards to it. */
+enum pp_sample_mode { PP_SAMPLE_BILINEAR = 0, PP_SAMPLE_NEAREST = 1, PP_SAMPLE_BICUBIC = 2 };
+enum pp_pad_mode { PP_PAD_ZEROS = 0, PP_PAD_BORDER = 1, PP_PAD_REFLECTION = 2 };
+PP_API int pp_grid_sample(const float* feat, const float* grid, int N, int C, int Hf, int Wf,
+                   int Ho, int Wo, int grid_chw, int align_corners, int scale, int mode, int padding_mode,
+                   float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage 1 -- query-vs-template matching.
  *

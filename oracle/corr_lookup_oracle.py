@@ -7,6 +7,8 @@ reference's ``utils/corr_lookup.py``:
 * ``bilinear_sample``   <- utils/corr_lookup.py:29-65 (bilinear / zeros padding only)
 * ``corr_lookup``       <- CorrLookup.forward, utils/corr_lookup.py:100-134
 * ``correlation_pyramid`` <- model/stage3/raft_decoder.py:30-53
+* ``grid_sample`` / ``corr_lookup_general`` <- the same two functions for the other interpolation / padding modes the
+  reference hands through to F.grid_sample (ATen GridSampler rules written out)
 
 and ``corr_lookup_loops`` (numpy scalar loops, tiny shapes).
 
@@ -69,6 +71,103 @@ def bilinear_sample(feat, grid, align_corners=False, scale=True):
     out = tap(x0, y0, wx0 * wy0) + tap(x0 + 1, y0, wx1 * wy0) \
         + tap(x0, y0 + 1, wx0 * wy1) + tap(x0 + 1, y0 + 1, wx1 * wy1)
     return out
+
+
+# ---- the other argument combinations (utils/corr_lookup.py:29-65 hands mode / padding_mode to F.grid_sample) ----------
+# ATen GridSampler rules written out: unnormalise -> padding transform (border: clip; reflection: reflect then clip) ->
+# taps.  Bicubic pads every one of its 4 x 4 taps separately and uses the A = -0.75 convolution coefficients; nearest
+# rounds half to even.
+
+def _reflect(c: torch.Tensor, twice_low: int, twice_high: int) -> torch.Tensor:
+    if twice_low == twice_high:
+        return torch.zeros_like(c)
+    mn, span = twice_low / 2.0, (twice_high - twice_low) / 2.0
+    c = (c - mn).abs()
+    extra = torch.fmod(c, span)
+    flips = torch.floor(c / span)
+    return torch.where(flips % 2 == 0, extra + mn, span - extra + mn)
+
+
+def _pad_coord(c: torch.Tensor, size: int, padding_mode: str, align_corners: bool) -> torch.Tensor:
+    if padding_mode == "border":
+        return c.clamp(0, size - 1)
+    if padding_mode == "reflection":
+        c = _reflect(c, 0, 2 * (size - 1)) if align_corners else _reflect(c, -1, 2 * size - 1)
+        return c.clamp(0, size - 1)
+    return c
+
+
+def _fetch(feat: torch.Tensor, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """feat (N,C,Hf,Wf); x, y (N,Ho,Wo) float pixel indices (already integral) -> (N,C,Ho,Wo), 0 outside."""
+    N, C, Hf, Wf = feat.shape
+    ok = (x >= 0) & (x <= Wf - 1) & (y >= 0) & (y <= Hf - 1)
+    xi = x.clamp(0, Wf - 1).long()
+    yi = y.clamp(0, Hf - 1).long()
+    lin = (yi * Wf + xi).view(N, 1, -1).expand(N, C, -1)
+    v = torch.gather(feat.reshape(N, C, Hf * Wf), 2, lin).view(N, C, *x.shape[1:])
+    return v * ok.unsqueeze(1)
+
+
+def _cubic_weights(t: torch.Tensor):
+    A = -0.75
+    def c1(x): return ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0
+    def c2(x): return ((A * x - 5.0 * A) * x + 8.0 * A) * x - 4.0 * A
+    return [c2(t + 1.0), c1(t), c1(1.0 - t), c2(2.0 - t)]
+
+
+def grid_sample(feat, grid, mode="bilinear", padding_mode="zeros", align_corners=False, scale=True):
+    """bilinear_sample with every mode / padding_mode F.grid_sample has (finite coordinates)."""
+    if mode == "bilinear" and padding_mode == "zeros":
+        return bilinear_sample(feat, grid, align_corners, scale)
+    feat = feat.float()
+    N, C, Hf, Wf = feat.shape
+    if grid.shape[-1] != 2:
+        grid = grid.permute(0, 2, 3, 1)
+    gx, gy = grid[..., 0].float(), grid[..., 1].float()
+    if scale:
+        gx, gy = _normalise(gx, Wf), _normalise(gy, Hf)
+    ix, iy = _unnormalise(gx, Wf, align_corners), _unnormalise(gy, Hf, align_corners)
+    if mode == "nearest":
+        x = torch.round(_pad_coord(ix, Wf, padding_mode, align_corners))    # torch.round: half to even, as nearbyint
+        y = torch.round(_pad_coord(iy, Hf, padding_mode, align_corners))
+        return _fetch(feat, x, y)
+    if mode == "bicubic":
+        fx, fy = torch.floor(ix), torch.floor(iy)
+        wx, wy = _cubic_weights(ix - fx), _cubic_weights(iy - fy)
+        out = 0.0
+        for j in range(4):
+            y = torch.floor(_pad_coord(fy - 1.0 + j, Hf, padding_mode, align_corners))    # int() truncation of a value >= 0
+            row = 0.0
+            for k in range(4):
+                x = torch.floor(_pad_coord(fx - 1.0 + k, Wf, padding_mode, align_corners))
+                xx = fx - 1.0 + k if padding_mode == "zeros" else x
+                yy = fy - 1.0 + j if padding_mode == "zeros" else y
+                row = row + _fetch(feat, xx, yy) * wx[k].unsqueeze(1)
+            out = out + row * wy[j].unsqueeze(1)
+        return out
+    ix, iy = _pad_coord(ix, Wf, padding_mode, align_corners), _pad_coord(iy, Hf, padding_mode, align_corners)
+    fx, fy = torch.floor(ix), torch.floor(iy)
+    wx1, wy1 = ix - fx, iy - fy
+    wx0, wy0 = (fx + 1.0) - ix, (fy + 1.0) - iy
+    return (_fetch(feat, fx, fy) * (wx0 * wy0).unsqueeze(1) + _fetch(feat, fx + 1, fy) * (wx1 * wy0).unsqueeze(1)
+            + _fetch(feat, fx, fy + 1) * (wx0 * wy1).unsqueeze(1) + _fetch(feat, fx + 1, fy + 1) * (wx1 * wy1).unsqueeze(1))
+
+
+def corr_lookup_general(corr_pyramid, flow, radius, mode="bilinear", padding_mode="zeros", align_corners=True):
+    """CorrLookup.forward (utils/corr_lookup.py:100-134) for any mode / padding_mode / align_corners."""
+    B, _, H, W = flow.shape
+    r = int(radius)
+    D = 2 * r + 1
+    Q = B * H * W
+    g = coords_grid(B, W, H) + flow.float()
+    centre = g.permute(0, 2, 3, 1).reshape(Q, 1, 1, 2)
+    d = torch.linspace(-r, r, D)
+    delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1).view(1, D, D, 2)     # [a, b] = (d[a], d[b]) on (x, y)
+    outs = []
+    for i, corr in enumerate(corr_pyramid):
+        coords = centre / float(2 ** i) + delta
+        outs.append(grid_sample(corr, coords, mode, padding_mode, align_corners).view(B, H, W, D * D))
+    return torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().float()
 
 
 def corr_lookup(corr_pyramid, flow, radius):

@@ -11,6 +11,8 @@ copied) and records inputs + outputs of
     model.stage3.raft_decoder.CorrelationPyramid   (through a stub mmcv.cnn.ConvModule)
     model.picopose.Net.select_template_data, model.stage3.raft_decoder.MotionEncoder.corr_net[0],
     model.stage3.flow_decoder.FlowDecoder.forward   (`python oracle/make_golden.py r2` mints only these)
+    utils.corr_lookup.bilinear_sample / CorrLookup with the other interpolation / padding modes and with
+    non-finite flows                                (`python oracle/make_golden.py r2b` mints only these)
 
 on seeded synthetic inputs (picopose_b200/synth.py).  /root/reference does not
 exist on the GPU box, so tests only ever read the committed .npz files.
@@ -135,11 +137,58 @@ def main_round2():
     print("round-2 golden vectors written to", OUT)
 
 
+def main_sampling_modes():
+    """`python oracle/make_golden.py r2b`: the argument combinations of bilinear_sample / CorrLookup that PicoPose does
+    not use (other interpolation and padding modes, align_corners=False) and non-finite flows, from the reference."""
+    from picopose_b200 import synth
+    _, ref_lookup, _, _ = _import_reference()
+    g = torch.Generator().manual_seed(41)
+    feat = torch.randn(2, 3, 6, 9, generator=g)
+    # coordinates from well outside the map (several reflections) to inside, plus exact pixel centres and borders
+    grid = torch.stack([torch.rand(2, 5, 8, generator=g) * 40 - 15, torch.rand(2, 5, 8, generator=g) * 30 - 12], dim=-1)
+    grid[0, 0, :4, 0] = torch.tensor([0.0, 8.0, 4.0, -0.5])
+    grid[0, 0, :4, 1] = torch.tensor([0.0, 5.0, 2.5, 5.5])
+    d = dict(feat=_np(feat), grid=_np(grid))
+    for mode in ("bilinear", "nearest", "bicubic"):
+        for pad in ("zeros", "border", "reflection"):
+            for ac in (True, False):
+                d[f"{mode}_{pad}_{int(ac)}"] = _np(ref_lookup.bilinear_sample(feat, grid.clone(), mode, pad, ac))
+    np.savez_compressed(os.path.join(OUT, "sample_modes.npz"), **d)
+    print("sample_modes:", len(d) - 2, "combinations")
+
+    pyr, flow = synth.lookup_inputs(1, 8, 2, seed=42, flow_sigma=3.0)
+    d = dict(flow=_np(flow), **{f"pyr{i}": _np(v) for i, v in enumerate(pyr)})
+    for mode, pad, ac in (("bilinear", "zeros", False), ("bilinear", "border", True), ("nearest", "zeros", True),
+                          ("bicubic", "reflection", False), ("nearest", "reflection", False)):
+        out = ref_lookup.CorrLookup(2, mode, pad, ac)([v.clone() for v in pyr], flow.clone())
+        d[f"{mode}_{pad}_{int(ac)}"] = _np(out)
+    np.savez_compressed(os.path.join(OUT, "lookup_modes.npz"), radius=2, **d)
+
+    # non-finite flows: a NaN / infinite coordinate poisons every tap weight of the query (F.grid_sample), a finite
+    # far-away one is padding; 3e38 overflows the reference's `* 2.` at level 0 only
+    pyr, flow = synth.lookup_inputs(1, 8, 2, seed=43, flow_sigma=1.0)
+    flow[0, 0, 1, 1] = float("nan")
+    flow[0, 1, 2, 3] = float("inf")
+    flow[0, 0, 4, 4] = float("-inf")
+    flow[0, 1, 4, 4] = float("nan")
+    flow[0, 0, 5, 0] = 3.0e38
+    flow[0, 1, 6, 6] = -1.0e30
+    out = ref_lookup.CorrLookup(2)([v.clone() for v in pyr], flow.clone())
+    feat = torch.randn(1, 4, 8, 8, generator=g)
+    grid = (ref_lookup.coords_grid(1, torch.arange(8), torch.arange(8)) + flow)
+    warped = ref_lookup.bilinear_sample(feat, grid.clone(), align_corners=True)
+    np.savez_compressed(os.path.join(OUT, "lookup_nonfinite.npz"), flow=_np(flow), out=_np(out), radius=2, feat=_np(feat),
+                        warped=_np(warped), **{f"pyr{i}": _np(v) for i, v in enumerate(pyr)})
+    print("lookup_nonfinite: NaN outputs", int(torch.isnan(out).sum()), "of", out.numel())
+
+
 def main():
     from picopose_b200 import synth
 
     if len(sys.argv) > 1 and sys.argv[1] == "r2":
         return main_round2()
+    if len(sys.argv) > 1 and sys.argv[1] == "r2b":
+        return main_sampling_modes()
     ref_matching, ref_lookup, ref_corresp, CorrelationPyramid = _import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pp_corr_lookup_tiled": (_i, [C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pp_volume_retile": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     "pp_bilinear_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pp_grid_sample": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pp_match_kp": (_i, [_i, _i]),
     "pp_match_prepare": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pp_match_scores_workspace": (_sz, [_i, _i, _i]),

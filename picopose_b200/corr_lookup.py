@@ -15,6 +15,10 @@ from torch import Tensor
 from . import _lib
 
 
+_SAMPLE_MODES = {'bilinear': 0, 'nearest': 1, 'bicubic': 2}      # pp_sample_mode
+_PAD_MODES = {'zeros': 0, 'border': 1, 'reflection': 2}          # pp_pad_mode
+
+
 def coords_grid(batch: int, xx: Tensor, yy: Tensor) -> Tensor:
     """(batch, 2, H, W) float grid: channel 0 repeats `xx` along rows, channel 1 repeats `yy` along columns."""
     H, W = yy.shape[0], xx.shape[0]
@@ -29,10 +33,9 @@ def bilinear_sample(feat: Tensor, grid: Tensor, mode: str = 'bilinear', padding_
 
     Unlike the reference this does not scale the caller's `grid` in place (its callers pass temporaries).
     """
-    if mode != 'bilinear' or padding_mode != 'zeros':
-        raise NotImplementedError(
-            f"picopose_b200.bilinear_sample implements mode='bilinear', padding_mode='zeros' "
-            f"(the only combination PicoPose uses); got mode='{mode}', padding_mode='{padding_mode}'")
+    if mode not in _SAMPLE_MODES or padding_mode not in _PAD_MODES:
+        raise ValueError(f"bilinear_sample: mode must be one of {sorted(_SAMPLE_MODES)}, padding_mode one of "
+                         f"{sorted(_PAD_MODES)}; got '{mode}', '{padding_mode}'")      # F.grid_sample raises ValueError too
     _lib.require_cuda(feat, grid)
     _lib.require_inference("bilinear_sample", feat, grid)
     lib = _lib.load()
@@ -43,10 +46,37 @@ def bilinear_sample(feat: Tensor, grid: Tensor, mode: str = 'bilinear', padding_
     Ho, Wo = (grid.shape[2], grid.shape[3]) if chw else (grid.shape[1], grid.shape[2])
     out = torch.empty(N, Cc, Ho, Wo, dtype=torch.float32, device=feat.device)
     with torch.cuda.device(feat.device):
-        _lib.check(lib.pp_bilinear_sample(_lib.ptr(feat), _lib.ptr(grid), N, Cc, Hf, Wf, Ho, Wo, int(chw),
-                                          int(bool(align_corners)), int(bool(scale)), _lib.ptr(out),
-                                          _lib.stream_of(feat)), "pp_bilinear_sample")
+        if mode == 'bilinear' and padding_mode == 'zeros':            # what PicoPose uses: the tuned kernel
+            _lib.check(lib.pp_bilinear_sample(_lib.ptr(feat), _lib.ptr(grid), N, Cc, Hf, Wf, Ho, Wo, int(chw),
+                                              int(bool(align_corners)), int(bool(scale)), _lib.ptr(out),
+                                              _lib.stream_of(feat)), "pp_bilinear_sample")
+        else:
+            _lib.check(lib.pp_grid_sample(_lib.ptr(feat), _lib.ptr(grid), N, Cc, Hf, Wf, Ho, Wo, int(chw),
+                                          int(bool(align_corners)), int(bool(scale)), _SAMPLE_MODES[mode],
+                                          _PAD_MODES[padding_mode], _lib.ptr(out), _lib.stream_of(feat)), "pp_grid_sample")
     return out
+
+
+def _corr_lookup_general(corr_pyramid: Sequence[Tensor], flow: Tensor, radius: int, mode: str, padding_mode: str,
+                         align_corners: bool) -> Tensor:
+    """CorrLookup.forward for the argument combinations PicoPose does not use (utils/corr_lookup.py:100-134 with another
+    interpolation / padding mode, or align_corners=False): the window coordinates are laid out as the reference does
+    and sampled level by level with pp_grid_sample.  A compatibility path, not a tuned one."""
+    B, _, H, W = flow.shape
+    r = int(radius)
+    D = 2 * r + 1
+    dev = flow.device
+    xx = torch.arange(0, W, device=dev)
+    yy = torch.arange(0, H, device=dev)
+    centre = (coords_grid(B, xx, yy) + flow.float()).permute(0, 2, 3, 1).reshape(B * H * W, 1, 1, 2)
+    d = torch.linspace(-r, r, D, device=dev)
+    # delta[a, b] = (d[a], d[b]) is added to an (x, y) centre: the FIRST window axis moves x (:116-121,126)
+    delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1).view(1, D, D, 2)
+    outs = []
+    for i, corr in enumerate(corr_pyramid):
+        coords = centre / 2 ** i + delta
+        outs.append(bilinear_sample(corr, coords, mode, padding_mode, align_corners).view(B, H, W, -1))
+    return torch.cat(outs, dim=-1).permute(0, 3, 1, 2).contiguous().float()
 
 
 def corr_lookup(corr_pyramid: Sequence[Tensor], flow: Tensor, radius: int) -> Tensor:
@@ -101,11 +131,17 @@ class CorrLookup(nn.Module):
         self.align_corners = align_corners
 
     def forward(self, corr_pyramid: Sequence[Tensor], flow: Tensor) -> Tensor:
+        from .correlation import (LazyCorrelationPyramid, LazyLookup, TiledPyramid, encoder_fusion_enabled,
+                                  windowed_correlation)
         if self.mode != 'bilinear' or self.padding_mode != 'zeros' or not self.align_corners:
-            raise NotImplementedError(
-                "picopose_b200.CorrLookup implements the configuration PicoPose uses "
-                "(bilinear, zeros padding, align_corners=True)")
-        from .correlation import LazyCorrelationPyramid, LazyLookup, encoder_fusion_enabled, windowed_correlation
+            # not a configuration PicoPose uses (model/stage3/flow_decoder.py:44 takes the defaults): generic sampler
+            if isinstance(corr_pyramid, LazyCorrelationPyramid):
+                corr_pyramid = corr_pyramid.for_lookup(0)
+            if isinstance(corr_pyramid, TiledPyramid):
+                corr_pyramid = corr_pyramid.rowmajor()
+            _lib.require_cuda(flow, *corr_pyramid)
+            _lib.require_inference("CorrLookup", flow, *corr_pyramid)
+            return _corr_lookup_general(corr_pyramid, flow, self.r, self.mode, self.padding_mode, self.align_corners)
         if isinstance(corr_pyramid, LazyCorrelationPyramid):
             if corr_pyramid.fusable(self.r) and encoder_fusion_enabled():
                 # our MotionEncoder consumes the result (overlay): leave the lookup to it, fused with its first 1x1 conv

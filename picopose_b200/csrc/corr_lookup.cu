@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(128) bilinear_sample_kernel(const float* __res
         const float wx1 = ix - fx0, wy1 = iy - fy0;
         const float wx0 = (fx0 + 1.0f) - ix, wy0 = (fy0 + 1.0f) - iy;
         const bool finite = (ix == ix) && (iy == iy) && fabsf(ix) < 1e9f && fabsf(iy) < 1e9f;
+        // a NaN / infinite coordinate makes every tap weight NaN in F.grid_sample: the sample is NaN, not padding
+        const bool poisoned = !(fabsf(ix) <= 3.402823466e38f) || !(fabsf(iy) <= 3.402823466e38f);
         const int x0 = finite ? (int)fx0 : -2, y0 = finite ? (int)fy0 : -2;
         const bool okx0 = x0 >= 0 && x0 < Wf, okx1 = x0 + 1 >= 0 && x0 + 1 < Wf;
         const bool oky0 = y0 >= 0 && y0 < Hf, oky1 = y0 + 1 >= 0 && y0 + 1 < Hf;
@@ -375,7 +377,116 @@ __global__ void __launch_bounds__(128) bilinear_sample_kernel(const float* __res
             acc = fmaf(v01[c], w01, acc);
             acc = fmaf(v10[c], w10, acc);
             acc = fmaf(v11[c], w11, acc);
-            if (c0 + c < C) __stcs(o + (size_t)c * oplane, acc);
+            if (c0 + c < C) __stcs(o + (size_t)c * oplane, poisoned ? __int_as_float(0x7fc00000) : acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// F.grid_sample for the argument combinations PicoPose never uses (utils/corr_lookup.py:29-65 passes mode / padding_mode
+// through): nearest and bicubic interpolation, border and reflection padding.  A compatibility path, one thread per
+// output pixel, written after ATen's GridSampler rules:
+//   unnormalise -> (border: clip | reflection: reflect, then clip) -> taps; bicubic applies the padding rule per tap and
+//   uses the A = -0.75 convolution coefficients; nearest rounds half to even.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gs_reflect(float in, int twice_low, int twice_high) {
+    if (twice_low == twice_high) return 0.0f;
+    const float mn = (float)twice_low * 0.5f, span = (float)(twice_high - twice_low) * 0.5f;
+    in = fabsf(in - mn);
+    const float extra = fmodf(in, span);
+    const int flips = (int)floorf(in / span);
+    return (flips & 1) == 0 ? extra + mn : span - extra + mn;
+}
+__device__ __forceinline__ float gs_pad(float c, int size, int padding, int align_corners) {
+    if (padding == 1) return fminf((float)(size - 1), fmaxf(c, 0.0f));
+    if (padding == 2) {
+        c = align_corners ? gs_reflect(c, 0, 2 * (size - 1)) : gs_reflect(c, -1, 2 * size - 1);
+        return fminf((float)(size - 1), fmaxf(c, 0.0f));
+    }
+    return c;
+}
+__device__ __forceinline__ float gs_fetch(const float* fc, float x, float y, int Wf, int Hf) {
+    // a non-finite or far-away coordinate is out of bounds
+    if (!(x > -1.0e9f && x < 1.0e9f && y > -1.0e9f && y < 1.0e9f)) return 0.0f;
+    const int xi = (int)x, yi = (int)y;
+    return (xi >= 0 && xi < Wf && yi >= 0 && yi < Hf) ? __ldg(fc + (size_t)yi * Wf + xi) : 0.0f;
+}
+__device__ __forceinline__ void gs_cubic(float t, float (&w)[4]) {
+    const float A = -0.75f;
+    float x = t + 1.0f;
+    w[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+    x = t;
+    w[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+    x = 1.0f - t;
+    w[2] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+    x = 2.0f - t;
+    w[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+
+__global__ void __launch_bounds__(128) grid_sample_general_kernel(const float* __restrict__ feat, const float* __restrict__ grid,
+                                                                  int N, int C, int Hf, int Wf, int Ho, int Wo, int grid_chw,
+                                                                  int align_corners, int scale, int mode, int padding,
+                                                                  float* __restrict__ out) {
+    const long long total = (long long)N * Ho * Wo;
+    const size_t plane = (size_t)Hf * Wf, oplane = (size_t)Ho * Wo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ((long long)Ho * Wo));
+        const int pix = (int)(i - (long long)n * Ho * Wo);
+        float gx = grid_chw ? __ldg(grid + ((size_t)n * 2 + 0) * oplane + pix) : __ldg(grid + ((size_t)n * oplane + pix) * 2);
+        float gy = grid_chw ? __ldg(grid + ((size_t)n * 2 + 1) * oplane + pix) : __ldg(grid + ((size_t)n * oplane + pix) * 2 + 1);
+        if (scale) {
+            gx = __fsub_rn(__fdiv_rn(__fmul_rn(gx, 2.0f), (float)(Wf > 1 ? Wf - 1 : 1)), 1.0f);
+            gy = __fsub_rn(__fdiv_rn(__fmul_rn(gy, 2.0f), (float)(Hf > 1 ? Hf - 1 : 1)), 1.0f);
+        }
+        float ix, iy;
+        if (align_corners) {
+            ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(Wf - 1));
+            iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(Hf - 1));
+        } else {
+            ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)Wf), 1.0f), 0.5f);
+            iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)Hf), 1.0f), 0.5f);
+        }
+        const float* f = feat + (size_t)n * C * plane;
+        float* o = out + (size_t)n * C * oplane + pix;
+        if (mode == 1) {  // nearest
+            const float x = nearbyintf(gs_pad(ix, Wf, padding, align_corners)), y = nearbyintf(gs_pad(iy, Hf, padding, align_corners));
+            for (int c = 0; c < C; ++c) o[(size_t)c * oplane] = gs_fetch(f + (size_t)c * plane, x, y, Wf, Hf);
+        } else if (mode == 2) {  // bicubic: the padding rule applies to each of the 4 x 4 taps
+            const float fx = floorf(ix), fy = floorf(iy);
+            float wx[4], wy[4];
+            gs_cubic(ix - fx, wx);
+            gs_cubic(iy - fy, wy);
+            float xs[4], ys[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                xs[k] = gs_pad(fx - 1.0f + (float)k, Wf, padding, align_corners);
+                ys[k] = gs_pad(fy - 1.0f + (float)k, Hf, padding, align_corners);
+            }
+            for (int c = 0; c < C; ++c) {
+                const float* fc = f + (size_t)c * plane;
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float row = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) row += gs_fetch(fc, xs[k], ys[j], Wf, Hf) * wx[k];
+                    acc += row * wy[j];
+                }
+                o[(size_t)c * oplane] = acc;
+            }
+        } else {  // bilinear with border / reflection padding
+            ix = gs_pad(ix, Wf, padding, align_corners);
+            iy = gs_pad(iy, Hf, padding, align_corners);
+            const float fx = floorf(ix), fy = floorf(iy);
+            const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy;
+            for (int c = 0; c < C; ++c) {
+                const float* fc = f + (size_t)c * plane;
+                float acc = gs_fetch(fc, fx, fy, Wf, Hf) * (wx0 * wy0);
+                acc += gs_fetch(fc, fx + 1.0f, fy, Wf, Hf) * (wx1 * wy0);
+                acc += gs_fetch(fc, fx, fy + 1.0f, Wf, Hf) * (wx0 * wy1);
+                acc += gs_fetch(fc, fx + 1.0f, fy + 1.0f, Wf, Hf) * (wx1 * wy1);
+                o[(size_t)c * oplane] = acc;
+            }
         }
     }
 }
@@ -517,6 +628,28 @@ extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, i
     if (grid_dim > cap) grid_dim = cap;
     bilinear_sample_kernel<<<dim3(grid_dim, (C + BS_CPT - 1) / BS_CPT), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         feat, grid, N, C, Hf, Wf, Ho, Wo, grid_chw, align_corners, scale, out);
+    PP_LAUNCHED();
+    return PP_OK;
+}
+
+extern "C" int pp_grid_sample(const float* feat, const float* grid, int N, int C, int Hf, int Wf, int Ho, int Wo,
+                              int grid_chw, int align_corners, int scale, int mode, int padding_mode, float* out,
+                              void* stream) {
+    using namespace pp;
+    if (int rc = require_sm100()) return rc;
+    if (mode == PP_SAMPLE_BILINEAR && padding_mode == PP_PAD_ZEROS)
+        return pp_bilinear_sample(feat, grid, N, C, Hf, Wf, Ho, Wo, grid_chw, align_corners, scale, out, stream);
+    if (N == 0) return PP_OK;
+    PP_CHECK_ARG(feat && grid && out, "pp_grid_sample: null pointer");
+    PP_CHECK_ARG(N > 0 && C > 0 && Hf > 0 && Wf > 0 && Ho > 0 && Wo > 0, "pp_grid_sample: bad shape");
+    PP_CHECK_ARG(mode >= 0 && mode <= 2 && padding_mode >= 0 && padding_mode <= 2, "pp_grid_sample: unknown mode %d / padding %d",
+                 mode, padding_mode);
+    const long long total = (long long)N * Ho * Wo;
+    int grid_dim = (int)((total + 127) / 128);
+    const int cap = sm_count() * 64;
+    if (grid_dim > cap) grid_dim = cap;
+    grid_sample_general_kernel<<<grid_dim, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        feat, grid, N, C, Hf, Wf, Ho, Wo, grid_chw, align_corners, scale, mode, padding_mode, out);
     PP_LAUNCHED();
     return PP_OK;
 }

@@ -37,7 +37,7 @@ __device__ __forceinline__ void axis_tap(float p, int size, int& i0, float& w1) 
     // a clamped index is out of bounds and contributes zero, exactly as zero padding does.
     f = fminf(fmaxf(f, -2.0f), (float)size);
     i0 = (f == f) ? (int)f : -2;
-    if (!(w1 >= 0.0f && w1 <= 1.0f)) w1 = 0.0f;  // non-finite coordinates: everything is padding
+    // a non-finite coordinate leaves w1 = NaN: every sample that uses this tap is NaN, as in F.grid_sample
 }
 
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ void axis_tap_raw(float p, int size, int& i0, float& 
     raw = (f == f) ? (int)fminf(fmaxf(f, -1.0e6f), 1.0e6f) : -2000000;
     f = fminf(fmaxf(f, -2.0f), (float)size);
     i0 = (f == f) ? (int)f : -2;
-    if (!(w1 >= 0.0f && w1 <= 1.0f)) w1 = 0.0f;
+    // a non-finite coordinate leaves w1 = NaN: every sample that uses this tap is NaN, as in F.grid_sample
 }
 
 // corr_lookup_tma.cu: tiled volumes fetched with bulk copies (radius 1..8); *handled = false leaves it to the banded kernel

@@ -48,7 +48,7 @@ __device__ __forceinline__ void wc_axis_tap(float p, int size, int& i0, float& w
     w1 = __fsub_rn(i, f);
     f = fminf(fmaxf(f, -2.0f), (float)size);
     i0 = (f == f) ? (int)f : -2;
-    if (!(w1 >= 0.0f && w1 <= 1.0f)) w1 = 0.0f;
+    // a non-finite coordinate leaves w1 = NaN: every sample that uses this tap is NaN, as in F.grid_sample
 }
 
 // (N, C, H, W) -> (N, (H>>l)*(W>>l), C): 2^l x 2^l average pooling (what l AvgPool2d(2,2) steps do to the

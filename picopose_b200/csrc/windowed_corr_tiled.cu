@@ -63,7 +63,7 @@ __device__ __forceinline__ void wt_axis_tap(float p, int size, int& i0, float& w
     w1 = __fsub_rn(i, f);
     f = fminf(fmaxf(f, -2.0f), (float)size);
     i0 = (f == f) ? (int)f : -2;
-    if (!(w1 >= 0.0f && w1 <= 1.0f)) w1 = 0.0f;
+    // a non-finite coordinate leaves w1 = NaN: every sample that uses this tap is NaN, as in F.grid_sample
 }
 
 __device__ __forceinline__ void tma_load_4d(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
@@ -459,7 +459,7 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
                     float* dst = p.conv.out + (((size_t)n * cout + co0 + a) * p.H + qh) * p.W + qw;
 #pragma unroll
                     for (int b2 = 0; b2 < 4; ++b2) {
-                        const float v = p.conv.relu ? fmaxf(acc[a][b2], 0.f) : acc[a][b2];
+                        const float v = (p.conv.relu && acc[a][b2] < 0.f) ? 0.f : acc[a][b2];  // torch.relu keeps NaN; fmaxf would not
                         if (qw + b2 < p.W) __stcs(dst + b2, v);
                     }
                 }

@@ -120,12 +120,13 @@ def test_corr_lookup_tiled_adversarial_flows(r, kernel, monkeypatch):
     flow[1, :, 5, 5] = float("inf")
     flow[1, :, 6, 6] = -3e9
     flow[1, 0, 7, 7] = float("nan")
-    ref = OL.corr_lookup(pyr, torch.nan_to_num(flow, nan=1e9, posinf=1e9, neginf=-1e9), r)
+    ref = OL.corr_lookup(pyr, flow, r)                 # NaN windows for the inf / NaN queries (F.grid_sample), zeros for -3e9
     tp = TiledPyramid.from_volumes([p.to(DEV) for p in pyr])
     out = corr_lookup(tp, flow.to(DEV), r)
     _lib.check_device_faults()
-    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5)
-    assert torch.equal(out, corr_lookup([p.to(DEV) for p in pyr], flow.to(DEV), r))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-5, equal_nan=True)
+    rm = corr_lookup([p.to(DEV) for p in pyr], flow.to(DEV), r)
+    assert torch.equal(torch.isnan(out), torch.isnan(rm)) and torch.equal(torch.nan_to_num(out), torch.nan_to_num(rm))
 
 
 def test_tiled_pyramid_from_the_contraction():
@@ -212,6 +213,90 @@ def test_bilinear_sample_and_coords_grid():
     ref = OL.bilinear_sample(f, gr, align_corners=True)
     out = bilinear_sample(f.to(DEV), gr.to(DEV), align_corners=True)
     np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=1e-5)
+
+
+def test_sampling_modes_golden():
+    """bilinear_sample / CorrLookup with the interpolation and padding modes PicoPose never passes (the reference hands
+    them to F.grid_sample): reference outputs for all 18 combinations, and CorrLookup in five of them."""
+    from picopose_b200.corr_lookup import CorrLookup, bilinear_sample
+    g = load("sample_modes.npz")
+    feat, grid = cuda(g["feat"]), cuda(g["grid"])
+    for key in g.files:
+        if key in ("feat", "grid"):
+            continue
+        mode, pad, ac = key.rsplit("_", 2)
+        out = bilinear_sample(feat, grid, mode, pad, bool(int(ac)))
+        np.testing.assert_allclose(out.cpu().numpy(), g[key], rtol=0, atol=1e-5, err_msg=key)
+        chw = bilinear_sample(feat, grid.permute(0, 3, 1, 2).contiguous(), mode, pad, bool(int(ac)))   # (N,2,Ho,Wo) grids too
+        assert torch.equal(chw, out)
+    g = load("lookup_modes.npz")
+    pyr, flow = [cuda(g["pyr0"]), cuda(g["pyr1"])], cuda(g["flow"])
+    for key in g.files:
+        if key in ("flow", "pyr0", "pyr1", "radius"):
+            continue
+        mode, pad, ac = key.rsplit("_", 2)
+        out = CorrLookup(int(g["radius"]), mode, pad, bool(int(ac)))(pyr, flow)
+        np.testing.assert_allclose(out.cpu().numpy(), g[key], rtol=0, atol=1e-5, err_msg=key)
+    # larger, seeded, against the oracle
+    gen = torch.Generator().manual_seed(77)
+    feat = torch.randn(3, 5, 16, 12, generator=gen)
+    grid = torch.stack([torch.rand(3, 9, 7, generator=gen) * 60 - 24, torch.rand(3, 9, 7, generator=gen) * 70 - 27], dim=-1)
+    for mode in ("bilinear", "nearest", "bicubic"):
+        for pad in ("zeros", "border", "reflection"):
+            for ac in (True, False):
+                ref = OL.grid_sample(feat, grid.clone(), mode, pad, ac)
+                out = bilinear_sample(feat.to(DEV), grid.to(DEV), mode, pad, ac)
+                np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=2e-5, err_msg=f"{mode} {pad} {ac}")
+    with pytest.raises(ValueError):
+        bilinear_sample(feat.to(DEV), grid.to(DEV), "lanczos")
+    _lib.check_device_faults()
+
+
+def test_nonfinite_flows_propagate_like_grid_sample():
+    """A NaN / infinite flow makes every tap weight of that query NaN in F.grid_sample, so the reference returns NaN for
+    the query's whole window (all levels whose coordinate is non-finite); a finite far-away flow is padding.  Reference
+    outputs (tests/golden/lookup_nonfinite.npz) through every lookup path."""
+    from picopose_b200.corr_lookup import bilinear_sample, coords_grid, corr_lookup
+    from picopose_b200.correlation import TiledPyramid, retile_volume, windowed_correlation, windowed_correlation_conv
+    g = load("lookup_nonfinite.npz")
+    pyr, flow, r = [cuda(g["pyr0"]), cuda(g["pyr1"])], cuda(g["flow"]), int(g["radius"])
+    out = corr_lookup(pyr, flow, r)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=0, atol=1e-5, equal_nan=True)
+    pyr16, flow16 = synth.lookup_inputs(1, 16, 2, seed=79, flow_sigma=2.0)           # 16^2 / 8^2 slices can be tiled
+    flow16[0, 0, 3, 3] = float("nan")
+    flow16[0, 1, 9, 2] = float("-inf")
+    flow16[0, 1, 15, 15] = 2.0e38                                                     # overflows at level 0 only
+    ref16 = OL.corr_lookup(pyr16, flow16, 4).numpy()
+    assert np.isnan(ref16).sum() == 5 * 81
+    tiled = TiledPyramid([retile_volume(v.to(DEV), True) for v in pyr16])
+    np.testing.assert_allclose(corr_lookup(tiled, flow16.to(DEV), 4).cpu().numpy(), ref16, rtol=0, atol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(corr_lookup([v.to(DEV) for v in pyr16], flow16.to(DEV), 4).cpu().numpy(), ref16, rtol=0,
+                               atol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(corr_lookup(pyr, flow, 10).cpu().numpy(), OL.corr_lookup([v.cpu() for v in pyr], flow.cpu(), 10).numpy(),
+                               rtol=0, atol=1e-5, equal_nan=True)                     # runtime-radius kernel
+    grid = coords_grid(1, torch.arange(8, device=DEV), torch.arange(8, device=DEV)) + flow
+    warped = bilinear_sample(cuda(g["feat"]), grid, align_corners=True)
+    np.testing.assert_allclose(warped.cpu().numpy(), g["warped"], rtol=0, atol=1e-5, equal_nan=True)
+    # the no-volume kernels: same poisoned queries, on features
+    gen = torch.Generator().manual_seed(78)
+    for H, L, rr in ((8, 2, 2), (16, 3, 1), (16, 2, 4)):
+        f1, f2 = torch.randn(1, 64, H, H, generator=gen), torch.randn(1, 64, H, H, generator=gen)
+        fl = torch.randn(1, 2, H, H, generator=gen)
+        fl[0, 0, 1, 1] = float("nan")
+        fl[0, 1, 2, 3] = float("inf")
+        fl[0, 0, 5, 0] = 3.0e38
+        fl[0, 1, 6, 6] = -1.0e30
+        ref = OL.corr_lookup(OL.correlation_pyramid(f1, f2, L), fl, rr)
+        assert bool(torch.isnan(ref).any()) and not bool(torch.isnan(ref[0, :, 6, 6]).any())
+        out = windowed_correlation(f1.to(DEV), f2.to(DEV), fl.to(DEV), L, rr)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=5e-5, equal_nan=True, err_msg=f"{H} {L} {rr}")
+        if rr <= 2:
+            w = torch.randn(32, L * (2 * rr + 1) ** 2, generator=gen)
+            bias = torch.randn(32, generator=gen)
+            conv = windowed_correlation_conv(f1.to(DEV), f2.to(DEV), fl.to(DEV), L, rr, w.to(DEV), bias.to(DEV), relu=True)
+            cref = torch.relu(OL.conv1x1_relu(ref, w, bias, relu=False))              # torch.relu keeps NaN
+            np.testing.assert_allclose(conv.cpu().numpy(), cref.numpy(), rtol=0, atol=2e-4, equal_nan=True)
+    _lib.check_device_faults()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -46,8 +46,10 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         corr_lookup.CorrLookup(2)([torch.zeros(16, 1, 4, 4)], torch.zeros(1, 2, 4, 4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         correspondence.compute_stage3_correspondences(torch.zeros(1, 2, 4, 4), torch.zeros(1, 1, 4, 4))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         corr_lookup.bilinear_sample(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2), mode="nearest")
+    with pytest.raises(ValueError):                                          # F.grid_sample rejects unknown modes too
+        corr_lookup.bilinear_sample(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2), mode="lanczos")
 
 
 def test_overlay_shadows_exactly_three_reference_modules(tmp_path):

@@ -17,6 +17,9 @@ def load(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
+T = torch.from_numpy
+
+
 MATCH = ["small", "medium", "bern", "ones", "allmasked", "identical", "tiles"]   # tiles: 32x32 patches, prefix masks
 
 
@@ -99,6 +102,34 @@ def test_bilinear_and_grid():
     np.testing.assert_allclose(OL.bilinear_sample(feat, grid.clone(), True).numpy(), g["out_true"], atol=3e-6)
     np.testing.assert_allclose(OL.bilinear_sample(feat, grid.clone(), False).numpy(), g["out_false"], atol=3e-6)
     np.testing.assert_array_equal(OL.coords_grid(2, 7, 5).numpy(), g["coords"])
+
+
+def test_sampling_modes_and_nonfinite_flows():
+    """The argument combinations PicoPose does not use (nearest / bicubic, border / reflection, align_corners=False) and
+    NaN / infinite flows, against reference outputs (oracle/make_golden.py r2b)."""
+    g = load("sample_modes.npz")
+    feat, grid = T(g["feat"]), T(g["grid"])
+    for key in g.files:
+        if key in ("feat", "grid"):
+            continue
+        mode, pad, ac = key.rsplit("_", 2)
+        out = OL.grid_sample(feat, grid.clone(), mode, pad, bool(int(ac)))
+        np.testing.assert_allclose(out.numpy(), g[key], rtol=0, atol=5e-6, err_msg=key)
+    g = load("lookup_modes.npz")
+    pyr, flow = [T(g["pyr0"]), T(g["pyr1"])], T(g["flow"])
+    for key in g.files:
+        if key in ("flow", "pyr0", "pyr1", "radius"):
+            continue
+        mode, pad, ac = key.rsplit("_", 2)
+        out = OL.corr_lookup_general(pyr, flow, int(g["radius"]), mode, pad, bool(int(ac)))
+        np.testing.assert_allclose(out.numpy(), g[key], rtol=0, atol=5e-6, err_msg=key)
+    g = load("lookup_nonfinite.npz")
+    pyr, flow = [T(g["pyr0"]), T(g["pyr1"])], T(g["flow"])
+    out = OL.corr_lookup(pyr, flow, int(g["radius"])).numpy()
+    assert np.isnan(g["out"]).sum() == 175                            # 3 poisoned queries x 2 levels + one at level 0 only
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=2e-6, equal_nan=True)
+    warped = OL.bilinear_sample(T(g["feat"]), OL.coords_grid(1, 8, 8) + flow, align_corners=True).numpy()
+    np.testing.assert_allclose(warped, g["warped"], rtol=0, atol=2e-6, equal_nan=True)
 
 
 def test_correlation_pyramid():
