@@ -86,7 +86,7 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int RB_BYTES = NUM_EPI_WARPS * EPI_COLS * 8;  // per epilogue warp: factor + patch index of its columns
-    static constexpr int PREFIX_BYTES = (MAX_DETS_PER_LAUNCH + 1) * 4;  // tile mode: per-detection tile prefix
+    static constexpr int PREFIX_BYTES = (3 * MAX_DETS_PER_LAUNCH + 1) * 4;  // per-detection tile prefix (tile mode), live rows, order
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + RB_BYTES + PREFIX_BYTES + 1024;  // + alignment slack
 };
 
@@ -125,7 +125,12 @@ struct TileCoord {
 // (r1 dealt single tiles round-robin; the column tiles of one M-side tile then ran on neighbouring clusters, which drift
 // apart over a long batch until the shared tile has left L2: ncu showed 25 GB of DRAM reads for 10.8 GB of operands on an
 // 8 x 642 batch, and every detection streamed its whole bank again.)
-__device__ __forceinline__ int live_rows(const GemmParams& p, int b) { return p.tv ? __ldg(p.tv + b) : p.T; }
+// (launches of up to MAX_DETS_PER_LAUNCH detections keep copies of tv[] and det_order[] in shared memory: the per-tile /
+// per-detection decode of all three roles then stays off the global-memory path, whose L1 lines the epilogue's streaming
+// loads keep evicting -- measured +3 % on the configs[1] contraction, same box)
+__device__ __forceinline__ int live_rows(const GemmParams& p, int b, const int* rows_s = nullptr) {
+    return rows_s ? rows_s[b] : (p.tv ? __ldg(p.tv + b) : p.T);
+}
 __device__ __forceinline__ uint32_t col_tiles(int rows) { return (uint32_t)((rows + BLOCK_N - 1) / BLOCK_N); }
 // bank of detection b, forced into range: a bad index must not become an out-of-bounds TMA coordinate / rnorm read
 __device__ __forceinline__ int bank_of(const GemmParams& p, int b) {
@@ -141,7 +146,7 @@ __device__ __forceinline__ int bank_of(const GemmParams& p, int b) {
 struct WorkItem {
     int pos0, pos1, n, mt, nt0, nts;
 };
-__device__ __forceinline__ WorkItem decode_work(uint32_t g, const GemmParams& p, const uint32_t* prefix) {
+__device__ __forceinline__ WorkItem decode_work(uint32_t g, const GemmParams& p, const uint32_t* prefix, const int* rows_s) {
     WorkItem w;
     if (p.tile_mode) {
         // flat tile index -> detection by binary search in the per-detection tile prefix, then (n, mt, nt)
@@ -150,7 +155,7 @@ __device__ __forceinline__ WorkItem decode_work(uint32_t g, const GemmParams& p,
             const int mid = (lo + hi) >> 1;
             if (prefix[mid] <= g) lo = mid; else hi = mid;
         }
-        const uint32_t nct = col_tiles(live_rows(p, lo));
+        const uint32_t nct = col_tiles(live_rows(p, lo, rows_s));
         const uint32_t local = g - prefix[lo];
         const uint32_t r = local / nct;
         w.nt0 = (int)(local - r * nct);
@@ -174,15 +179,15 @@ __device__ __forceinline__ WorkItem decode_work(uint32_t g, const GemmParams& p,
 }
 // detection at position `pos` of the (bank-sorted) order: its tile shape
 template <bool MATCH>
-__device__ __forceinline__ TileCoord det_tiles(int pos, int n, int mt, const GemmParams& p) {
+__device__ __forceinline__ TileCoord det_tiles(int pos, int n, int mt, const GemmParams& p, const int* rows_s, const int* order_s) {
     TileCoord c;
-    c.b = p.det_order ? __ldg(p.det_order + pos) : pos;
+    c.b = order_s ? order_s[pos] : (p.det_order ? __ldg(p.det_order + pos) : pos);
     c.n = n;
     c.mt = mt;
     c.nt = 0;
     if (MATCH) {
         // a detection with tv unmasked patches is cut into ceil(tv / 256) column tiles of round_up(tv / tiles, 32) columns
-        c.rows = live_rows(p, c.b);
+        c.rows = live_rows(p, c.b, rows_s);
         c.nct = (int)col_tiles(c.rows);
         c.ncols = c.nct ? (int)((((uint32_t)c.rows + (uint32_t)c.nct - 1) / (uint32_t)c.nct + 31u) & ~31u) : 0;
     } else {
@@ -213,8 +218,13 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NUM_ACC));
     float* rb_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES);
     uint32_t* tile_prefix = reinterpret_cast<uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Cfg::RB_BYTES);
+    int* rows_tab = reinterpret_cast<int*>(tile_prefix + MAX_DETS_PER_LAUNCH + 1);
     constexpr bool MATCH = EPI == EPI_MATCH || EPI == EPI_MATCH_FAST;  // template patches on the M side, compact query rows on the N side
     constexpr bool FAST = EPI == EPI_MATCH_FAST;
+    int* order_tab = rows_tab + MAX_DETS_PER_LAUNCH;
+    const bool tabs = MATCH && p.B <= MAX_DETS_PER_LAUNCH;
+    const int* rows_s = tabs ? rows_tab : nullptr;
+    const int* order_s = tabs ? order_tab : nullptr;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -241,14 +251,20 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::fence_barrier_init();
     } else if (warp == 2) {
         ptx::tmem_alloc<CL>(ptx::smem_u32((const void*)tmem_slot), 512);
-    } else if (warp == 3 && MATCH && p.tile_mode) {
-        // inclusive scan of the per-detection tile counts (B <= MAX_DETS_PER_LAUNCH), 32 detections per step
+    } else if (warp == 3 && tabs) {
+        // live rows and launch order of every detection; tile mode: inclusive scan of the per-detection tile counts,
+        // 32 detections per step
         uint32_t run = 0;
         if (lane == 0) tile_prefix[0] = 0;
         for (int b0 = 0; b0 < p.B; b0 += 32) {
             const int b = b0 + lane;
             uint32_t cnt = 0;
-            if (b < p.B) cnt = col_tiles(live_rows(p, b)) * (uint32_t)(p.N * p.num_mt);
+            if (b < p.B) {
+                const int rows = live_rows(p, b);
+                rows_tab[b] = rows;
+                order_tab[b] = p.det_order ? __ldg(p.det_order + b) : b;
+                cnt = col_tiles(rows) * (uint32_t)(p.N * p.num_mt);
+            }
             uint32_t inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -272,9 +288,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         int stage = 0;
         uint32_t phase = 0;
         for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
-         const WorkItem wi = decode_work(grp, p, tile_prefix);
+         const WorkItem wi = decode_work(grp, p, tile_prefix, rows_s);
          for (int pos = wi.pos0; pos < wi.pos1; ++pos) {
-          TileCoord tc = det_tiles<MATCH>(pos, wi.n, wi.mt, p);
+          TileCoord tc = det_tiles<MATCH>(pos, wi.n, wi.mt, p, rows_s, order_s);
           const int bank = bank_of(p, tc.b);
           const int q_row0 = tc.b * p.T;                                       // query operand: rows of detection b
           const int t_row0 = (int)(((long long)bank * p.N + tc.n) * p.T);      // bank operand: rows of view n
@@ -313,9 +329,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t phase = 0;
         uint32_t iter = 0;
         for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
-         const WorkItem wi = decode_work(grp, p, tile_prefix);
+         const WorkItem wi = decode_work(grp, p, tile_prefix, rows_s);
          for (int pos = wi.pos0; pos < wi.pos1; ++pos) {
-          const TileCoord gc = det_tiles<MATCH>(pos, wi.n, wi.mt, p);
+          const TileCoord gc = det_tiles<MATCH>(pos, wi.n, wi.mt, p, rows_s, order_s);
           const uint32_t idesc = ptx::idesc_bf16(BLOCK_M * CL, gc.ncols);
           const int nt_end = wi.nts < 0 ? gc.nct : wi.nt0 + wi.nts;
           for (int nt = wi.nt0; nt < nt_end; ++nt, ++iter) {
@@ -352,9 +368,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int hh = e >> 2;    // first 32-column chunk of the tile this warp reads (then hh + 4)
         uint32_t iter = 0;
         for (uint32_t grp = cluster_id; grp < num_groups; grp += num_clusters) {
-         const WorkItem wi = decode_work(grp, p, tile_prefix);
+         const WorkItem wi = decode_work(grp, p, tile_prefix, rows_s);
          for (int pos = wi.pos0; pos < wi.pos1; ++pos) {
-          TileCoord tc = det_tiles<MATCH>(pos, wi.n, wi.mt, p);
+          TileCoord tc = det_tiles<MATCH>(pos, wi.n, wi.mt, p, rows_s, order_s);
           const int nt_end = wi.nts < 0 ? tc.nct : wi.nt0 + wi.nts;
           // column maxima (over the query rows, lane-local) run across all column tiles of the group: one atomic per
           // (template patch, group) instead of one per tile
