@@ -48,7 +48,14 @@ struct LookupCfg {
     static constexpr int PITCH = NV * 4;              // words per staged row
     static constexpr int QS = ((NRB * NV) | 1) * 4;   // words per query: odd number of 16-byte units (bank spread)
     static constexpr int WARP_WORDS = 32 * QS;
+    // per query a table of NRB row offsets + NV piece offsets (odd pitch: the owners' stores spread over banks)
+    static constexpr int TW = (NRB + NV) | 1;
+    static constexpr int WARP_WORDS_TAB = WARP_WORDS + 32 * TW;
 };
+
+// table entries: an element offset (>= 0), "outside the map: zero-fill", or "no tap touches it: skip"
+constexpr int TAB_OOB = (int)0x80000000u;
+constexpr int TAB_SKIP = (int)0xC0000000u;
 
 // TILED: every (Hl x Wl) slice is stored as 4-row x 8-column tiles, one 128-byte line per tile (our own
 // CorrelationPyramid writes it that way on request).  DRAM moves whole 128-byte lines on this GPU
@@ -56,15 +63,25 @@ struct LookupCfg {
 // 6.9 lines at r = 4 -- instead of (2r+2) * 1.17 row segments (11.7 lines) in the reference's row-major slices.  Only the
 // global address of a 16-byte piece changes: pieces are 4-aligned in x, tile rows are 8 floats, so a piece never
 // straddles two tiles; the staged footprint in shared memory and everything after it are the same.
+//
+// How the staging loop finds its addresses.  The element offset of (y, x) separates into a row part and a column part
+// in both layouts (row-major: y * W + x; tiled: ((y >> 2) * (W >> 3) << 5) + ((y & 3) << 3)  +  ((x >> 3) << 5) + (x & 7)),
+// so every lane -- as the owner of its query -- writes the NRB row parts of the band and the NV column parts of its
+// footprint into a small table (with "zero-fill" / "skip" encoded as negative values); the staging loop, where lane =
+// (row, piece) and the query index is the unrolled loop variable, then needs two shared loads at compile-time offsets, an
+// OR, an ADD and two predicates per copy instead of two shuffles, the field unpacking, four range checks and the tile
+// arithmetic (the first form of this kernel): ~13 instead of ~30 instructions for each of the 32 x PASSES x NB copies of a
+// work item; r = 4 on tiled volumes 0.258 -> 0.224 ms, r = 8 0.885 -> 0.703 ms (profiles/r2z_*).
 template <int R, int JB, bool TILED>
 __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupParams p) {
     using Cfg = LookupCfg<R, JB>;
-    constexpr int D = Cfg::D, NB = Cfg::NB, NRB = Cfg::NRB, NV = Cfg::NV, PITCH = Cfg::PITCH, QS = Cfg::QS;
+    constexpr int D = Cfg::D, NB = Cfg::NB, NRB = Cfg::NRB, NV = Cfg::NV, PITCH = Cfg::PITCH, QS = Cfg::QS, TW = Cfg::TW;
     extern __shared__ __align__(16) float smem[];
     const int warps_per_block = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    float* stage = smem + (size_t)warp * Cfg::WARP_WORDS;
+    float* stage = smem + (size_t)warp * Cfg::WARP_WORDS_TAB;
+    int* tab = reinterpret_cast<int*>(stage + Cfg::WARP_WORDS);  // [32 queries][TW] offset tables
 
     // work item = (query group, pyramid level): levels of one group run on different warps, which keeps the
     // dependent chain per warp short when there are few queries (the native 16^2..64^2 ladder)
@@ -83,7 +100,6 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
         const float cx = __fadd_rn((float)qw, fx);  // coords_grid + flow, utils/corr_lookup.py:113
         const float cy = __fadd_rn((float)qh, fy);
         float* out_b = p.out + (size_t)b * p.L * D * D * p.HW;  // warp-uniform base, 32-bit offsets below
-        const int nq = min(32, p.HW - hw0);                     // live queries of this group
 
         {
             const int Hl = p.vh[l], Wl = p.vw[l];
@@ -101,6 +117,15 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
             // slice base of the group's first query; query ql of the group is ql slices further
             const float* vol_g = p.vol[l] + ((size_t)b * p.HW + hw0) * ((size_t)Hl * Wl);
             const uint32_t slice = (uint32_t)Hl * (uint32_t)Wl;
+            {
+                __syncwarp();  // the previous item's staging loop is done with the table
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int x = xs + 4 * v;
+                    const int xoff = TILED ? ((x >> 3) << 5) + (x & 7) : x;
+                    tab[lane * TW + NRB + v] = (!live || v >= pieces) ? TAB_SKIP : ((unsigned)x < (unsigned)Wl ? xoff : TAB_OOB);
+                }
+            }
 
 #pragma unroll
             for (int band = 0; band < NB; ++band) {
@@ -117,12 +142,21 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                 const int rows = regular ? (j1 - j0) + 1 : yo[j1 - 1] + 1 - yb + 1;
                 const bool warp_regular = __all_sync(0xffffffffu, regular || !live);
                 __syncwarp();  // previous band's readers are done with the staging area
-                const int packed = (yb + 16) | (pieces << 20) | (rows << 26);  // yb >= -(JB + 1) >= -10
+                {
+#pragma unroll
+                    for (int row = 0; row < NRB; ++row) {
+                        const int y = yb + row;
+                        const int yoff = TILED ? (((y >> 2) * (Wl >> 3)) << 5) + ((y & 3) << 3) : y * Wl;
+                        // the row part carries the query's slice too: the staging loop adds nothing but the column part
+                        tab[lane * TW + row] = (!live || row >= rows) ? TAB_SKIP
+                                               : ((unsigned)y < (unsigned)Hl ? yoff + lane * (int)slice : TAB_OOB);
+                    }
+                    __syncwarp();
+                }
 
-                // ---- cooperative staging: for query ql (warp-uniform) lane -> (row, piece) of its footprint, so
-                // consecutive lanes fetch consecutive 16-byte pieces of a row; the footprint origin of query ql
-                // comes from its owner lane by shuffle.  Pieces outside the map are zero-filled (src-size 0),
-                // pieces no tap touches are skipped.
+                // ---- cooperative staging: for query ql (the unrolled loop variable) lane -> (row, piece) of its footprint, so
+                // consecutive lanes fetch consecutive 16-byte pieces of a row; where the piece lives comes out of query
+                // ql's table.  Pieces outside the map are zero-filled (src-size 0), pieces no tap touches are skipped.
                 constexpr int PER_Q = NRB * NV;
                 constexpr int PASSES = (PER_Q + 31) / 32;
 #pragma unroll
@@ -132,19 +166,23 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                     const int v = slot - row * NV;
                     const bool slot_ok = slot < PER_Q;
                     float* dst0 = stage + slot * 4;
-#pragma unroll 4
-                    for (int ql = 0; ql < 32; ++ql) {
-                        const int qx = __shfl_sync(0xffffffffu, xs, ql);
-                        const int qp = __shfl_sync(0xffffffffu, packed, ql);
-                        const int y = (qp & 0xFFFFF) - 16 + row;
-                        const int x = qx + 4 * v;
-                        const bool need = slot_ok && row < (qp >> 26) && v < ((qp >> 20) & 63);
-                        const bool inb = (unsigned)y < (unsigned)Hl && (unsigned)x < (unsigned)Wl && ql < nq;
-                        const uint32_t off = !inb ? 0u
-                                             : TILED ? (uint32_t)((((y >> 2) * (Wl >> 3) + (x >> 3)) << 5) + ((y & 3) << 3) + (x & 7))
-                                                     : (uint32_t)(y * Wl + x);
-                        const float* src = vol_g + (size_t)(inb ? ql : 0) * slice + off;
-                        if (need) cp_async16_zfill(dst0 + ql * QS, src, inb ? 16u : 0u);
+                    {
+                        // one opaque 64-bit base: keeps the compiler from carrying (base, 64-bit index) pairs through every copy
+                        const float* vol_q = vol_g;
+                        asm volatile("" : "+l"(vol_q));
+                        // (lanes without a slot must still read inside the table)
+                        const int* ty = tab + (slot_ok ? row : 0);
+                        const int* tx = tab + NRB + (slot_ok ? v : 0);
+                        // fully unrolled where the band loop is short; many bands x 32 copies would outgrow the instruction cache
+                        constexpr int UNR = (NB * PASSES <= 2) ? 32 : 8;
+#pragma unroll UNR
+                        for (int ql = 0; ql < 32; ++ql) {
+                            const int t_y = ty[ql * TW], t_x = tx[ql * TW];
+                            const int t = t_y | t_x;
+                            const bool ok = t >= 0;
+                            const float* src = vol_q + (ok ? (uint32_t)(t_y + t_x) : 0u);
+                            if (slot_ok && !(t & 0x40000000)) cp_async16_zfill(dst0 + ql * QS, src, ok ? 16u : 0u);
+                        }
                     }
                 }
                 cp_async_wait_all();
@@ -502,7 +540,7 @@ static int grid_for(long long items, int wpb, size_t smem) {
 template <int R, int JB, bool TILED>
 static int launch_banded_l(const LookupParams& p, cudaStream_t st) {
     using Cfg = LookupCfg<R, JB>;
-    const size_t per_warp = (size_t)Cfg::WARP_WORDS * sizeof(float);
+    const size_t per_warp = (size_t)Cfg::WARP_WORDS_TAB * sizeof(float);
     // blocks of up to 4 warps, sized so that at least two blocks share an SM
     int wpb = (int)((110 * 1024) / per_warp);
     wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
@@ -539,7 +577,9 @@ static int corr_lookup_impl(const void* const* pyr_ptrs, const int* pyr_h, const
         p.vh[l] = pyr_h[l];
         p.vw[l] = pyr_w[l];
         p.vec_ok[l] = (pyr_w[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(pyr_ptrs[l]) & 15) == 0);
-        all_vec = all_vec && p.vec_ok[l];
+        // the banded kernels keep element offsets within a group's 32 slices in 30 bits (bits 31 / 30 of a table entry are
+        // flags): larger slices take the generic kernel
+        all_vec = all_vec && p.vec_ok[l] && (long long)pyr_h[l] * pyr_w[l] < (1LL << 25);
         if (tiled)
             PP_CHECK_ARG(pyr_w[l] % 8 == 0 && pyr_h[l] % 4 == 0 && p.vec_ok[l],
                          "pp_corr_lookup_tiled: level %d is %dx%d; tiled slices need H %% 4 == 0, W %% 8 == 0, 16-byte alignment", l,
@@ -571,9 +611,8 @@ static int corr_lookup_impl(const void* const* pyr_ptrs, const int* pyr_h, const
         }
     }
     if (all_vec) {
-        // Band height per radius and layout, from the sweeps in profiles/r2u_lookup_sweep*.json.  Row-major volumes want
-        // many warps per SM (small bands); tiled volumes want few bands (a band boundary cuts through tiles, whose lines
-        // are then requested twice) as long as 8-12 warps still fit.
+        // Band height per radius and layout, from the sweep in profiles/r2z_lookup_band_sweep.txt: taller bands amortise the
+        // x-interpolated row two taps share and cut fewer tiles twice, until the staged footprint costs occupancy.
         const bool t = p.tiled != 0;
         switch (radius) {
             case 1: return launch_banded<1, 3>(p, st);
@@ -582,11 +621,12 @@ static int corr_lookup_impl(const void* const* pyr_ptrs, const int* pyr_h, const
             case 4: return t ? launch_banded<4, 6>(p, st) : launch_banded<4, 5>(p, st);
             case 5: return launch_banded<5, 6>(p, st);
             case 6: return t ? launch_banded<6, 7>(p, st) : launch_banded<6, 5>(p, st);
-            case 7: return t ? launch_banded<7, 8>(p, st) : launch_banded<7, 5>(p, st);
-            case 8: return t ? launch_banded<8, 6>(p, st) : launch_banded<8, 3>(p, st);
+            case 7: return t ? launch_banded<7, 4>(p, st) : launch_banded<7, 5>(p, st);
+            case 8: return launch_banded<8, 6>(p, st);
             default: break;
         }
     }
+    PP_CHECK_ARG(!tiled, "pp_corr_lookup_tiled: slices of 2^25 elements or more are not supported in the tiled layout");
     // generic kernel: whole window staged at once
     p.nr_max = D + 2;
     p.nv_max = (D + 2 + 3 + 3) / 4;
