@@ -174,14 +174,24 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                         const int* ty = tab + (slot_ok ? row : 0);
                         const int* tx = tab + NRB + (slot_ok ? v : 0);
                         // fully unrolled where the band loop is short; many bands x 32 copies would outgrow the instruction cache
-                        constexpr int UNR = (NB * PASSES <= 2) ? 32 : 8;
+                        // eight queries at a time: their 16 table entries are loaded first, so the shared-memory latency is paid
+                        // once per batch and not once per copy
+                        constexpr int UNR = (NB * PASSES <= 2) ? 4 : 1;
 #pragma unroll UNR
-                        for (int ql = 0; ql < 32; ++ql) {
-                            const int t_y = ty[ql * TW], t_x = tx[ql * TW];
-                            const int t = t_y | t_x;
-                            const bool ok = t >= 0;
-                            const float* src = vol_q + (ok ? (uint32_t)(t_y + t_x) : 0u);
-                            if (slot_ok && !(t & 0x40000000)) cp_async16_zfill(dst0 + ql * QS, src, ok ? 16u : 0u);
+                        for (int q0 = 0; q0 < 32; q0 += 8) {
+                            int t_y[8], t_x[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                t_y[u] = ty[(q0 + u) * TW];
+                                t_x[u] = tx[(q0 + u) * TW];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int t = t_y[u] | t_x[u];
+                                const bool ok = t >= 0;
+                                const float* src = vol_q + (ok ? (uint32_t)(t_y[u] + t_x[u]) : 0u);
+                                if (slot_ok && !(t & 0x40000000)) cp_async16_zfill(dst0 + (q0 + u) * QS, src, ok ? 16u : 0u);
+                            }
                         }
                     }
                 }
@@ -194,7 +204,11 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                     // rows bb and bb + 1.  Same expressions as the general form below, so the results are bit-identical;
                     // 2 shared loads per (row, a) instead of 4 per (tap, a), no per-sample address arithmetic.
                     const float* win = stage + lane * QS - xs;
-                    const uint32_t obase = (uint32_t)(l * D * D) * (uint32_t)p.HW + (uint32_t)hw;
+                    // one 64-bit pointer per lane walks the channels k = a * D + j of tap row j (D * HW floats apart): a 64-bit
+                    // add per store.  (Opaque to the compiler, which otherwise either rebuilds the address from a uniform base
+                    // and a 64-bit index for every store or precomputes all D * D addresses into registers.)
+                    char* out_q = reinterpret_cast<char*>(out_b + ((size_t)(l * D * D) * (size_t)p.HW + (size_t)hw));
+                    const unsigned long long ostep = (unsigned long long)p.HW * (unsigned)(4 * D);
                     float hp[D], hc[D], wx0[D];
 #pragma unroll
                     for (int a = 0; a < D; ++a) {
@@ -206,30 +220,40 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                         const int j = j0 + bb;
                         if (j < j1) {
                             const float wy1 = yw[j], wy0 = __fsub_rn(1.0f, wy1);
+                            char* op = out_q + (unsigned long long)p.HW * (unsigned)(4 * j);
 #pragma unroll
                             for (int a = 0; a < D; ++a) {
                                 hc[a] = fmaf(win[(bb + 1) * PITCH + xo[a] + 1], xw[a], win[(bb + 1) * PITCH + xo[a]] * wx0[a]);
-                                __stcs(out_b + (obase + (uint32_t)(a * D + j) * (uint32_t)p.HW), fmaf(hc[a], wy1, hp[a] * wy0));
+                                asm volatile("" : "+l"(op));
+                                __stcs(reinterpret_cast<float*>(op), fmaf(hc[a], wy1, hp[a] * wy0));
+                                op += ostep;
                                 hp[a] = hc[a];
                             }
                         }
                     }
                 } else if (live) {
                     const float* win = stage + lane * QS;
-                    const uint32_t obase = (uint32_t)(l * D * D) * (uint32_t)p.HW + (uint32_t)hw;
+                    // one 64-bit pointer per lane walks the channels k = a * D + j of tap row j (D * HW floats apart): a 64-bit
+                    // add per store.  (Opaque to the compiler, which otherwise either rebuilds the address from a uniform base
+                    // and a 64-bit index for every store or precomputes all D * D addresses into registers.)
+                    char* out_q = reinterpret_cast<char*>(out_b + ((size_t)(l * D * D) * (size_t)p.HW + (size_t)hw));
+                    const unsigned long long ostep = (unsigned long long)p.HW * (unsigned)(4 * D);
 #pragma unroll
                     for (int bb = 0; bb < JB; ++bb) {
                         const int j = j0 + bb;
                         if (j < j1) {
                             const float wy1 = yw[j], wy0 = __fsub_rn(1.0f, wy1);
                             const float* rowp = win + (yo[j] - yb) * PITCH - xs;
+                            char* op = out_q + (unsigned long long)p.HW * (unsigned)(4 * j);
 #pragma unroll
                             for (int a = 0; a < D; ++a) {
                                 const float* t0 = rowp + xo[a];
                                 const float wx1 = xw[a], wx0 = __fsub_rn(1.0f, wx1);
                                 const float h0 = fmaf(t0[1], wx1, t0[0] * wx0);
                                 const float h1 = fmaf(t0[PITCH + 1], wx1, t0[PITCH] * wx0);
-                                __stcs(out_b + (obase + (uint32_t)(a * D + j) * (uint32_t)p.HW), fmaf(h1, wy1, h0 * wy0));
+                                asm volatile("" : "+l"(op));
+                                __stcs(reinterpret_cast<float*>(op), fmaf(h1, wy1, h0 * wy0));
+                                op += ostep;
                             }
                         }
                     }
