@@ -107,13 +107,24 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
             const float lx = __fmul_rn(cx, inv), ly = __fmul_rn(cy, inv);
             int xo[D], yo[D], yraw[D];
             float xw[D], yw[D];
+            // Regular in x: tap a sits exactly a columns right of tap 0 (before clamping; true for all but ~1e-5 of the
+            // windows).  The footprint is then staged from the UNCLAMPED origin -- columns outside the map are zero-filled,
+            // which is what the clamped taps read anyway -- and a staged row is D + 1 consecutive values from column c0.
+            bool regx = true;
+            int xraw0 = 0;
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                axis_tap(__fadd_rn(lx, (float)(a - R)), Wl, xo[a], xw[a]);
+                int xraw;
+                axis_tap_raw(__fadd_rn(lx, (float)(a - R)), Wl, xo[a], xw[a], xraw);
+                if (a == 0) xraw0 = xraw;
+                regx = regx && (xraw == xraw0 + a);
                 axis_tap_raw(__fadd_rn(ly, (float)(a - R)), Hl, yo[a], yw[a], yraw[a]);
             }
-            const int xs = xo[0] & ~3;                        // two's complement: rounds towards -inf
-            const int pieces = ((xo[D - 1] + 1 - xs) >> 2) + 1;  // 16-byte pieces per row some tap touches
+            const int xb = regx ? min(max(xraw0, -(D + 2)), Wl) : xo[0];
+            const int xs = xb & ~3;                           // two's complement: rounds towards -inf
+            const int c0 = xb - xs;                           // regular: column of tap 0 in the staged row (0..3)
+            // 16-byte pieces per row some tap touches
+            const int pieces = regx ? ((c0 + D) >> 2) + 1 : ((xo[D - 1] + 1 - xs) >> 2) + 1;
             // slice base of the group's first query; query ql of the group is ql slices further
             const float* vol_g = p.vol[l] + ((size_t)b * p.HW + hw0) * ((size_t)Hl * Wl);
             const uint32_t slice = (uint32_t)Hl * (uint32_t)Wl;
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                 for (int bb = 1; bb < j1 - j0; ++bb) regular = regular && (yraw[j0 + bb] == yraw[j0] + bb);
                 const int yb = regular ? min(max(yraw[j0], -(JB + 1)), Hl) : yo[j0];
                 const int rows = regular ? (j1 - j0) + 1 : yo[j1 - 1] + 1 - yb + 1;
-                const bool warp_regular = __all_sync(0xffffffffu, regular || !live);
+                const bool warp_regular = __all_sync(0xffffffffu, (regular && regx) || !live);
                 __syncwarp();  // previous band's readers are done with the staging area
                 {
 #pragma unroll
@@ -202,18 +213,21 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                 if (live && warp_regular) {
                     // rows once: h[rr][a] = lerp_x(row yb + rr) is shared by the two taps that touch row rr; tap bb blends
                     // rows bb and bb + 1.  Same expressions as the general form below, so the results are bit-identical;
-                    // 2 shared loads per (row, a) instead of 4 per (tap, a), no per-sample address arithmetic.
-                    const float* win = stage + lane * QS - xs;
+                    // D + 1 shared loads per row (neighbouring taps share a column) instead of 4 per (tap, a), no per-sample
+                    // address arithmetic.
+                    const float* win = stage + lane * QS + c0;
                     // one 64-bit pointer per lane walks the channels k = a * D + j of tap row j (D * HW floats apart): a 64-bit
                     // add per store.  (Opaque to the compiler, which otherwise either rebuilds the address from a uniform base
                     // and a 64-bit index for every store or precomputes all D * D addresses into registers.)
                     char* out_q = reinterpret_cast<char*>(out_b + ((size_t)(l * D * D) * (size_t)p.HW + (size_t)hw));
                     const unsigned long long ostep = (unsigned long long)p.HW * (unsigned)(4 * D);
-                    float hp[D], hc[D], wx0[D];
+                    float hp[D], hc[D], wx0[D], v[D + 1];
+#pragma unroll
+                    for (int k = 0; k <= D; ++k) v[k] = win[k];
 #pragma unroll
                     for (int a = 0; a < D; ++a) {
                         wx0[a] = __fsub_rn(1.0f, xw[a]);
-                        hp[a] = fmaf(win[xo[a] + 1], xw[a], win[xo[a]] * wx0[a]);
+                        hp[a] = fmaf(v[a + 1], xw[a], v[a] * wx0[a]);
                     }
 #pragma unroll
                     for (int bb = 0; bb < JB; ++bb) {
@@ -222,8 +236,10 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
                             const float wy1 = yw[j], wy0 = __fsub_rn(1.0f, wy1);
                             char* op = out_q + (unsigned long long)p.HW * (unsigned)(4 * j);
 #pragma unroll
+                            for (int k = 0; k <= D; ++k) v[k] = win[(bb + 1) * PITCH + k];
+#pragma unroll
                             for (int a = 0; a < D; ++a) {
-                                hc[a] = fmaf(win[(bb + 1) * PITCH + xo[a] + 1], xw[a], win[(bb + 1) * PITCH + xo[a]] * wx0[a]);
+                                hc[a] = fmaf(v[a + 1], xw[a], v[a] * wx0[a]);
                                 asm volatile("" : "+l"(op));
                                 __stcs(reinterpret_cast<float*>(op), fmaf(hc[a], wy1, hp[a] * wy0));
                                 op += ostep;
