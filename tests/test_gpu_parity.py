@@ -252,6 +252,35 @@ def test_sampling_modes_golden():
     _lib.check_device_faults()
 
 
+def test_corr_lookup_other_modes_on_our_pyramid_types():
+    """CorrLookup configured with a mode the tuned kernels do not cover still accepts what our CorrelationPyramid hands
+    out (a lazy pyramid, a tiled pyramid): it materialises the reference's row-major volumes and samples them with
+    pp_grid_sample; and pp_grid_sample(bilinear, zeros) is the tuned kernel, bit for bit."""
+    from picopose_b200 import _lib as L
+    from picopose_b200.corr_lookup import CorrLookup, bilinear_sample
+    from picopose_b200.correlation import LazyCorrelationPyramid, correlation_pyramid
+    gen = torch.Generator().manual_seed(91)
+    f1, f2 = torch.randn(2, 64, 16, 16, generator=gen), torch.randn(2, 64, 16, 16, generator=gen)
+    flow = 2.5 * torch.randn(2, 2, 16, 16, generator=gen)
+    ref_pyr = OL.correlation_pyramid(f1, f2, 2)
+    for mode, pad, ac in (("nearest", "border", True), ("bilinear", "reflection", False), ("bicubic", "zeros", True)):
+        ref = OL.corr_lookup_general(ref_pyr, flow, 3, mode, pad, ac).numpy()
+        look = CorrLookup(3, mode, pad, ac)
+        lazy = LazyCorrelationPyramid(f1.to(DEV), f2.to(DEV), 2)
+        tiled = correlation_pyramid(f1.to(DEV), f2.to(DEV), 2, layout="tiled")
+        for pyr in (lazy, tiled, [v.to(DEV) for v in ref_pyr]):
+            out = look(pyr, flow.to(DEV))
+            np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-4, err_msg=f"{mode} {pad} {ac} {type(pyr).__name__}")
+    feat = torch.randn(2, 5, 9, 7, generator=gen).to(DEV)
+    grid = (torch.rand(2, 6, 4, 2, generator=gen) * 12 - 2).to(DEV)
+    tuned = bilinear_sample(feat, grid, align_corners=True)
+    out = torch.empty_like(tuned)
+    lib = L.load()
+    L.check(lib.pp_grid_sample(L.ptr(feat), L.ptr(grid), 2, 5, 9, 7, 6, 4, 0, 1, 1, 0, 0, L.ptr(out), L.stream_of(feat)), "pp_grid_sample")
+    assert torch.equal(out, tuned)
+    L.check_device_faults()
+
+
 def test_nonfinite_flows_propagate_like_grid_sample():
     """A NaN / infinite flow makes every tap weight of that query NaN in F.grid_sample, so the reference returns NaN for
     the query's whole window (all levels whose coordinate is non-finite); a finite far-away flow is padding.  Reference
