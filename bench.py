@@ -409,12 +409,18 @@ def config_blocks(args, dev, world, rank, dist):
               1.5 * torch.randn(min(chunk, len(my)), 2, 1, 1, device=dev, generator=g)
               + 0.5 * torch.randn(min(chunk, len(my)), 2, h, h, device=dev, generator=g), L) for h, L in ladder]
 
+    from picopose_b200.corr_lookup import CorrLookup
+    from picopose_b200.correlation import LazyCorrelationPyramid
+    look3 = CorrLookup(radius=r3)
+
     def stage3():
-        # the same synthetic feature chunk stands for every chunk of this rank's detections (values do not change the work)
+        # the same synthetic feature chunk stands for every chunk of this rank's detections (values do not change the work);
+        # CorrelationPyramid -> CorrLookup as FlowDecoder calls them: the library picks, per level of the ladder, the
+        # no-volume kernel or pyramid + lookup on tiled volumes (LazyCorrelationPyramid.fusable)
         for c0 in range(0, len(my), chunk):
             n = min(chunk, len(my) - c0)
             for f1, f2, fl, L in feats:
-                windowed_correlation(f1[:n], f2[:n], fl[:n], L, r3)
+                look3(LazyCorrelationPyramid(f1[:n], f2[:n], L), fl[:n])
 
     stage3()
     barrier()
@@ -431,7 +437,7 @@ def config_blocks(args, dev, world, rank, dist):
     ms1, ms3 = [float(x) for x in t.tolist()]
     out["config4"] = {
         "workload": "configs[4]: %d detections x %d views stage-1 ranking (as config2) + stage-3 correlation lookups of every "
-                    "detection's top-1 hypothesis on the ladder %s, C=%d, r=%d, fused CorrelationPyramid+CorrLookup (no volume), "
+                    "detection's top-1 hypothesis on the ladder %s, C=%d, r=%d, CorrelationPyramid -> CorrLookup (no-volume kernel at 16^2 and 64^2, tiled volumes at 32^2), "
                     "detections sharded x%d" % (D4, N, "/".join("%d^2xL%d" % (h, L) for h, L in ladder), Cf, r3, world),
         "n_gpus": world, "stage1_ms": ms1, "stage3_ms": ms3, "detections_per_s": D4 * 1e3 / (ms1 + ms3),
         "stage1_detections_per_s": D4 * 1e3 / ms1, "top1_recovered": ok4,

@@ -262,7 +262,14 @@ class LazyCorrelationPyramid(Sequence):
         return self.materialise()
 
     def fusable(self, radius: int) -> bool:
+        """Whether CorrLookup(radius) should take the no-volume path.  Radius 1-2 has the TMA-tiled kernel and always does;
+        from radius 3 on only the per-query kernel exists, which loses to pyramid + lookup on mid-sized maps (16 x 256 x
+        32^2, L=2, r=4: 0.29 ms against 0.13 ms; at 64^2 the two are level, 1.2 ms, and the volume would be 84 MB per sample;
+        at 16^2 both are launch-bound -- profiles/r2f_stage3_r4.json), so those materialise their (small) volumes."""
         Cc = self.feat1.shape[1]
+        H, W = self.feat1.shape[-2:]
+        if radius >= 3 and 512 <= H * W <= 2048:
+            return False
         return (self._volumes is None and 1 <= radius <= 8 and Cc % 4 == 0 and Cc <= 2048
                 and self.num_levels * (2 * radius + 1) ** 2 * 33 * 4 + 8 * Cc * 4 < 190 * 1024)
 

@@ -256,3 +256,17 @@ def test_peer_gather_buffer_layout():
             base = lay["flag_bytes"] + par * lay["parity_bytes"]
             assert base + (world - 1) * tar_b + tar_b <= base + lay["mask_off"]
             assert base + lay["mask_off"] + world * mask_b <= lay["flag_bytes"] + (par + 1) * lay["parity_bytes"]
+
+
+def test_lookup_path_choice_by_radius_and_map_size():
+    """CorrLookup on a lazy pyramid: radius 1-2 always takes the no-volume path (TMA-tiled kernel); from radius 3 on the
+    per-query kernel is only chosen where it is not slower than pyramid + lookup (launch-bound 16^2, memory-heavy 64^2)."""
+    from picopose_b200.correlation import LazyCorrelationPyramid
+    def lazy(h, L):
+        return LazyCorrelationPyramid(torch.zeros(1, 256, h, h), torch.zeros(1, 256, h, h), L)
+    for h, L in ((16, 1), (32, 2), (64, 3)):
+        assert lazy(h, L).fusable(1) and lazy(h, L).fusable(2)
+    assert lazy(16, 1).fusable(4) and lazy(64, 3).fusable(4)
+    assert not lazy(32, 2).fusable(4) and not lazy(32, 2).fusable(3)
+    assert not lazy(64, 3).fusable(9)
+
