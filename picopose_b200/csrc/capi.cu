@@ -65,6 +65,11 @@ int require_sm100() {
     return PP_OK;
 }
 
+bool pdl_enabled() {
+    const char* e = getenv("PICOPOSE_B200_PDL");
+    return !(e && e[0] == '0');
+}
+
 int sm_count() {
     int dev;
     if (probe_device(&dev)) return 148;

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(128) corr_lookup_banded_kernel(const LookupPar
     const int lane = threadIdx.x & 31;
     float* stage = smem + (size_t)warp * Cfg::WARP_WORDS_TAB;
     int* tab = reinterpret_cast<int*>(stage + Cfg::WARP_WORDS);  // [32 queries][TW] offset tables
+    grid_dependency_wait();  // flow and volumes may come from the kernel launched just before (programmatic dependent launch)
 
     // work item = (query group, pyramid level): levels of one group run on different warps, which keeps the
     // dependent chain per warp short when there are few queries (the native 16^2..64^2 ladder)
@@ -586,7 +587,8 @@ static int launch_banded_l(const LookupParams& p, cudaStream_t st) {
     wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
     const size_t smem = per_warp * wpb;
     PP_CUDA(cudaFuncSetAttribute(corr_lookup_banded_kernel<R, JB, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_lookup_banded_kernel<R, JB, TILED><<<grid_for((long long)p.total_groups * p.L, wpb, smem), wpb * 32, smem, st>>>(p);
+    PP_CUDA(launch_dependent(corr_lookup_banded_kernel<R, JB, TILED>, dim3(grid_for((long long)p.total_groups * p.L, wpb, smem)),
+                             dim3(wpb * 32), smem, st, p));
     PP_LAUNCHED();
     return PP_OK;
 }

@@ -254,6 +254,7 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     } else if (warp == 3 && tabs) {
         // live rows and launch order of every detection; tile mode: inclusive scan of the per-detection tile counts,
         // 32 detections per step
+        grid_dependency_wait();  // tv / det_order come from the kernels before this one
         uint32_t run = 0;
         if (lane == 0) tile_prefix[0] = 0;
         for (int b0 = 0; b0 < p.B; b0 += 32) {
@@ -280,6 +281,9 @@ match_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t num_groups = (MATCH && p.tile_mode) ? tile_prefix[p.B] : p.num_groups;
+    // programmatic dependent launch: barrier set-up and the TMEM allocation above overlap the tail of the previous kernel;
+    // operands, norms and masks are only touched from here on
+    grid_dependency_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA) =====================
@@ -664,13 +668,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     const bool prof = take_profile_events(&ev0, &ev1);
     if (prof) PP_CUDA(cudaEventRecord(ev0, st));

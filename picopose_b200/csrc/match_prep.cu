@@ -71,6 +71,9 @@ match_prepare_kernel(const float* __restrict__ feats, int C, int P, int Kp, int 
     const int g = blockIdx.y;
     const int p0 = blockIdx.x * PREP_PT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // programmatic dependent launch (bank instance): nothing is read or written before the previous kernel on the stream --
+    // which may have produced the features, or may still be reading this call's output buffers -- has completed
+    grid_dependency_wait();
     int tv_total = 0;
     if (QM) {
         if (qm.clear) {
@@ -295,9 +298,17 @@ extern "C" int pp_match_prepare(const float* feats, int64_t G, int C, int P, int
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(prepared) + (size_t)g0 * P * Kp;
         float* rn = rnorm + (size_t)g0 * P;
         const QueryMaskArgs none{};
-        if (nparts == 1) match_prepare_kernel<1, false><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, none);
-        else if (nparts == 2) match_prepare_kernel<2, false><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, none);
-        else match_prepare_kernel<3, false><<<grid, PREP_THREADS, 0, st>>>(f, C, P, Kp, nseg, is_query, o, rn, none);
+        const float* no_feats2 = nullptr;
+        const int no_split = 0x7fffffff;
+        if (nparts == 1)
+            PP_CUDA(launch_dependent(match_prepare_kernel<1, false>, grid, dim3(PREP_THREADS), 0, st, f, C, P, Kp, nseg, is_query, o, rn,
+                                     none, no_feats2, no_split));
+        else if (nparts == 2)
+            PP_CUDA(launch_dependent(match_prepare_kernel<2, false>, grid, dim3(PREP_THREADS), 0, st, f, C, P, Kp, nseg, is_query, o, rn,
+                                     none, no_feats2, no_split));
+        else
+            PP_CUDA(launch_dependent(match_prepare_kernel<3, false>, grid, dim3(PREP_THREADS), 0, st, f, C, P, Kp, nseg, is_query, o, rn,
+                                     none, no_feats2, no_split));
         PP_LAUNCHED();
     }
     return PP_OK;

@@ -47,6 +47,7 @@ finalize_scores_kernel(const unsigned long long* __restrict__ rowkey, const unsi
                        int* __restrict__ fault) {
     const size_t bn = blockIdx.x;
     const int b = (int)(bn / N);
+    grid_dependency_wait();  // the keys come from the contraction launched just before (programmatic dependent launch)
     if (bn == 0 && bank_of_det) {
         // range check of the caller's bank indices (the contraction clamps them in its loads): an index outside
         // [0, n_banks) is reported through the fault record (code 6), never trapped
@@ -346,9 +347,9 @@ static int match_scores_impl(const void* q_prep, const float* q_rnorm, const voi
         if (smem > 48 * 1024)
             PP_CUDA(cudaFuncSetAttribute(finalize_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    finalize_scores_kernel<<<(unsigned)((size_t)B * N), 256, smem, st>>>(
-        rowkey, colkey, qm.mrow, q_rnorm, qm.rank, qm.fm, N, T, 1.0f / (float)(H * H), sim_avg, score_t2s, idx_t2s, idx_s2t,
-        mutual_nn, k, done, topk_score, reinterpret_cast<long long*>(topk_idx), bank_of_det, B, (int)n_banks, fault);
+    PP_CUDA(launch_dependent(finalize_scores_kernel, dim3((unsigned)((size_t)B * N)), dim3(256), smem, st, rowkey, colkey, qm.mrow,
+                             q_rnorm, qm.rank, qm.fm, N, T, 1.0f / (float)(H * H), sim_avg, score_t2s, idx_t2s, idx_s2t, mutual_nn, k,
+                             done, topk_score, reinterpret_cast<long long*>(topk_idx), bank_of_det, B, (int)n_banks, fault));
     PP_LAUNCHED();
     return PP_OK;
 }

@@ -69,6 +69,27 @@ struct WConv {
 int require_sm100();
 int sm_count();
 
+// Programmatic dependent launch: a kernel launched through launch_dependent() may be scheduled while the kernel before it
+// on the stream is still draining, so its launch latency and its own prologue overlap that tail; the data dependency is
+// kept by the kernel itself, which calls grid_dependency_wait() before it touches anything the predecessor wrote (a no-op
+// when there is no programmatic edge).  PICOPOSE_B200_PDL=0 launches plainly.
+bool pdl_enabled();
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- small device helpers -----------------------------------------------------------------
 // Monotone map float -> uint32 (a < b  <=>  ord(a) < ord(b)); -0.0 must be canonicalised first.
 __device__ __forceinline__ uint32_t f32_ord(float v) {
