@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(128) bilinear_sample_kernel(const float* __res
                                                               int align_corners, int scale, float* __restrict__ out) {
     const long long total = (long long)N * Ho * Wo;
     const int c0 = blockIdx.y * BS_CPT;
+    grid_dependency_wait();  // programmatic dependent launch
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i / ((long long)Ho * Wo));
@@ -708,8 +709,8 @@ extern "C" int pp_bilinear_sample(const float* feat, const float* grid, int N, i
     int grid_dim = (int)((total + 127) / 128);
     const int cap = sm_count() * 64;
     if (grid_dim > cap) grid_dim = cap;
-    bilinear_sample_kernel<<<dim3(grid_dim, (C + BS_CPT - 1) / BS_CPT), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        feat, grid, N, C, Hf, Wf, Ho, Wo, grid_chw, align_corners, scale, out);
+    PP_CUDA(launch_dependent(bilinear_sample_kernel, dim3(grid_dim, (C + BS_CPT - 1) / BS_CPT), dim3(128), 0,
+                             static_cast<cudaStream_t>(stream), feat, grid, N, C, Hf, Wf, Ho, Wo, grid_chw, align_corners, scale, out));
     PP_LAUNCHED();
     return PP_OK;
 }

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) wcorr_prepare_patch_kernel(const WPatchAr
     __shared__ __align__(16) float s1[4 * (WP_COLS / 2)][WP_PITCH];    // level 1
     __shared__ __align__(16) float s2[2 * (WP_COLS / 4)][WP_PITCH];    // level 2
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    grid_dependency_wait();  // programmatic dependent launch: the features come from the kernel before this one
     const int which = blockIdx.z / a.N, n = blockIdx.z - which * a.N;
     const int py0 = (blockIdx.x / a.patches_x) * 8, px0 = (blockIdx.x % a.patches_x) * WP_COLS;
     const int c0 = blockIdx.y * WP_CH;
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(WC_WARPS * 32) windowed_corr_kernel(const WCor
     int* s_yo = s_xo + D;
     float* s_xw = reinterpret_cast<float*>(s_yo + D);
     float* s_yw = s_xw + D;
+    grid_dependency_wait();  // programmatic dependent launch: the layout pass before this kernel wrote what it reads
 
     const int n = blockIdx.x / p.groups_per_n;
     const int hw0 = (blockIdx.x - n * p.groups_per_n) * WC_QUERIES;
@@ -313,7 +315,7 @@ static int launch_wcorr_cv(const WCorrParams& p, cudaStream_t st) {
     const size_t smem = words * sizeof(float);
     PP_CHECK_ARG(smem <= 200 * 1024, "pp_windowed_correlation: %zu bytes of shared memory needed (levels x window too large)", smem);
     PP_CUDA(cudaFuncSetAttribute(windowed_corr_kernel<R, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    windowed_corr_kernel<R, CV><<<p.N * p.groups_per_n, WC_WARPS * 32, smem, st>>>(p);
+    PP_CUDA(launch_dependent(windowed_corr_kernel<R, CV>, dim3(p.N * p.groups_per_n), dim3(WC_WARPS * 32), smem, st, p));
     PP_LAUNCHED();
     return PP_OK;
 }
@@ -382,7 +384,7 @@ extern "C" int pp_windowed_correlation_prepare_all(const float* feat1, const flo
             a.W = W;
             a.patches_x = (W + WP_COLS - 1) / WP_COLS;
             dim3 grid(a.patches_x * ((H + 7) / 8), (C + WP_CH - 1) / WP_CH, 2 * N);
-            wcorr_prepare_patch_kernel<<<grid, 256, 0, st>>>(a);
+            PP_CUDA(launch_dependent(wcorr_prepare_patch_kernel, grid, dim3(256), 0, st, a));
             PP_LAUNCHED();
             return PP_OK;
         }

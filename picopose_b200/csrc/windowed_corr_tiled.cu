@@ -204,6 +204,9 @@ windowed_corr_tiled_kernel(const __grid_constant__ WTileMaps maps, const WTilePa
     }
     if (tid == 32) *s_nslow = 0;
     __syncthreads();
+    // programmatic dependent launch: the barrier set-up above overlaps the tail of the layout pass, whose key maps (and the
+    // caller's flow) are only read from here on
+    grid_dependency_wait();
 
     // ---- taps and window extents of every level; per level the tile's mean window and the box around all windows ----
     int q_hw[QPW];
@@ -511,7 +514,7 @@ int launch(const WTileMaps& maps, const WTileParams& p, cudaStream_t st) {
     const size_t smem = WT<R>::smem_bytes(p.L);
     auto kern = windowed_corr_tiled_kernel<R>;
     PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<p.N * p.tiles_x * p.tiles_y, WT_THREADS, smem, st>>>(maps, p);
+    PP_CUDA(launch_dependent(kern, dim3(p.N * p.tiles_x * p.tiles_y), dim3(WT_THREADS), smem, st, maps, p));
     PP_LAUNCHED();
     return PP_OK;
 }
