@@ -51,6 +51,7 @@ SIGNATURES = {
     "pp_xchg_close": (_i, [_vp]),
     "pp_xchg_destroy": (_i, [_vp]),
     "pp_xchg_push": (_i, [_vp, _sz, _vp, _i, _sz, _vp]),
+    "pp_xchg_push_signal": (_i, [_vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp, _sz, _i, _i, C.c_uint32, _vp]),
     "pp_xchg_signal": (_i, [_vp, _sz, _i, _i, C.c_uint32, _vp]),
     "pp_xchg_wait": (_i, [_vp, _sz, _i, C.c_uint32, _vp]),
     "pp_topk_exchange": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _i, C.c_uint32, _vp, _vp, _vp]),

@@ -16,8 +16,10 @@
 // never collide.
 #include "pp_common.cuh"
 
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace pp {
 
@@ -187,6 +189,24 @@ __global__ void xchg_signal_kernel(char* const* __restrict__ peers, size_t flag_
         *flag = epoch;
     }
 }
+// The same flag write with a small payload in front of it (the query masks of a gather, a few KB): the block stores the
+// payload into every peer's buffer with plain 16-byte stores through the peer mapping, fences, and only then raises the
+// flags -- world fewer copy-engine transfers on the chain a gather has to finish within one step.
+__global__ void __launch_bounds__(256)
+xchg_signal_payload_kernel(char* const* __restrict__ peers, size_t flag_off, int rank, int world, unsigned epoch,
+                           const uint4* __restrict__ src, unsigned n16, size_t dst_off) {
+    for (int p = 0; p < world; ++p) {
+        uint4* dst = reinterpret_cast<uint4*>(peers[p] + dst_off);
+        for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(peers[threadIdx.x] + flag_off) + rank;
+        *flag = epoch;
+    }
+}
 __global__ void xchg_wait_kernel(const char* __restrict__ own, size_t flag_off, int world, unsigned epoch,
                                  unsigned long long timeout_ns, int* __restrict__ fault) {
     if ((int)threadIdx.x < world) {
@@ -212,6 +232,86 @@ extern "C" int pp_xchg_push(const void* src, size_t bytes, const void* const* pe
     for (int p = 0; p < world; ++p)
         PP_CUDA(cudaMemcpyAsync(static_cast<char*>(const_cast<void*>(peers_host[p])) + dst_offset, src, bytes,
                                 cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return PP_OK;
+}
+
+// Optional fan-out of the bulk copies (PICOPOSE_B200_PUSH_STREAMS = n > 1; default 1 = all on the caller's stream):
+// copies issued on one stream run one after the other, and a gather at 8 GPUs is 8 x 4 MB of them behind a host upload,
+// all of which has to fit into one 0.4 ms step.  With n > 1 they are dealt over n internal non-blocking streams per
+// device (fork / join with events on the caller's stream).  Measured (tools/microbench/push_chain.py,
+// profiles/r2i_push_chain.md): on an idle GPU the 8-copy chain takes 86 us either way (one stream already fills the
+// link); with the copy engines busy 4 streams take 328 us against 398 us; inside bench.py --gpus 2 the fork / join costs
+// 4-8 % of the end-to-end rate.  Hence off by default.
+namespace pp {
+constexpr int kMaxPushStreams = 8;
+struct PushLanes {
+    int n = 0;     // 0 = not created yet, < 0 = creation failed (stay on the caller's stream)
+    cudaStream_t st[kMaxPushStreams];
+    cudaEvent_t fork, join[kMaxPushStreams];
+};
+static int push_lanes_wanted() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("PICOPOSE_B200_PUSH_STREAMS");
+        int n = e ? atoi(e) : 1;
+        cached = n < 1 ? 1 : (n > kMaxPushStreams ? kMaxPushStreams : n);
+    }
+    return cached;
+}
+static PushLanes* push_lanes() {
+    static PushLanes lanes[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    PushLanes& l = lanes[dev];
+    if (l.n == 0) {
+        const int want = push_lanes_wanted();
+        bool ok = cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < want; ++i)
+            ok = cudaStreamCreateWithFlags(&l.st[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&l.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+        l.n = ok ? want : -1;
+    }
+    return l.n > 0 ? &l : nullptr;
+}
+}  // namespace pp
+
+extern "C" int pp_xchg_push_signal(const void* src, size_t bytes, size_t dst_offset, const void* payload,
+                                   size_t payload_bytes, size_t payload_offset, const void* const* peers_host,
+                                   const void* const* peers_dev, size_t flag_offset, int rank, int world, uint32_t epoch,
+                                   void* stream) {
+    using namespace pp;
+    PP_CHECK_ARG(src && peers_host && peers_dev && world > 0 && world <= 256 && rank >= 0 && rank < world && epoch != 0,
+                 "pp_xchg_push_signal: bad arguments");
+    PP_CHECK_ARG(payload_bytes == 0 || (payload && payload_bytes % 16 == 0 && payload_offset % 16 == 0 &&
+                                        reinterpret_cast<uintptr_t>(payload) % 16 == 0 && payload_bytes <= (size_t)1 << 24),
+                 "pp_xchg_push_signal: the payload must be 16-byte aligned and at most 16 MB");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PushLanes* lanes = push_lanes_wanted() > 1 && world > 1 ? push_lanes() : nullptr;
+    if (lanes) {
+        static std::mutex issue_mu;                         // the events are per device, not per caller
+        std::lock_guard<std::mutex> lock(issue_mu);
+        const int n = lanes->n < world ? lanes->n : world;
+        PP_CUDA(cudaEventRecord(lanes->fork, st));
+        for (int i = 0; i < n; ++i) PP_CUDA(cudaStreamWaitEvent(lanes->st[i], lanes->fork, 0));
+        for (int p = 0; p < world; ++p) {
+            const int q = (rank + 1 + p) % world;          // start with the neighbour: ranks do not all hit peer 0 first
+            PP_CUDA(cudaMemcpyAsync(static_cast<char*>(const_cast<void*>(peers_host[q])) + dst_offset, src, bytes,
+                                    cudaMemcpyDeviceToDevice, lanes->st[p % n]));
+        }
+        for (int i = 0; i < n; ++i) {
+            PP_CUDA(cudaEventRecord(lanes->join[i], lanes->st[i]));
+            PP_CUDA(cudaStreamWaitEvent(st, lanes->join[i], 0));
+        }
+    } else {
+        if (int rc = pp_xchg_push(src, bytes, peers_host, world, dst_offset, stream)) return rc;
+    }
+    xchg_signal_payload_kernel<<<1, 256, 0, st>>>(reinterpret_cast<char* const*>(const_cast<void* const*>(peers_dev)),
+                                                  flag_offset, rank, world, epoch, static_cast<const uint4*>(payload),
+                                                  (unsigned)(payload_bytes / 16), payload_offset);
+    PP_LAUNCHED();
     return PP_OK;
 }
 

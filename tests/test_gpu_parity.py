@@ -1074,15 +1074,20 @@ def test_topk_exchange_three_ranks_on_one_gpu():
             lib.pp_xchg_destroy(b)
 
 
-def test_peer_gather_primitives_two_ranks_on_one_gpu():
-    """pp_xchg_push / pp_xchg_signal / pp_xchg_wait with two 'ranks' on one GPU (two buffers, two streams): every rank
-    copies its slice into slot [rank] of both buffers, flags it, and waits for both flags of its own buffer; afterwards
-    both buffers hold both slices.  Two epochs, flags at different offsets (the two parities)."""
+@pytest.mark.parametrize("form", ["push+signal", "push_signal"])
+def test_peer_gather_primitives_two_ranks_on_one_gpu(form):
+    """pp_xchg_push / pp_xchg_signal / pp_xchg_wait, and the one-call form pp_xchg_push_signal (copies dealt over the
+    library's push streams, a small payload stored by the flag kernel), with two 'ranks' on one GPU (two buffers, two
+    streams): every rank copies its slice into slot [rank] of both buffers (and its payload into payload slot [rank]),
+    flags it, and waits for both flags of its own buffer; afterwards both buffers hold both slices and both payloads.
+    Three epochs, flags at different offsets (the two parities), the first parity reused."""
     import ctypes as C
+    from picopose_b200.sharded import _DeviceView
     lib = _lib.load()
-    world, n = 2, 4096
-    flag_bytes, slot = 256, n * 4
-    nbytes = flag_bytes + world * slot
+    world, n, npay = 2, 4096, 1024
+    flag_bytes, slot, pslot = 256, n * 4, npay * 4
+    pay_off = flag_bytes + world * slot
+    nbytes = pay_off + world * pslot
     bufs = []
     for _ in range(world):
         buf, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -1092,22 +1097,41 @@ def test_peer_gather_primitives_two_ranks_on_one_gpu():
     peers_dev = torch.tensor(bufs, dtype=torch.int64, device=DEV)
     streams = [torch.cuda.Stream(device=DEV) for _ in range(world)]
     try:
-        for epoch in (1, 2):
+        for epoch in (1, 2, 3):
             par = epoch & 1
             slices = [torch.full((n,), float(10 * epoch + r), device=DEV) for r in range(world)]
+            pays = [torch.arange(npay, device=DEV, dtype=torch.float32) + 1000 * epoch + 100 * r for r in range(world)]
             torch.cuda.synchronize()
             for r in range(world):                       # every rank's pushes and flags first, then the waits: no
                 st = streams[r].cuda_stream              # ordering of the streams can make a wait starve a push
+                if form == "push_signal":
+                    _lib.check(lib.pp_xchg_push_signal(_lib.ptr(slices[r]), slot, flag_bytes + r * slot, _lib.ptr(pays[r]), pslot,
+                                                       pay_off + r * pslot, peers_host, _lib.ptr(peers_dev), par * world * 4,
+                                                       r, world, epoch, st), "pp_xchg_push_signal")
+                    continue
                 _lib.check(lib.pp_xchg_push(_lib.ptr(slices[r]), slot, peers_host, world, flag_bytes + r * slot, st), "pp_xchg_push")
+                _lib.check(lib.pp_xchg_push(_lib.ptr(pays[r]), pslot, peers_host, world, pay_off + r * pslot, st), "pp_xchg_push")
                 _lib.check(lib.pp_xchg_signal(_lib.ptr(peers_dev), par * world * 4, r, world, epoch, st), "pp_xchg_signal")
             for r in range(world):
                 _lib.check(lib.pp_xchg_wait(bufs[r], par * world * 4, world, epoch, streams[r].cuda_stream), "pp_xchg_wait")
+            # what a consumer ordered after the wait on the rank's stream sees (no device-wide synchronisation first)
+            seen = []
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    got = torch.as_tensor(_DeviceView(bufs[r] + flag_bytes, (world, n)), device=DEV).clone()
+                    gpay = torch.as_tensor(_DeviceView(bufs[r] + pay_off, (world, npay)), device=DEV).clone()
+                seen.append((got, gpay))
             torch.cuda.synchronize()
             _lib.check_device_faults()
-            from picopose_b200.sharded import _DeviceView
-            for r in range(world):
-                got = torch.as_tensor(_DeviceView(bufs[r] + flag_bytes, (world, n)), device=DEV)
+            for got, gpay in seen:
                 assert got[0].eq(10 * epoch + 0).all() and got[1].eq(10 * epoch + 1).all()
+                assert torch.equal(gpay, torch.stack(pays))
+        if form == "push_signal":                        # argument checks of the one-call form
+            st = streams[0].cuda_stream
+            assert lib.pp_xchg_push_signal(_lib.ptr(slices[0]), slot, flag_bytes, _lib.ptr(pays[0]), 24, pay_off, peers_host,
+                                           _lib.ptr(peers_dev), 0, 0, world, 5, st) != 0          # payload not 16-byte sized
+            assert lib.pp_xchg_push_signal(_lib.ptr(slices[0]), slot, flag_bytes, _lib.ptr(pays[0]), pslot, pay_off, peers_host,
+                                           _lib.ptr(peers_dev), 0, 0, world, 0, st) != 0          # epoch 0 is reserved
     finally:
         torch.cuda.synchronize()
         for b in bufs:

@@ -50,7 +50,12 @@ def _worker(rank, world, port, ret):
         mask = synth.disc_mask(world)
         matcher = ShardedMatcher(12)
         lo, hi = matcher.lo, matcher.hi
-        for step in range(3):
+        tar0, mask0 = tar, mask
+        for step in range(4):
+            # new data every step (a stale slot of the other parity or of two steps ago would show): the features are
+            # rescaled (cosine scores do not move), the mask of the odd steps is the full patch grid
+            tar = tar0 * float(step + 1)
+            mask = mask0 if step % 2 == 0 else torch.ones_like(mask0)
             t_all, m_all = matcher.gather_queries(tar[rank:rank + 1].to(dev), mask[rank:rank + 1].to(dev))
             ok = ok and matcher.uses_peer_memory
             s, i = matcher.match(src[:, lo:hi].contiguous().to(dev), t_all, m_all, topk=4,
@@ -59,7 +64,7 @@ def _worker(rank, world, port, ret):
             ok = ok and torch.equal(t_all.cpu(), tar) and torch.equal(m_all.cpu(), mask)
             s1, i1 = M.matching_templates(src.to(dev), tar.to(dev), None, mask.to(dev), topk=4)     # unsharded, same GPU
             ok = ok and torch.equal(i.cpu(), i1.cpu()) and torch.equal(s.cpu(), s1.cpu())
-            ok = ok and i.cpu().tolist() == planted[:, :4].tolist()
+            ok = ok and (step % 2 == 1 or i.cpu().tolist() == planted[:, :4].tolist())
         # the one-step-ahead contract is enforced on the host
         g = matcher._gather
         g.gather(tar[rank:rank + 1].to(dev), mask[rank:rank + 1].to(dev))
