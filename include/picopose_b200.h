@@ -207,11 +207,11 @@ PP_API int pp_xchg_destroy(void* buf);
  * pp_xchg_wait spins on the `world` flags of the own buffer; all three are stream-ordered. */
 PP_API int pp_xchg_push(const void* src, size_t bytes, const void* const* peers_host, int world, size_t dst_offset,
                  void* stream);
-/* One call for the push side of a gather: `bytes` from `src` to offset `dst_offset` of every peer's buffer with the copy
- * engines (on `stream`; PICOPOSE_B200_PUSH_STREAMS = n > 1 deals them over n internal streams that are joined back
- * into `stream`, which pays only while the copy engines are contended); then one kernel that stores the small `payload` (16-byte
- * multiples, e.g. the query masks) at `payload_offset` of every peer's buffer through the peer mapping and raises flag
- * [rank] = `epoch` on every peer, as pp_xchg_signal does.  pp_xchg_wait is the receiving side. */
+/* One call for the push side of a gather: `bytes` from `src` to offset `dst_offset` and the small `payload` (e.g. the
+ * query masks) to `payload_offset` of every peer's buffer with the copy engines (on `stream`; PICOPOSE_B200_PUSH_STREAMS
+ * = n > 1 deals the bulk copies over n internal streams that are joined back into `stream`, which pays only while the
+ * copy engines are contended), then flag [rank] = `epoch` on every peer as pp_xchg_signal does.  pp_xchg_wait is the
+ * receiving side. */
 PP_API int pp_xchg_push_signal(const void* src, size_t bytes, size_t dst_offset, const void* payload, size_t payload_bytes,
                         size_t payload_offset, const void* const* peers_host, const void* const* peers_dev,
                         size_t flag_offset, int rank, int world, uint32_t epoch, void* stream);

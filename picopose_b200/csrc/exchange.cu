@@ -189,24 +189,6 @@ __global__ void xchg_signal_kernel(char* const* __restrict__ peers, size_t flag_
         *flag = epoch;
     }
 }
-// The same flag write with a small payload in front of it (the query masks of a gather, a few KB): the block stores the
-// payload into every peer's buffer with plain 16-byte stores through the peer mapping, fences, and only then raises the
-// flags -- world fewer copy-engine transfers on the chain a gather has to finish within one step.
-__global__ void __launch_bounds__(256)
-xchg_signal_payload_kernel(char* const* __restrict__ peers, size_t flag_off, int rank, int world, unsigned epoch,
-                           const uint4* __restrict__ src, unsigned n16, size_t dst_off) {
-    for (int p = 0; p < world; ++p) {
-        uint4* dst = reinterpret_cast<uint4*>(peers[p] + dst_off);
-        for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < world) {
-        __threadfence_system();
-        volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(peers[threadIdx.x] + flag_off) + rank;
-        *flag = epoch;
-    }
-}
 __global__ void xchg_wait_kernel(const char* __restrict__ own, size_t flag_off, int world, unsigned epoch,
                                  unsigned long long timeout_ns, int* __restrict__ fault) {
     if ((int)threadIdx.x < world) {
@@ -285,9 +267,7 @@ extern "C" int pp_xchg_push_signal(const void* src, size_t bytes, size_t dst_off
     using namespace pp;
     PP_CHECK_ARG(src && peers_host && peers_dev && world > 0 && world <= 256 && rank >= 0 && rank < world && epoch != 0,
                  "pp_xchg_push_signal: bad arguments");
-    PP_CHECK_ARG(payload_bytes == 0 || (payload && payload_bytes % 16 == 0 && payload_offset % 16 == 0 &&
-                                        reinterpret_cast<uintptr_t>(payload) % 16 == 0 && payload_bytes <= (size_t)1 << 24),
-                 "pp_xchg_push_signal: the payload must be 16-byte aligned and at most 16 MB");
+    PP_CHECK_ARG(payload_bytes == 0 || payload, "pp_xchg_push_signal: null payload");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     PushLanes* lanes = push_lanes_wanted() > 1 && world > 1 ? push_lanes() : nullptr;
     if (lanes) {
@@ -308,18 +288,21 @@ extern "C" int pp_xchg_push_signal(const void* src, size_t bytes, size_t dst_off
     } else {
         if (int rc = pp_xchg_push(src, bytes, peers_host, world, dst_offset, stream)) return rc;
     }
-    xchg_signal_payload_kernel<<<1, 256, 0, st>>>(reinterpret_cast<char* const*>(const_cast<void* const*>(peers_dev)),
-                                                  flag_offset, rank, world, epoch, static_cast<const uint4*>(payload),
-                                                  (unsigned)(payload_bytes / 16), payload_offset);
-    PP_LAUNCHED();
-    return PP_OK;
+    // The payload (the query masks, a few KB) takes the copy engines as well.  Storing it from the flag kernel instead
+    // (world copies fewer; 115 -> 86 us for the 8-rank chain on an idle GPU) was built and measured inside the real loop:
+    // bench.py --gpus 2 end to end 5363 / 5145 det/s with copies against 3998 / 4036 with kernel stores, same box,
+    // alternating (profiles/r2i_push_chain.md).  The cause was not isolated; the suspect is the system-scope fence behind
+    // peer stores on an SM whose memory pipes the contraction keeps full.
+    if (payload_bytes)
+        if (int rc = pp_xchg_push(payload, payload_bytes, peers_host, world, payload_offset, stream)) return rc;
+    return pp_xchg_signal(peers_dev, flag_offset, rank, world, epoch, stream);
 }
 
 extern "C" int pp_xchg_signal(const void* const* peers_dev, size_t flag_offset, int rank, int world, uint32_t epoch,
                               void* stream) {
     using namespace pp;
     PP_CHECK_ARG(peers_dev && world > 0 && world <= 256 && rank >= 0 && rank < world && epoch != 0, "pp_xchg_signal: bad arguments");
-    xchg_signal_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    xchg_signal_kernel<<<1, 32 * ((world + 31) / 32), 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<char* const*>(const_cast<void* const*>(peers_dev)), flag_offset, rank, world, epoch);
     PP_LAUNCHED();
     return PP_OK;
@@ -330,7 +313,7 @@ extern "C" int pp_xchg_wait(const void* own_buf, size_t flag_offset, int world, 
     PP_CHECK_ARG(own_buf && world > 0 && world <= 256 && epoch != 0, "pp_xchg_wait: bad arguments");
     int* fault = nullptr;
     if (int rc = fault_buffer(&fault)) return rc;
-    xchg_wait_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const char*>(own_buf), flag_offset, world, epoch,
+    xchg_wait_kernel<<<1, 32 * ((world + 31) / 32), 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const char*>(own_buf), flag_offset, world, epoch,
                                                                        xchg_timeout_ns(), fault);
     PP_LAUNCHED();
     return PP_OK;

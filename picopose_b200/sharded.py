@@ -207,9 +207,8 @@ class PeerGather:
 
     An NCCL all-gather needs SMs, and the contraction kernel holds all of them, so a gather issued for step i+1 while
     step i computes only runs in the gaps between kernels.  Here rank r copies its slice into slot r of every peer's
-    buffer with `cudaMemcpyAsync` peer copies (no SM), a one-block kernel then stores the few KB of masks into every peer's
-    buffer and writes the call's epoch into flag [r] of every peer, and a one-block kernel spins on the `world` flags of
-    the own buffer; all ordered on the caller's stream.
+    buffer with `cudaMemcpyAsync` peer copies (no SM), a one-block kernel then writes the call's epoch into flag [r]
+    of every peer, and a one-block kernel spins on the `world` flags of the own buffer; all on the caller's stream.
     Slots are double-buffered by epoch parity.  Contract: (1) a `gather` may run at most one step ahead of the compute it
     feeds -- the stream it is issued on must be ordered after the `match` (top-k exchange) that consumed the gather before
     the previous one, as any double-buffered upload loop is; that exchange proves every peer has passed the query
@@ -217,8 +216,6 @@ class PeerGather:
     step's `match` may read them: a faster peer is free to overwrite that parity as soon as the exchange of the same
     step has completed.  Pass `out=` to `ShardedMatcher.gather_queries` for a private copy.
     """
-
-    PAYLOAD_MAX = 256 << 10     # masks up to this size ride in the flag kernel; larger ones take the copy engines
 
     def __init__(self, tar_slice_shape, mask_slice_shape, group=None, device=None):
         import ctypes as C
@@ -237,6 +234,8 @@ class PeerGather:
         self._own, ptrs, self._opened = _open_peers(lib, group, nbytes, self.device)
         self._peers_host = (C.c_void_p * self.world)(*ptrs)
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        import os
+        self._fused = os.environ.get("PICOPOSE_B200_FUSED_GATHER", "1") != "0"   # 0: separate push / push / signal calls
         self.epoch = 0
         self.consumed = 0      # gathers whose batch has been handed to a `match` (ShardedMatcher keeps it up to date)
         self._issued = 0
@@ -276,9 +275,8 @@ class PeerGather:
         t_off, m_off = self._offsets(par)
         st = _lib.stream_of(tar_local)
         with torch.cuda.device(self.device):
-            if self.mask_bytes <= self.PAYLOAD_MAX:
-                # features: copy engines; masks (a few KB): stored by the kernel that raises the flags -- `world` copies
-                # and two library calls less per gather than the form below (8-rank push chain 115 -> 86 us)
+            if self._fused:
+                # one library call for both pushes and the flag kernel (host time per gather 39 -> 22-30 us at 8 ranks)
                 _lib.check(lib.pp_xchg_push_signal(_lib.ptr(tar_local), self.tar_bytes, t_off + self.rank * self.tar_bytes,
                                                    _lib.ptr(mask_local), self.mask_bytes, m_off + self.rank * self.mask_bytes,
                                                    self._peers_host, _lib.ptr(self.peers), par * self.world * 4, self.rank,

@@ -1076,8 +1076,8 @@ def test_topk_exchange_three_ranks_on_one_gpu():
 
 @pytest.mark.parametrize("form", ["push+signal", "push_signal"])
 def test_peer_gather_primitives_two_ranks_on_one_gpu(form):
-    """pp_xchg_push / pp_xchg_signal / pp_xchg_wait, and the one-call form pp_xchg_push_signal (copies dealt over the
-    library's push streams, a small payload stored by the flag kernel), with two 'ranks' on one GPU (two buffers, two
+    """pp_xchg_push / pp_xchg_signal / pp_xchg_wait, and the one-call form pp_xchg_push_signal (both pushes and the flag
+    kernel behind one library call), with two 'ranks' on one GPU (two buffers, two
     streams): every rank copies its slice into slot [rank] of both buffers (and its payload into payload slot [rank]),
     flags it, and waits for both flags of its own buffer; afterwards both buffers hold both slices and both payloads.
     Three epochs, flags at different offsets (the two parities), the first parity reused."""
@@ -1128,8 +1128,8 @@ def test_peer_gather_primitives_two_ranks_on_one_gpu(form):
                 assert torch.equal(gpay, torch.stack(pays))
         if form == "push_signal":                        # argument checks of the one-call form
             st = streams[0].cuda_stream
-            assert lib.pp_xchg_push_signal(_lib.ptr(slices[0]), slot, flag_bytes, _lib.ptr(pays[0]), 24, pay_off, peers_host,
-                                           _lib.ptr(peers_dev), 0, 0, world, 5, st) != 0          # payload not 16-byte sized
+            assert lib.pp_xchg_push_signal(_lib.ptr(slices[0]), slot, flag_bytes, None, 16, pay_off, peers_host,
+                                           _lib.ptr(peers_dev), 0, 0, world, 5, st) != 0          # payload size without payload
             assert lib.pp_xchg_push_signal(_lib.ptr(slices[0]), slot, flag_bytes, _lib.ptr(pays[0]), pslot, pay_off, peers_host,
                                            _lib.ptr(peers_dev), 0, 0, world, 0, st) != 0          # epoch 0 is reserved
     finally:

@@ -2,9 +2,10 @@
 
 One process, two devices: the sender's own buffer on cuda:0 and seven "peer" buffers on cuda:1, so the chain is what rank
 r of `bench.py --gpus 8` issues per step -- 8 x 4 MB feature slices + 8 x 4 KB masks + the flag kernel -- timed with CUDA
-events on the issuing stream.  Forms: `separate` = pp_xchg_push x 2 + pp_xchg_signal (16 copies in stream order, round
-1 ... r2h), `fused` = pp_xchg_push_signal (8 copies, on PICOPOSE_B200_PUSH_STREAMS internal streams if that is > 1, masks
-stored by the flag kernel).  The stream count is read once per process: run it once per value.
+events on the issuing stream.  Forms: `separate` = pp_xchg_push x 2 + pp_xchg_signal, `fused` = pp_xchg_push_signal
+(the same copies and flag kernel behind one library call; the bulk copies on PICOPOSE_B200_PUSH_STREAMS internal streams
+if that is > 1).  profiles/r2i_push_chain.md was taken with an earlier `fused` whose flag kernel stored the masks itself.
+The stream count is read once per process: run it once per value.
     for n in 1 2 4 8; do PICOPOSE_B200_PUSH_STREAMS=$n python tools/microbench/push_chain.py; done
 With --load a 1 GB device copy runs on cuda:0 beside every chain (HBM and copy engines busy; the real step's bank
 prologue is an SM kernel, so this is the pessimistic case).  Results: profiles/r2i_push_chain.md."""
