@@ -14,6 +14,7 @@ couples views, hence one exchange.  Two forms of it:
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -234,7 +235,6 @@ class PeerGather:
         self._own, ptrs, self._opened = _open_peers(lib, group, nbytes, self.device)
         self._peers_host = (C.c_void_p * self.world)(*ptrs)
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
-        import os
         self._fused = os.environ.get("PICOPOSE_B200_FUSED_GATHER", "1") != "0"   # 0: separate push / push / signal calls
         self.epoch = 0
         self.consumed = 0      # gathers whose batch has been handed to a `match` (ShardedMatcher keeps it up to date)
@@ -318,7 +318,6 @@ class ShardedMatcher:
         self.bank = None
         # top-k exchange through NVLink peer memory unless a custom merge was injected or it is switched off
         if peer_exchange is None:
-            import os
             peer_exchange = merge is None and os.environ.get("PICOPOSE_B200_PEER_EXCHANGE", "1") != "0"
         self._want_peer = bool(peer_exchange) and self.world > 1
         self._xchg = None
