@@ -1002,6 +1002,55 @@ def test_matching_templates_dense_call_paths(monkeypatch):
     _lib.check_device_faults()
 
 
+def test_step_is_cuda_graph_capturable():
+    """After its first use no library call allocates, synchronises or goes through the host: a whole step (dense
+    matching_templates with its forked prologue stream, a resident-bank call, the stage-2 volume, pyramid + lookup in
+    every form, the warp) is captured into a CUDA graph, replayed on NEW input values written into the captured buffers,
+    and gives what the eager calls give (tools/bench_graph.py times the configs[1] step this way)."""
+    from picopose_b200 import matching as M
+    from picopose_b200.corr_lookup import CorrLookup, bilinear_sample
+    from picopose_b200.correlation import CorrelationPyramid
+    src, tar, planted = synth.planted_match_inputs(2, 7, 64, 16, seed=21)
+    mask = synth.disc_mask(2)
+    src_d, tar_d, mask_d = src.to(DEV), tar.to(DEV), mask.to(DEV)
+    bank = M.TemplateBank.from_features(src_d)
+    pyr, flow = synth.lookup_inputs(2, 16, 2, seed=22, flow_sigma=2.0)
+    pyr_d, flow_d = [p.to(DEV) for p in pyr], flow.to(DEV)
+    g = torch.Generator().manual_seed(23)
+    f1, f2 = torch.randn(2, 32, 16, 16, generator=g).to(DEV), torch.randn(2, 32, 16, 16, generator=g).to(DEV)
+    look = CorrLookup(radius=2)
+    both = torch.arange(2, dtype=torch.int32, device=DEV)
+    view0 = src_d[:, 0].contiguous()
+
+    def step():
+        s, i = M.matching_templates(src_d, tar_d, None, mask_d, topk=3)
+        s2, i2 = M.matching_templates(bank, tar_d, None, mask_d, topk=3, bank_index=both)
+        vol = M.matching_features_similarity(view0, tar_d, mask_d, mask_d)
+        return [s, i, s2, i2, vol, look(pyr_d, flow_d), look(CorrelationPyramid(num_levels=2)(f1, f2), flow_d),
+                bilinear_sample(f1, flow_d + 8.0, "bilinear", "zeros", True)]
+
+    side = torch.cuda.Stream(device=DEV)
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()                                   # first use: one-time allocations, attribute settings
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        captured = step()
+    # new values in the captured input buffers: the replay must compute on them, not on what was there at capture time
+    tar_d.copy_(torch.roll(tar_d, 1, 0))
+    flow_d.mul_(-0.5)
+    f1.copy_(f1.flip(0))
+    graph.replay()
+    torch.cuda.synchronize()
+    _lib.check_device_faults()
+    eager = step()
+    torch.cuda.synchronize()
+    for a, b in zip(captured, eager):
+        assert torch.equal(a, b)
+    assert torch.equal(captured[0], captured[2]) and torch.equal(captured[1], captured[3])   # dense call == resident bank
+
+
 def test_topk_exchange_chunks_batches_beyond_one_wave():
     """A block of the exchange kernel spins until its peers' blocks of the same detection have run, so a launch must not
     exceed the blocks the device holds at once: pp_topk_exchange cuts larger batches into launches that fit (one rank
