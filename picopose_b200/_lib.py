@@ -11,7 +11,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpicopose_b200.so")
+# PICOPOSE_B200_LIB names another build of the same library (A/B runs of two builds in one process tree)
+LIB_PATH = os.environ.get("PICOPOSE_B200_LIB") or os.path.join(HERE, "lib", "libpicopose_b200.so")
 
 MODE_BF16, MODE_FP32, MODE_BF16X3 = 0, 1, 2
 MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "bf16x3": MODE_BF16X3}
